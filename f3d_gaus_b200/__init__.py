@@ -1,0 +1,24 @@
+"""f3d_gaus_b200 -- B200-native (sm_100a) GOF Gaussian rasterizer + render loop for F3D-Gaus.
+
+Layout (only what the hot path needs):
+  csrc/                    hand-written CUDA kernels + the extern "C" ABI (include/gof_b200.h)
+  _lib.py                  ctypes loader of libgof_b200.so (fails loudly if it is missing)
+  diff_gof_rasterization/  drop-in for the reference's rasterizer package
+  gaussian_renderer/       drop-in for src/gaussian_renderer (render_predicted_more_v2_gof, render)
+  cycle.py                 the cycle-aggregative render loop of visualize.py:281-340
+  sharding.py              scene-sharded multi-GPU runner (one process per GPU, NCCL gather)
+"""
+from __future__ import annotations
+
+import sys
+
+__version__ = "0.1.0"
+
+
+def install_drop_in() -> None:
+    """Register this package's modules under the reference's import names, so that
+    `from diff_gof_rasterization import GaussianRasterizationSettings_GOF, GaussianRasterizer_GOF`
+    (src/gaussian_renderer/__init__.py:10) resolves to the B200 implementation."""
+    from . import diff_gof_rasterization as _dgr
+
+    sys.modules["diff_gof_rasterization"] = _dgr

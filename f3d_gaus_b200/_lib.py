@@ -1,0 +1,97 @@
+"""ctypes binding of libgof_b200.so (include/gof_b200.h).
+
+The CUDA library is the product: there is NO fallback.  If it is missing or cannot be loaded
+this module raises at import time.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgof_b200.so")
+
+GOF_OK = 0
+GOF_EINVAL, GOF_ECUDA, GOF_ENOMEM, GOF_EOVERFLOW = -1, -2, -3, -4
+OUTPUT_CHANNELS = 9
+
+
+class GofParams(Structure):
+    _fields_ = [
+        ("P", c_int32), ("D", c_int32), ("M", c_int32), ("W", c_int32), ("H", c_int32),
+        ("tan_fovx", c_float), ("tan_fovy", c_float), ("kernel_size", c_float), ("scale_modifier", c_float),
+        ("prefiltered", c_int32), ("debug", c_int32),
+    ]
+
+
+class GofInputs(Structure):
+    _fields_ = [(n, c_void_p) for n in (
+        "background", "means3D", "shs", "colors_precomp", "opacities", "scales", "rotations",
+        "cov3D_precomp", "view2gaussian_precomp", "viewmatrix", "projmatrix", "campos")]
+
+
+class GofGrads(Structure):
+    _fields_ = [(n, c_void_p) for n in (
+        "dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh",
+        "dL_dscales", "dL_drotations", "dL_dview2gaussian")]
+
+
+ALLOC_FN = ctypes.CFUNCTYPE(c_void_p, c_void_p, c_size_t)
+
+# name -> (restype, argtypes); every symbol include/gof_b200.h declares
+SIGNATURES = {
+    "gof_last_error": (c_char_p, []),
+    "gof_version": (c_char_p, []),
+    "gof_context_create": (c_int32, [c_int32, POINTER(c_void_p)]),
+    "gof_context_destroy": (None, [c_void_p]),
+    "gof_state_sizes": (c_int32, [c_int32, c_int32, c_int32, c_int64, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t)]),
+    "gof_forward": (c_int32, [c_void_p, POINTER(GofParams), POINTER(GofInputs), c_void_p, c_size_t, c_void_p, c_size_t,
+                              c_void_p, c_size_t, ALLOC_FN, c_void_p, c_void_p, c_void_p,
+                              POINTER(c_int32), POINTER(c_void_p), c_void_p]),
+    "gof_num_rendered": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, POINTER(c_int32)]),
+    "gof_backward": (c_int32, [c_void_p, POINTER(GofParams), POINTER(GofInputs), c_int32, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_void_p, POINTER(GofGrads), c_void_p]),
+    "gof_mark_visible": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gof_render_epilogue": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    "gof_state_get": (c_int64, [c_char_p, c_int32, c_int32, c_int32, c_int64, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_int64, c_void_p]),
+}
+
+
+def load(path: str = LIB_PATH) -> ctypes.CDLL:
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} not found: the sm_100a CUDA library is required (no fallback exists). "
+            "Build it with `python -m f3d_gaus_b200.build` or `__graft_entry__.build()`.")
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = load()
+
+
+def last_error() -> str:
+    msg = lib.gof_last_error()
+    return msg.decode() if msg else ""
+
+
+def check(rc: int, what: str) -> None:
+    if rc != GOF_OK:
+        raise RuntimeError(f"{what} failed ({rc}): {last_error()}")
+
+
+_contexts: dict[int, c_void_p] = {}
+
+
+def context(device_index: int) -> c_void_p:
+    ctx = _contexts.get(device_index)
+    if ctx is None:
+        out = c_void_p()
+        check(lib.gof_context_create(device_index, ctypes.byref(out)), "gof_context_create")
+        ctx = _contexts[device_index] = out
+    return ctx

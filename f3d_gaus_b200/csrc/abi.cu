@@ -1,0 +1,364 @@
+// abi.cu -- the extern "C" boundary of libgof_b200.so (see include/gof_b200.h) and the
+// stage orchestration that replaces CudaRasterizer::Rasterizer::forward/backward
+// (RAST/cuda_rasterizer/rasterizer_impl.cu:247-526).
+#include "gof_common.cuh"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+namespace gof {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+}
+
+}  // namespace gof
+
+struct GofContext {
+	int device = 0;
+	int32_t* pinned = nullptr;      // host mailbox for num_rendered (callback mode)
+	float* gacc = nullptr;          // backward gradient accumulator, grown on demand
+	size_t gacc_floats = 0;
+};
+
+using namespace gof;
+
+#define GOF_STAGE_CHECK(prm, s)                                   \
+	do {                                                          \
+		if ((prm)->debug) {                                       \
+			GOF_CUDA_CHECK(cudaStreamSynchronize(s));             \
+			GOF_CUDA_CHECK(cudaGetLastError());                   \
+		}                                                         \
+	} while (0)
+
+extern "C" {
+
+const char* gof_last_error(void) { return g_err; }
+const char* gof_version(void) { return "gof_b200 0.1 (sm_100a)"; }
+
+int gof_context_create(int device, GofContext** out)
+{
+	if (!out) { set_error("gof_context_create: out is NULL"); return GOF_EINVAL; }
+	GOF_CUDA_CHECK(cudaSetDevice(device));
+	GofContext* c = new GofContext();
+	c->device = device;
+	cudaError_t e = cudaMallocHost(&c->pinned, 64);
+	if (e != cudaSuccess) { delete c; set_error("cudaMallocHost failed: %s", cudaGetErrorString(e)); return GOF_ECUDA; }
+	*out = c;
+	return GOF_OK;
+}
+
+void gof_context_destroy(GofContext* c)
+{
+	if (!c) return;
+	if (c->pinned) cudaFreeHost(c->pinned);
+	if (c->gacc) cudaFree(c->gacc);
+	delete c;
+}
+
+int gof_state_sizes(int32_t P, int32_t W, int32_t H, int64_t num_rendered,
+                    size_t* geom_bytes, size_t* img_bytes, size_t* binning_bytes)
+{
+	if (P < 0 || W <= 0 || H <= 0 || num_rendered < 0) { set_error("gof_state_sizes: bad sizes"); return GOF_EINVAL; }
+	const size_t T = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
+	if (geom_bytes) *geom_bytes = GeomState::carve(nullptr, (size_t)P).total;
+	if (img_bytes) *img_bytes = ImgState::carve(nullptr, (size_t)W * H, T).total;
+	if (binning_bytes) *binning_bytes = BinState::carve(nullptr, (size_t)num_rendered).total;
+	return GOF_OK;
+}
+
+static char* align_base(void* p) { return reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(p))); }
+
+// Device-side hand-off of R for the sync-free mode: mailbox[0] = R, mailbox[1] = overflow.
+__global__ void publish_num_rendered(const uint32_t* point_offsets, int P, int64_t capacity, int32_t* mailbox)
+{
+	const uint32_t R = point_offsets[P - 1];
+	mailbox[0] = (int32_t)R;
+	mailbox[1] = ((int64_t)R > capacity) ? 1 : 0;
+}
+
+int gof_forward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
+                void* geom, size_t geom_bytes, void* img, size_t img_bytes,
+                void* binning, size_t binning_bytes, GofAllocFn alloc, void* alloc_user,
+                float* out_color, int32_t* radii,
+                int32_t* num_rendered, void** binning_out, gof_stream_t stream)
+{
+	if (!ctx || !prm || !in) { set_error("gof_forward: NULL argument"); return GOF_EINVAL; }
+	cudaStream_t s = (cudaStream_t)stream;
+	const int P = prm->P, W = prm->W, H = prm->H;
+	if (W <= 0 || H <= 0 || P < 0) { set_error("gof_forward: bad sizes P=%d W=%d H=%d", P, W, H); return GOF_EINVAL; }
+	if (!out_color) { set_error("gof_forward: out_color is NULL"); return GOF_EINVAL; }
+	if (num_rendered) *num_rendered = 0;
+	if (binning_out) *binning_out = binning;
+	const size_t N = (size_t)W * H;
+	if (P == 0) {   // rasterize_points.cu:85: nothing is launched, outputs stay zero
+		GOF_CUDA_CHECK(cudaMemsetAsync(out_color, 0, N * OUT_CH * sizeof(float), s));
+		return GOF_OK;
+	}
+	if (!in->means3D || !in->opacities || !in->viewmatrix || !in->projmatrix || !in->campos || !in->background || !radii) {
+		set_error("gof_forward: a required input pointer is NULL");
+		return GOF_EINVAL;
+	}
+	if ((in->shs == nullptr) == (in->colors_precomp == nullptr)) {
+		set_error("gof_forward: provide exactly one of shs / colors_precomp");
+		return GOF_EINVAL;
+	}
+	if (((in->scales == nullptr) || (in->rotations == nullptr)) == (in->cov3D_precomp == nullptr)) {
+		set_error("gof_forward: provide exactly one of (scales, rotations) / cov3D_precomp");
+		return GOF_EINVAL;
+	}
+	if (in->cov3D_precomp && !in->view2gaussian_precomp) {
+		set_error("gof_forward: cov3D_precomp needs view2gaussian_precomp (no scales/rotations to build the quadric)");
+		return GOF_EINVAL;
+	}
+	if (in->shs && prm->M < (prm->D + 1) * (prm->D + 1)) {
+		set_error("gof_forward: sh has %d coefficients, degree %d needs %d", prm->M, prm->D, (prm->D + 1) * (prm->D + 1));
+		return GOF_EINVAL;
+	}
+
+	const dim3 tile_grid((W + TILE_X - 1) / TILE_X, (H + TILE_Y - 1) / TILE_Y, 1);
+	const size_t T = (size_t)tile_grid.x * tile_grid.y;
+	const float focal_y = H / (2.0f * prm->tan_fovy);
+	const float focal_x = W / (2.0f * prm->tan_fovx);
+
+	GeomState g = GeomState::carve(align_base(geom), (size_t)P);
+	ImgState im = ImgState::carve(align_base(img), N, T);
+	if (!geom || g.total > geom_bytes) { set_error("gof_forward: geom blob too small (%zu < %zu)", geom_bytes, g.total); return GOF_ENOMEM; }
+	if (!img || im.total > img_bytes) { set_error("gof_forward: img blob too small (%zu < %zu)", img_bytes, im.total); return GOF_ENOMEM; }
+
+	int rc;
+	if ((rc = launch_preprocess(*prm, *in, focal_x, focal_y, tile_grid, g, radii, s)) != GOF_OK) return rc;
+	GOF_STAGE_CHECK(prm, s);
+	if ((rc = launch_scan(g, P, s)) != GOF_OK) return rc;
+	GOF_STAGE_CHECK(prm, s);
+
+	int R;
+	BinState b;
+	if (binning != nullptr) {
+		// sync-free mode: capacity is whatever fits in the caller's blob
+		int64_t lo = 0, hi = (int64_t)1 << 31;
+		while (lo + 1 < hi) {   // largest R whose layout fits (host arithmetic only)
+			const int64_t mid = (lo + hi) / 2;
+			if (BinState::carve(nullptr, (size_t)mid).total <= binning_bytes) lo = mid; else hi = mid;
+		}
+		R = (int)lo;
+		publish_num_rendered<<<1, 1, 0, s>>>(g.point_offsets, P, lo, g.mailbox);
+		GOF_CUDA_CHECK(cudaGetLastError());
+		set_error("gof_forward: sync-free binning is not available in this build");
+		return GOF_EINVAL;
+	} else {
+		if (!alloc) { set_error("gof_forward: neither a binning blob nor an allocation callback"); return GOF_EINVAL; }
+		GOF_CUDA_CHECK(cudaMemcpyAsync(ctx->pinned, g.point_offsets + P - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+		GOF_CUDA_CHECK(cudaStreamSynchronize(s));
+		R = ctx->pinned[0];
+		const size_t need = BinState::carve(nullptr, (size_t)R).total;
+		void* blob = alloc(alloc_user, need);
+		if (!blob) { set_error("gof_forward: binning allocation callback returned NULL for %zu bytes", need); return GOF_ENOMEM; }
+		if (binning_out) *binning_out = blob;
+		b = BinState::carve(align_base(blob), (size_t)R);
+	}
+	if (num_rendered) *num_rendered = R;
+
+	if ((rc = launch_binning(*prm, tile_grid, g, im, b, radii, R, s)) != GOF_OK) return rc;
+	GOF_STAGE_CHECK(prm, s);
+	if ((rc = launch_render_fwd(*prm, tile_grid, focal_x, focal_y, im, b, in->background, out_color, s)) != GOF_OK) return rc;
+	GOF_STAGE_CHECK(prm, s);
+	return GOF_OK;
+}
+
+int gof_num_rendered(GofContext* ctx, const void* geom, int32_t P, gof_stream_t stream, int32_t* num_rendered)
+{
+	if (!ctx || !geom || !num_rendered || P <= 0) { set_error("gof_num_rendered: bad argument"); return GOF_EINVAL; }
+	cudaStream_t s = (cudaStream_t)stream;
+	GeomState g = GeomState::carve(align_base(const_cast<void*>(geom)), (size_t)P);
+	GOF_CUDA_CHECK(cudaMemcpyAsync(ctx->pinned, g.mailbox, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+	GOF_CUDA_CHECK(cudaStreamSynchronize(s));
+	*num_rendered = ctx->pinned[0];
+	if (ctx->pinned[1]) { set_error("num_rendered=%d exceeded the binning capacity", ctx->pinned[0]); return GOF_EOVERFLOW; }
+	return GOF_OK;
+}
+
+int gof_backward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
+                 int32_t num_rendered, const int32_t* radii,
+                 const void* geom, const void* binning, const void* img,
+                 const float* dL_dout_color, const GofGrads* gr, gof_stream_t stream)
+{
+	if (!ctx || !prm || !in || !gr) { set_error("gof_backward: NULL argument"); return GOF_EINVAL; }
+	cudaStream_t s = (cudaStream_t)stream;
+	const int P = prm->P, W = prm->W, H = prm->H;
+	if (P == 0) return GOF_OK;
+	if (!geom || !img || !radii || !dL_dout_color) { set_error("gof_backward: NULL state/gradient pointer"); return GOF_EINVAL; }
+	if (!gr->dL_dmeans2D || !gr->dL_dcolors || !gr->dL_dopacity || !gr->dL_dmeans3D || !gr->dL_dcov3D ||
+	    !gr->dL_dscales || !gr->dL_drotations || !gr->dL_dview2gaussian || (prm->M > 0 && !gr->dL_dsh)) {
+		set_error("gof_backward: a gradient output pointer is NULL");
+		return GOF_EINVAL;
+	}
+	const dim3 tile_grid((W + TILE_X - 1) / TILE_X, (H + TILE_Y - 1) / TILE_Y, 1);
+	const size_t T = (size_t)tile_grid.x * tile_grid.y;
+	const float focal_y = H / (2.0f * prm->tan_fovy);
+	const float focal_x = W / (2.0f * prm->tan_fovx);
+	GeomState g = GeomState::carve(align_base(const_cast<void*>(geom)), (size_t)P);
+	ImgState im = ImgState::carve(align_base(const_cast<void*>(img)), (size_t)W * H, T);
+	BinState b{};
+	if (num_rendered > 0) {
+		if (!binning) { set_error("gof_backward: binning blob is NULL but num_rendered=%d", num_rendered); return GOF_EINVAL; }
+		b = BinState::carve(align_base(const_cast<void*>(binning)), (size_t)num_rendered);
+	}
+
+	const size_t need = (size_t)P * GACC_FLOATS;
+	if (ctx->gacc_floats < need) {
+		if (ctx->gacc) { GOF_CUDA_CHECK(cudaStreamSynchronize(s)); cudaFree(ctx->gacc); ctx->gacc = nullptr; ctx->gacc_floats = 0; }
+		GOF_CUDA_CHECK(cudaMalloc(&ctx->gacc, need * sizeof(float)));
+		ctx->gacc_floats = need;
+	}
+	GOF_CUDA_CHECK(cudaMemsetAsync(ctx->gacc, 0, need * sizeof(float), s));
+	int rc;
+	if (num_rendered > 0) {
+		if ((rc = launch_render_bwd(*prm, tile_grid, focal_x, focal_y, g, im, b, in->background, dL_dout_color, ctx->gacc, s)) != GOF_OK) return rc;
+		GOF_STAGE_CHECK(prm, s);
+	}
+	if ((rc = launch_preprocess_bwd(*prm, *in, g, radii, ctx->gacc, *gr, s)) != GOF_OK) return rc;
+	GOF_STAGE_CHECK(prm, s);
+	return GOF_OK;
+}
+
+// ---- test accessor ---------------------------------------------------------------------------
+__global__ void extract_v2g_kernel(int P, const float* rec, float* v2g, float* rgb)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= P) return;
+	if (v2g) for (int k = 0; k < 10; k++) v2g[(size_t)i * 10 + k] = rec[(size_t)i * REC_FLOATS + k];
+	if (rgb) for (int k = 0; k < 3; k++) rgb[(size_t)i * 3 + k] = rec[(size_t)i * REC_FLOATS + REC_RGB + k];
+}
+
+int64_t gof_state_get(const char* name, int32_t P, int32_t W, int32_t H, int64_t R,
+                      const void* geom, const void* binning, const void* img,
+                      void* dst, int64_t dst_bytes, gof_stream_t stream)
+{
+	if (!name) { set_error("gof_state_get: NULL name"); return GOF_EINVAL; }
+	cudaStream_t s = (cudaStream_t)stream;
+	const size_t N = (size_t)W * H;
+	const size_t T = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
+	GeomState g = GeomState::carve(align_base(const_cast<void*>(geom)), (size_t)P);
+	ImgState im = ImgState::carve(align_base(const_cast<void*>(img)), N, T);
+	BinState b = BinState::carve(align_base(const_cast<void*>(binning)), (size_t)R);
+	const std::string n(name);
+	const void* src = nullptr;
+	size_t bytes = 0;
+	if (n == "depths") { src = g.depths; bytes = (size_t)P * 4; }
+	else if (n == "means2D") { src = g.means2D; bytes = (size_t)P * 8; }
+	else if (n == "conic_opacity") { src = g.conic_opacity; bytes = (size_t)P * 16; }
+	else if (n == "clamped") { src = g.clamped; bytes = (size_t)P * 3; }
+	else if (n == "tiles_touched") { src = g.tiles_touched; bytes = (size_t)P * 4; }
+	else if (n == "point_offsets") { src = g.point_offsets; bytes = (size_t)P * 4; }
+	else if (n == "final_T") { src = im.final_T; bytes = N * 16; }
+	else if (n == "n_contrib") { src = im.n_contrib; bytes = N * 8; }
+	else if (n == "ranges") { src = im.ranges; bytes = T * 8; }
+	else if (n == "point_list") { src = b.point_list; bytes = (size_t)R * 4; }
+	else if (n == "point_list_keys") { src = b.keys; bytes = (size_t)R * 8; }
+	else if (n == "view2gaussian" || n == "rgb") {
+		bytes = (size_t)P * (n == "rgb" ? 12 : 40);
+		if (dst) {
+			if ((int64_t)bytes > dst_bytes) { set_error("gof_state_get: dst too small"); return GOF_ENOMEM; }
+			if (P > 0) {
+				extract_v2g_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, g.rec, n == "rgb" ? nullptr : (float*)dst, n == "rgb" ? (float*)dst : nullptr);
+				GOF_CUDA_CHECK(cudaGetLastError());
+			}
+		}
+		return (int64_t)bytes;
+	} else { set_error("gof_state_get: unknown array '%s'", name); return GOF_EINVAL; }
+	if (dst) {
+		if ((int64_t)bytes > dst_bytes) { set_error("gof_state_get: dst too small"); return GOF_ENOMEM; }
+		if (bytes) GOF_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
+	}
+	return (int64_t)bytes;
+}
+
+// ---- fused L2 epilogue -----------------------------------------------------------------------
+// One thread per pixel; see gof_b200.h.  c2w = inverse of the (column-vector) world->view
+// matrix A|t with A[r][c] = vm[4c+r], t[r] = vm[12+r]  (src/gaussian_renderer/__init__.py:881-909).
+__global__ void epilogue_kernel(const float* __restrict__ out_color, const float* __restrict__ vm, int W, int H,
+                                float fx, float fy, float* __restrict__ normal_world, float* __restrict__ depth_normal)
+{
+	__shared__ float s_Ai[9], s_o[3];
+	if (threadIdx.x == 0) {
+		float A[3][3];
+		for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) A[r][c] = vm[4 * c + r];
+		const float t[3] = { vm[12], vm[13], vm[14] };
+		const float c00 = A[1][1] * A[2][2] - A[1][2] * A[2][1];
+		const float c01 = A[1][2] * A[2][0] - A[1][0] * A[2][2];
+		const float c02 = A[1][0] * A[2][1] - A[1][1] * A[2][0];
+		const float det = A[0][0] * c00 + A[0][1] * c01 + A[0][2] * c02;
+		const float id = 1.0f / det;
+		float Ai[3][3];
+		Ai[0][0] = c00 * id; Ai[1][0] = c01 * id; Ai[2][0] = c02 * id;
+		Ai[0][1] = (A[0][2] * A[2][1] - A[0][1] * A[2][2]) * id;
+		Ai[1][1] = (A[0][0] * A[2][2] - A[0][2] * A[2][0]) * id;
+		Ai[2][1] = (A[0][1] * A[2][0] - A[0][0] * A[2][1]) * id;
+		Ai[0][2] = (A[0][1] * A[1][2] - A[0][2] * A[1][1]) * id;
+		Ai[1][2] = (A[0][2] * A[1][0] - A[0][0] * A[1][2]) * id;
+		Ai[2][2] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) * id;
+		for (int r = 0; r < 3; r++) {
+			for (int c = 0; c < 3; c++) s_Ai[3 * r + c] = Ai[r][c];
+			s_o[r] = -(Ai[r][0] * t[0] + Ai[r][1] * t[1] + Ai[r][2] * t[2]);
+		}
+	}
+	__syncthreads();
+	const int x = blockIdx.x * blockDim.x + threadIdx.x;
+	const int y = blockIdx.y;
+	if (x >= W || y >= H) return;
+	const size_t N = (size_t)W * H;
+	const size_t pid = (size_t)y * W + x;
+
+	if (normal_world) {
+		float n0 = out_color[3 * N + pid], n1 = out_color[4 * N + pid], n2 = out_color[5 * N + pid];
+		const float nrm = fmaxf(sqrtf(n0 * n0 + n1 * n1 + n2 * n2), 1e-12f);
+		n0 /= nrm; n1 /= nrm; n2 /= nrm;
+		normal_world[0 * N + pid] = s_Ai[0] * n0 + s_Ai[1] * n1 + s_Ai[2] * n2;
+		normal_world[1 * N + pid] = s_Ai[3] * n0 + s_Ai[4] * n1 + s_Ai[5] * n2;
+		normal_world[2 * N + pid] = s_Ai[6] * n0 + s_Ai[7] * n1 + s_Ai[8] * n2;
+	}
+	if (depth_normal) {
+		float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+		if (x >= 1 && x < W - 1 && y >= 1 && y < H - 1) {
+			auto point = [&](int px, int py, float* p) {
+				const float d = out_color[CH_DEPTH * N + (size_t)py * W + px];
+				const float cx = (px - W / 2.f) / fx, cy = (py - H / 2.f) / fy;
+				for (int r = 0; r < 3; r++) p[r] = d * (s_Ai[3 * r] * cx + s_Ai[3 * r + 1] * cy + s_Ai[3 * r + 2]) + s_o[r];
+			};
+			float pu[3], pd[3], pl[3], pr[3];
+			point(x, y + 1, pd); point(x, y - 1, pu); point(x + 1, y, pr); point(x - 1, y, pl);
+			const float dx[3] = { pd[0] - pu[0], pd[1] - pu[1], pd[2] - pu[2] };   // along image rows (y)
+			const float dy[3] = { pr[0] - pl[0], pr[1] - pl[1], pr[2] - pl[2] };   // along image columns (x)
+			const float c0 = dx[1] * dy[2] - dx[2] * dy[1];
+			const float c1 = dx[2] * dy[0] - dx[0] * dy[2];
+			const float c2 = dx[0] * dy[1] - dx[1] * dy[0];
+			const float nrm = fmaxf(sqrtf(c0 * c0 + c1 * c1 + c2 * c2), 1e-12f);
+			o0 = c0 / nrm; o1 = c1 / nrm; o2 = c2 / nrm;
+		}
+		depth_normal[0 * N + pid] = o0;
+		depth_normal[1 * N + pid] = o1;
+		depth_normal[2 * N + pid] = o2;
+	}
+}
+
+int gof_render_epilogue(const float* out_color, const float* viewmatrix, int32_t W, int32_t H,
+                        float fovx, float fovy, float* normal_world, float* depth_normal, gof_stream_t stream)
+{
+	if (!out_color || !viewmatrix || W <= 0 || H <= 0) { set_error("gof_render_epilogue: bad argument"); return GOF_EINVAL; }
+	const float fx = W / (2.f * tanf(fovx / 2.f));
+	const float fy = H / (2.f * tanf(fovy / 2.f));
+	dim3 grid((W + 127) / 128, H);
+	epilogue_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(out_color, viewmatrix, W, H, fx, fy, normal_world, depth_normal);
+	GOF_CUDA_CHECK(cudaGetLastError());
+	return GOF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,127 @@
+// blend_math.cuh -- device helpers shared by the forward and backward tile blends:
+//   * mbarrier + TMA bulk-copy (cp.async.bulk, SASS UBLKCP) primitives for the slab pipeline;
+//   * the GOF ray-minimum evaluation of one (pixel, Gaussian) pair, split into a cheap
+//     conservative float32 pre-test and the exact path.
+//
+// Arithmetic contract.  The reference evaluates, per pair (forward.cu:502-535):
+//     n  = Sigma_v * (rx, ry, 1)            float32
+//     AA = (rx, ry, 1) . n                  float32, then widened to double
+//     BB = 2 * (B . (rx, ry, 1))            float32, then widened to double
+//     t  = float(-BB / (2 AA)),  skip if t <= 0.2
+//     mv = -(BB/AA) * (BB/4) + C            double
+//     power = min(0, float(-0.5 * mv)),  alpha = min(0.99, w * expf(power)),  skip if < 1/255
+// mv is a difference of two ~(t/s)^2 ~ 6e5 terms, so one ulp of the float32 n/AA/BB moves
+// alpha by percents: those float32 values must be reproduced to the bit.  They are written
+// with explicit round-to-nearest intrinsics in the association the reference's build uses
+// (n_k = S_kz + fma(S_kx, rx, S_ky*ry) etc.; established from its sm_100a SASS), so the
+// result does not depend on this compiler's contraction choices.
+//
+// The pre-test.  alpha >= 1/255 needs  w*exp(-mv/2) >= 1/255, i.e. mv <= 2 ln(255 w) =: tau0.
+// q32 = BB^2/(4 AA) evaluated in float32 is within 1e-6 relative of the exact q (3 roundings
+// + a 2-ulp approximate divide < 4e-7), so  mv >= C - q32 (1 + 1e-6)  whenever AA > 0.  If
+// that lower bound already exceeds tau = tau0 * 1.00001 + 2e-3 (stored per record by the
+// preprocess; -FLT_MAX when w < 1/255 since power <= 0 caps alpha at w) the pair is skipped
+// by the reference too -- either by its alpha test or by its t test, both of which have no
+// side effect other than `continue`.  NaNs fail every comparison and fall through to the
+// exact path.  Roughly 9 in 10 pairs of a tile list end here after ~20 float32 operations
+// and never touch the FP64 pipe.
+#pragma once
+#include "gof_common.cuh"
+
+namespace gof {
+
+// ---------------------------------------------------------------- async-copy primitives --
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+	return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+	uint32_t ok;
+	asm volatile(
+		"{\n\t.reg .pred p;\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+		"selp.u32 %0, 1, 0, p;\n\t}"
+		: "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+	return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+	while (!mbar_try_wait(bar, parity)) {}
+}
+// TMA bulk copy global -> shared, completion signalled on `bar` (bytes % 16 == 0, 16-B aligned).
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ------------------------------------------------------------------------- pixel rays ----
+// ray = ((px + 0.5 - W/2.) / fx, (py + 0.5 - H/2.) / fy): numerator and quotient in double,
+// narrowed to float (forward.cu:440,448).
+__device__ __forceinline__ float pixel_ray(uint32_t p, int S, float focal)
+{
+	const float pf = (float)p + 0.5f;
+	return (pf - S / 2.) / focal;
+}
+
+// ------------------------------------------------------------------ pair evaluation -----
+struct PairGeom {
+	float n0, n1, n2;   // Sigma_v * ray
+	float AA, BB;       // float32 quadratic coefficients
+};
+
+__device__ __forceinline__ PairGeom pair_geom(const float4& a, const float4& b, const float4& c, float rx, float ry)
+{
+	// a = (Sxx, Sxy, Sxz, Syy)  b = (Syz, Szz, Bx, By)  c = (Bz, C, tau, w)
+	PairGeom g;
+	g.n0 = __fadd_rn(a.z, __fmaf_rn(a.x, rx, __fmul_rn(a.y, ry)));
+	g.n1 = __fadd_rn(b.x, __fmaf_rn(a.y, rx, __fmul_rn(a.w, ry)));
+	g.n2 = __fadd_rn(b.y, __fmaf_rn(b.x, ry, __fmul_rn(a.z, rx)));
+	g.AA = __fadd_rn(__fmaf_rn(g.n0, rx, __fmul_rn(g.n1, ry)), g.n2);
+	const float bb = __fadd_rn(c.x, __fmaf_rn(b.z, rx, __fmul_rn(b.w, ry)));
+	g.BB = __fadd_rn(bb, bb);
+	return g;
+}
+
+// true  => the reference skips this pair (no side effects); false => run the exact path.
+__device__ __forceinline__ bool pair_pretest_reject(const PairGeom& g, float C, float tau)
+{
+	const float q32 = __fdividef(__fmul_rn(__fmul_rn(g.BB, g.BB), 0.25f), g.AA);
+	const float lower = __fmaf_rn(-1.000001f, q32, C);
+	return (g.AA > 0.0f) && (lower > tau);
+}
+
+// Exact alpha of the pair.  Returns false if the reference `continue`s (t <= near plane or
+// alpha < 1/255).  Outputs t, alpha and G = exp(power) (the backward needs G).
+__device__ __forceinline__ bool pair_alpha_exact(const PairGeom& g, float C, float w, float& t, float& alpha, float& G)
+{
+	const double AA = g.AA;
+	const double BB = g.BB;
+	// -BB/(2AA) == (-BB/AA) * 0.5 exactly (power-of-two scaling), so one IEEE division serves
+	// both t and the BB/AA factor of the ray minimum.
+	const double u = (-BB) / AA;
+	t = (float)(u * 0.5);
+	if (t <= 0.2) return false;   // compared in double, like NEAR_PLANE (auxiliary.h:26)
+	const double mv = fma(u, BB * 0.25, (double)C);
+	float power = (float)(mv * -0.5);
+	if (power > 0.0f) power = 0.0f;
+	G = expf(power);
+	alpha = min(0.99f, __fmul_rn(w, G));
+	if (alpha < 1.0f / 255.0f) return false;
+	return true;
+}
+
+}  // namespace gof

@@ -1,0 +1,315 @@
+"""Drop-in replacement for the reference's `diff_gof_rasterization` package
+(RAST/diff_gof_rasterization/__init__.py), backed by libgof_b200.so through ctypes.
+
+Exports the reference's names -- `GaussianRasterizationSettings_GOF`, `GaussianRasterizer_GOF`
+(:168,:185), `rasterize_gaussians` (:21), the private `_C` module surface (ext.cpp:15-19) --
+plus the un-suffixed `GaussianRasterizationSettings` / `GaussianRasterizer` aliases the
+vanilla renderer signature uses.  Install it under the reference's import name with
+`f3d_gaus_b200.install_drop_in()`.
+
+No CPU path exists: tensors must live on a CUDA device and the CUDA library must load.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+
+__all__ = [
+    "GaussianRasterizationSettings_GOF", "GaussianRasterizer_GOF", "GaussianRasterizationSettings",
+    "GaussianRasterizer", "rasterize_gaussians", "NumRendered",
+]
+
+
+def _dev_ptr(t: torch.Tensor | None, device: torch.device, keep: list, dtype=torch.float32):
+    """Device pointer of `t` (made contiguous), or None for the reference's "absent" sentinel
+    (a tensor with numel()==0, RAST/diff_gof_rasterization/__init__.py:211-225)."""
+    if t is None or t.numel() == 0:
+        return None
+    if t.device != device:
+        raise RuntimeError(f"expected a tensor on {device}, got one on {t.device}")
+    if t.dtype != dtype:
+        raise RuntimeError(f"expected dtype {dtype}, got {t.dtype}")
+    t = t.contiguous()
+    keep.append(t)
+    return t.data_ptr()
+
+
+class NumRendered(int):
+    """`num_rendered` as the reference returns it (a Python int)."""
+
+
+class _CModule:
+    """The four functions of the reference's pybind module `_C` (ext.cpp:15-19)."""
+
+    # -- forward ------------------------------------------------------------------------------
+    @staticmethod
+    def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier,
+                            cov3D_precomp, view2gaussian_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
+                            kernel_size, subpixel_offset, image_height, image_width, sh, degree, campos,
+                            prefiltered, debug):
+        if means3D.dim() != 2 or means3D.size(1) != 3:
+            raise RuntimeError("means3D must have dimensions (num_points, 3)")
+        if not means3D.is_cuda:
+            raise RuntimeError("diff_gof_rasterization (B200): tensors must be on a CUDA device; there is no CPU path")
+        device = means3D.device
+        P, H, W = int(means3D.size(0)), int(image_height), int(image_width)
+        M = int(sh.size(1)) if (sh is not None and sh.numel() != 0 and sh.size(0) != 0) else 0
+        keep: list = []
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            byte_opts = dict(dtype=torch.uint8, device=device)
+            if P == 0:
+                out_color = torch.zeros((_lib.OUTPUT_CHANNELS, H, W), dtype=torch.float32, device=device)
+                radii = torch.zeros((0,), dtype=torch.int32, device=device)
+                empty = torch.empty(0, **byte_opts)
+                return NumRendered(0), out_color, radii, empty, empty.clone(), empty.clone()
+
+            out_color = torch.empty((_lib.OUTPUT_CHANNELS, H, W), dtype=torch.float32, device=device)
+            radii = torch.empty((P,), dtype=torch.int32, device=device)
+            gsz, isz, bsz = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+            _lib.check(_lib.lib.gof_state_sizes(P, W, H, 0, ctypes.byref(gsz), ctypes.byref(isz), ctypes.byref(bsz)),
+                       "gof_state_sizes")
+            geom = torch.empty(gsz.value, **byte_opts)
+            img = torch.empty(isz.value, **byte_opts)
+            holder = {}
+
+            def _alloc(_user, nbytes):
+                holder["binning"] = torch.empty(int(nbytes), **byte_opts)
+                return holder["binning"].data_ptr()
+
+            alloc_cb = _lib.ALLOC_FN(_alloc)
+            prm = _lib.GofParams(P, int(degree), M, W, H, float(tan_fovx), float(tan_fovy), float(kernel_size),
+                                 float(scale_modifier), int(bool(prefiltered)), int(bool(debug)))
+            inp = _lib.GofInputs(
+                _dev_ptr(background, device, keep), _dev_ptr(means3D, device, keep), _dev_ptr(sh, device, keep),
+                _dev_ptr(colors, device, keep), _dev_ptr(opacity, device, keep), _dev_ptr(scales, device, keep),
+                _dev_ptr(rotations, device, keep), _dev_ptr(cov3D_precomp, device, keep),
+                _dev_ptr(view2gaussian_precomp, device, keep), _dev_ptr(viewmatrix, device, keep),
+                _dev_ptr(projmatrix, device, keep), _dev_ptr(campos, device, keep))
+            R = ctypes.c_int32(0)
+            bin_out = ctypes.c_void_p()
+            rc = _lib.lib.gof_forward(_lib.context(device.index), ctypes.byref(prm), ctypes.byref(inp),
+                                      geom.data_ptr(), geom.numel(), img.data_ptr(), img.numel(),
+                                      None, 0, alloc_cb, None, out_color.data_ptr(), radii.data_ptr(),
+                                      ctypes.byref(R), ctypes.byref(bin_out), stream)
+            _lib.check(rc, "rasterize_gaussians")
+            binning = holder.get("binning")
+            if binning is None:
+                binning = torch.empty(0, **byte_opts)
+        return NumRendered(R.value), out_color, radii, geom, binning, img
+
+    # -- backward -----------------------------------------------------------------------------
+    @staticmethod
+    def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations, scale_modifier,
+                                     cov3D_precomp, view2gaussian_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
+                                     kernel_size, subpixel_offset, dL_dout_color, sh, degree, campos, geomBuffer, R,
+                                     binningBuffer, imageBuffer, debug):
+        device = means3D.device
+        P = int(means3D.size(0))
+        H, W = int(dL_dout_color.size(1)), int(dL_dout_color.size(2))
+        M = int(sh.size(1)) if (sh is not None and sh.numel() != 0 and sh.size(0) != 0) else 0
+        opts = dict(dtype=torch.float32, device=device)
+        if P == 0:
+            z = lambda *shape: torch.zeros(shape, **opts)
+            return z(0, 3), z(0, 3), z(0, 1), z(0, 3), z(0, 6), z(0, M, 3), z(0, 3), z(0, 4), z(0, 10)
+        # every element is written by the library: no zero fill needed
+        e = lambda *shape: torch.empty(shape, **opts)
+        dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D = e(P, 3), e(P, 3), e(P, 1), e(P, 3)
+        dL_dcov3D, dL_dsh, dL_dscales, dL_drotations, dL_dv2g = e(P, 6), e(P, M, 3), e(P, 3), e(P, 4), e(P, 10)
+        keep: list = []
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            prm = _lib.GofParams(P, int(degree), M, W, H, float(tan_fovx), float(tan_fovy), float(kernel_size),
+                                 float(scale_modifier), 0, int(bool(debug)))
+            inp = _lib.GofInputs(
+                _dev_ptr(background, device, keep), _dev_ptr(means3D, device, keep), _dev_ptr(sh, device, keep),
+                _dev_ptr(colors, device, keep), None, _dev_ptr(scales, device, keep),
+                _dev_ptr(rotations, device, keep), _dev_ptr(cov3D_precomp, device, keep),
+                _dev_ptr(view2gaussian_precomp, device, keep), _dev_ptr(viewmatrix, device, keep),
+                _dev_ptr(projmatrix, device, keep), _dev_ptr(campos, device, keep))
+            grads = _lib.GofGrads(dL_dmeans2D.data_ptr(), dL_dcolors.data_ptr(), dL_dopacity.data_ptr(),
+                                  dL_dmeans3D.data_ptr(), dL_dcov3D.data_ptr(),
+                                  dL_dsh.data_ptr() if M > 0 else None, dL_dscales.data_ptr(),
+                                  dL_drotations.data_ptr(), dL_dv2g.data_ptr())
+            rc = _lib.lib.gof_backward(
+                _lib.context(device.index), ctypes.byref(prm), ctypes.byref(inp), int(R),
+                _dev_ptr(radii, device, keep, torch.int32),
+                geomBuffer.data_ptr(), binningBuffer.data_ptr() if binningBuffer.numel() else None,
+                imageBuffer.data_ptr(), _dev_ptr(dL_dout_color, device, keep), ctypes.byref(grads), stream)
+            _lib.check(rc, "rasterize_gaussians_backward")
+        return (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations,
+                dL_dv2g)
+
+    # -- markVisible --------------------------------------------------------------------------
+    @staticmethod
+    def mark_visible(means3D, viewmatrix, projmatrix):
+        if not means3D.is_cuda:
+            raise RuntimeError("mark_visible: tensors must be on a CUDA device")
+        device = means3D.device
+        P = int(means3D.size(0))
+        present = torch.zeros((P,), dtype=torch.bool, device=device)
+        if P:
+            keep: list = []
+            with torch.cuda.device(device):
+                rc = _lib.lib.gof_mark_visible(P, _dev_ptr(means3D, device, keep), _dev_ptr(viewmatrix, device, keep),
+                                               _dev_ptr(projmatrix, device, keep), present.data_ptr(),
+                                               torch.cuda.current_stream(device).cuda_stream)
+            _lib.check(rc, "mark_visible")
+        return present
+
+    @staticmethod
+    def integrate_gaussians_to_points(*args, **kwargs):
+        raise NotImplementedError(
+            "integrate_gaussians_to_points (GOF mesh extraction, forward.cu:803-1218) is outside the hot path "
+            "built so far; see DESIGN.md, 'next'")
+
+
+_C = _CModule()
+
+
+def state_array(name: str, P: int, W: int, H: int, R: int, geom, binning, img):
+    """Test accessor: decode one array of the opaque forward state (gof_state_get)."""
+    device = geom.device
+    spec = {
+        "depths": (torch.float32, (P,)), "means2D": (torch.float32, (P, 2)),
+        "conic_opacity": (torch.float32, (P, 4)), "view2gaussian": (torch.float32, (P, 10)),
+        "rgb": (torch.float32, (P, 3)), "clamped": (torch.uint8, (P, 3)),
+        "tiles_touched": (torch.int32, (P,)), "point_offsets": (torch.int32, (P,)),
+        "final_T": (torch.float32, (4, H, W)), "n_contrib": (torch.int32, (2, H, W)),
+        "ranges": (torch.int32, (((W + 15) // 16) * ((H + 15) // 16), 2)),
+        "point_list": (torch.int32, (R,)), "point_list_keys": (torch.int64, (R,)),
+    }[name]
+    out = torch.empty(spec[1], dtype=spec[0], device=device)
+    with torch.cuda.device(device):
+        n = _lib.lib.gof_state_get(name.encode(), P, W, H, R, geom.data_ptr(),
+                                   binning.data_ptr() if binning.numel() else None, img.data_ptr(),
+                                   out.data_ptr() if out.numel() else None, out.numel() * out.element_size(),
+                                   torch.cuda.current_stream(device).cuda_stream)
+    if n < 0:
+        raise RuntimeError(f"gof_state_get({name}) failed: {_lib.last_error()}")
+    return out
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        view2gaussian_precomp, raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, view2gaussian_precomp, raster_settings)
+
+
+def _cpu_copy(args):
+    return tuple(a.detach().cpu().clone() if isinstance(a, torch.Tensor) else a for a in args)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    """autograd bridge (reference: RAST/diff_gof_rasterization/__init__.py:46-165)."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                view2gaussian_precomp, raster_settings):
+        rs = raster_settings
+        args = (rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
+                view2gaussian_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.kernel_size,
+                rs.subpixel_offset, rs.image_height, rs.image_width, sh, rs.sh_degree, rs.campos, rs.prefiltered,
+                rs.debug)
+        if rs.debug:
+            snapshot = _cpu_copy(args)
+            try:
+                num_rendered, color, radii, geom, binning, img = _C.rasterize_gaussians(*args)
+            except Exception:
+                torch.save(snapshot, "snapshot_fw.dump")
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                raise
+        else:
+            num_rendered, color, radii, geom, binning, img = _C.rasterize_gaussians(*args)
+        ctx.raster_settings = rs
+        ctx.num_rendered = num_rendered
+        ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, view2gaussian_precomp,
+                              radii, sh, geom, binning, img)
+        ctx.mark_non_differentiable(radii)
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _grad_radii):
+        rs = ctx.raster_settings
+        (colors_precomp, means3D, scales, rotations, cov3Ds_precomp, view2gaussian_precomp, radii, sh, geom, binning,
+         img) = ctx.saved_tensors
+        args = (rs.bg, means3D, radii, colors_precomp, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
+                view2gaussian_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.kernel_size,
+                rs.subpixel_offset, grad_out_color, sh, rs.sh_degree, rs.campos, geom, ctx.num_rendered, binning, img,
+                rs.debug)
+        if rs.debug:
+            snapshot = _cpu_copy(args)
+            try:
+                out = _C.rasterize_gaussians_backward(*args)
+            except Exception:
+                torch.save(snapshot, "snapshot_bw.dump")
+                print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+                raise
+        else:
+            out = _C.rasterize_gaussians_backward(*args)
+        (g_means2D, g_colors, g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rot, g_v2g) = out
+        # forward-argument order; the reference returns a tensor for every slot, even absent inputs
+        return (g_means3D, g_means2D, g_sh, g_colors, g_opacity, g_scales, g_rot, g_cov3D, g_v2g, None)
+
+
+class GaussianRasterizationSettings_GOF(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    kernel_size: float
+    subpixel_offset: torch.Tensor
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+def _absent() -> torch.Tensor:
+    return torch.Tensor([])
+
+
+class GaussianRasterizer_GOF(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        with torch.no_grad():
+            rs = self.raster_settings
+            return _C.mark_visible(positions, rs.viewmatrix, rs.projmatrix)
+
+    @staticmethod
+    def _validate(shs, colors_precomp, scales, rotations, cov3D_precomp):
+        if (shs is None) == (colors_precomp is None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None, view2gaussian_precomp=None):
+        self._validate(shs, colors_precomp, scales, rotations, cov3D_precomp)
+        fill = lambda t: _absent() if t is None else t
+        return rasterize_gaussians(means3D, means2D, fill(shs), fill(colors_precomp), opacities, fill(scales),
+                                   fill(rotations), fill(cov3D_precomp), fill(view2gaussian_precomp),
+                                   self.raster_settings)
+
+    def integrate(self, points3D, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None,
+                  rotations=None, cov3D_precomp=None, view2gaussian_precomp=None):
+        self._validate(shs, colors_precomp, scales, rotations, cov3D_precomp)
+        return _C.integrate_gaussians_to_points()
+
+
+# Un-suffixed names (commented out in the reference at :167,:184; used by vanilla render()).
+GaussianRasterizationSettings = GaussianRasterizationSettings_GOF
+GaussianRasterizer = GaussianRasterizer_GOF

@@ -1,0 +1,176 @@
+"""Drop-in for the live part of the reference's `src/gaussian_renderer/__init__.py`:
+
+  render_predicted_more_v2_gof   (:915-1067)  dict-of-tensors -> rasterizer -> output dict
+  depths_to_points / depth_to_normal (:881-909)
+  render                          the vanilla signature (src/gaussian-splatting/gaussian_renderer/__init__.py:18-100)
+
+Same arguments, same output keys.  Differences are internal: the rasterizer is libgof_b200,
+the per-call `subpixel_offset` allocation is dropped (no kernel reads it), and when no autograd
+graph is needed the ~20 small torch kernels of the post-processing (normalise, 4x4 inverse,
+back-projection, cross product) are replaced by one fused epilogue kernel (gof_render_epilogue).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..diff_gof_rasterization import GaussianRasterizationSettings_GOF, GaussianRasterizer_GOF
+
+_EMPTY_OFFSET: dict = {}
+
+
+def focal2fov(focal, pixels):
+    return 2 * math.atan(pixels / (2 * focal))
+
+
+def depths_to_points(world_view_transform, image_width, image_height, FoVx, FoVy, depthmap):
+    """Back-project a depth map to world points (torch ops; differentiable)."""
+    dev = depthmap.device
+    c2w = (world_view_transform.T).inverse()
+    W, H = image_width, image_height
+    fx = W / (2 * math.tan(FoVx / 2.))
+    fy = H / (2 * math.tan(FoVy / 2.))
+    intrins = torch.tensor([[fx, 0., W / 2.], [0., fy, H / 2.], [0., 0., 1.0]], dtype=torch.float32, device=dev)
+    grid_x, grid_y = torch.meshgrid(torch.arange(W, device=dev).float(), torch.arange(H, device=dev).float(),
+                                    indexing='xy')
+    points = torch.stack([grid_x, grid_y, torch.ones_like(grid_x)], dim=-1).reshape(-1, 3)
+    rays_d = points @ intrins.inverse().T @ c2w[:3, :3].T
+    rays_o = c2w[:3, 3]
+    return depthmap.reshape(-1, 1) * rays_d + rays_o
+
+
+def depth_to_normal(world_view_transform, image_width, image_height, FoVx, FoVy, depth):
+    """Normals from finite differences of the back-projected depth; border pixels are 0."""
+    points = depths_to_points(world_view_transform, image_width, image_height, FoVx, FoVy, depth)
+    points = points.reshape(*depth.shape[1:], 3)
+    output = torch.zeros_like(points)
+    dx = points[2:, 1:-1] - points[:-2, 1:-1]
+    dy = points[1:-1, 2:] - points[1:-1, :-2]
+    output[1:-1, 1:-1, :] = torch.nn.functional.normalize(torch.cross(dx, dy, dim=-1), dim=-1)
+    return output
+
+
+def _postprocess_torch(rendered_image, world_view_transform, W, H, FovX, FovY):
+    render_normal = torch.nn.functional.normalize(rendered_image[3:6], p=2, dim=0)
+    c2w = (world_view_transform.squeeze().T).inverse()
+    normal_world = (c2w[:3, :3] @ render_normal.reshape(3, -1)).reshape(3, *render_normal.shape[1:])
+    depth_normal = depth_to_normal(world_view_transform.squeeze(), W, H, FovX, FovY, rendered_image[6:7])
+    return normal_world, depth_normal.permute(2, 0, 1)
+
+
+def fused_epilogue(rendered_image, world_view_transform, W, H, FovX, FovY):
+    """normal_world[3,H,W], depth_normal[3,H,W] from out_color[9,H,W] in one kernel."""
+    dev = rendered_image.device
+    img = rendered_image.contiguous()
+    vm = world_view_transform.reshape(-1).contiguous()
+    normal_world = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+    depth_normal = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib.gof_render_epilogue(img.data_ptr(), vm.data_ptr(), W, H, ctypes.c_float(FovX),
+                                          ctypes.c_float(FovY), normal_world.data_ptr(), depth_normal.data_ptr(),
+                                          torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc, "gof_render_epilogue")
+    return normal_world, depth_normal
+
+
+def _subpixel_offset(H, W, device):
+    # The reference allocates zeros(H,W,2) per call (:954); no kernel reads it, so share one.
+    key = (H, W, str(device))
+    t = _EMPTY_OFFSET.get(key)
+    if t is None:
+        t = _EMPTY_OFFSET[key] = torch.zeros((H, W, 2), dtype=torch.float32, device=device)
+    return t
+
+
+def render_predicted_more_v2_gof(pc: dict, bs, world_view_transform, full_proj_transform, camera_center,
+                                 bg_color: torch.Tensor, cfg, kernel_size=0.0, scaling_modifier=1.0,
+                                 override_color=None, subpixel_offset=None):
+    """Render scene `bs` of the predicted Gaussian dict `pc` (reference :915-1067)."""
+    xyz = pc["xyz"][bs]
+    device = xyz.device
+    screenspace_points = torch.zeros_like(xyz, dtype=pc["xyz"].dtype, requires_grad=True, device=device) + 0
+    try:
+        screenspace_points.retain_grad()
+    except Exception:
+        pass
+
+    fov = cfg['model']['fov']
+    tanfovx = math.tan(fov * np.pi / 360)
+    tanfovy = math.tan(fov * np.pi / 360)
+    FovX = fov * np.pi / 180
+    FovY = fov * np.pi / 180
+    image_height = int(cfg['model']['training_resolution'])
+    image_width = int(cfg['model']['training_resolution'])
+
+    raster_settings = GaussianRasterizationSettings_GOF(
+        image_height=image_height, image_width=image_width, tanfovx=tanfovx, tanfovy=tanfovy,
+        kernel_size=kernel_size, subpixel_offset=_subpixel_offset(image_height, image_width, device),
+        bg=bg_color, scale_modifier=scaling_modifier, viewmatrix=world_view_transform,
+        projmatrix=full_proj_transform, sh_degree=cfg['model']['max_sh_degree'], campos=camera_center,
+        prefiltered=False, debug=False)
+    rasterizer = GaussianRasterizer_GOF(raster_settings=raster_settings)
+
+    opacity = pc["opacity"][bs]
+    scales = pc["scaling"][bs]
+    rotations = pc["rotation"][bs]
+    if override_color is None:
+        shs = torch.cat([pc["features_dc"][bs], pc["features_rest"][bs]], dim=1).contiguous()
+        colors_precomp = None
+    else:
+        shs = None
+        colors_precomp = pc["rgbs"][bs]
+    rendered_image, radii = rasterizer(means3D=xyz, means2D=screenspace_points, shs=shs,
+                                       colors_precomp=colors_precomp, opacities=opacity, scales=scales,
+                                       rotations=rotations, cov3D_precomp=None, view2gaussian_precomp=None)
+
+    if rendered_image.requires_grad:
+        normal_world, depth_normal = _postprocess_torch(rendered_image, world_view_transform, image_width,
+                                                        image_height, FovX, FovY)
+    else:
+        normal_world, depth_normal = fused_epilogue(rendered_image, world_view_transform, image_width,
+                                                    image_height, FovX, FovY)
+
+    return {"render": rendered_image[:3, :, :],
+            "rendered_normal": normal_world,
+            "rendered_depth": rendered_image[6:7, :, :],
+            "depth_normal": depth_normal,
+            "rendered_alpha": rendered_image[7:8, :, :],
+            "distortion_map": rendered_image[8:9, :, :],
+            "viewspace_points": screenspace_points,
+            "visibility_filter": radii > 0,
+            "radii": radii}
+
+
+def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None,
+           kernel_size=0.0):
+    """The vanilla `render()` signature (src/gaussian-splatting/gaussian_renderer/__init__.py:18-100)
+    on top of the GOF rasterizer.  `viewpoint_camera` provides FoVx, FoVy, image_height, image_width,
+    world_view_transform, full_proj_transform, camera_center; `pc` provides get_xyz, get_opacity,
+    get_scaling, get_rotation, get_features, active_sh_degree (and get_covariance when
+    pipe.compute_cov3D_python)."""
+    xyz = pc.get_xyz
+    screenspace_points = torch.zeros_like(xyz, dtype=xyz.dtype, requires_grad=True, device=xyz.device) + 0
+    try:
+        screenspace_points.retain_grad()
+    except Exception:
+        pass
+    H, W = int(viewpoint_camera.image_height), int(viewpoint_camera.image_width)
+    raster_settings = GaussianRasterizationSettings_GOF(
+        image_height=H, image_width=W, tanfovx=math.tan(viewpoint_camera.FoVx * 0.5),
+        tanfovy=math.tan(viewpoint_camera.FoVy * 0.5), kernel_size=kernel_size,
+        subpixel_offset=_subpixel_offset(H, W, xyz.device), bg=bg_color, scale_modifier=scaling_modifier,
+        viewmatrix=viewpoint_camera.world_view_transform, projmatrix=viewpoint_camera.full_proj_transform,
+        sh_degree=pc.active_sh_degree, campos=viewpoint_camera.camera_center, prefiltered=False,
+        debug=bool(getattr(pipe, "debug", False)))
+    rasterizer = GaussianRasterizer_GOF(raster_settings=raster_settings)
+    shs, colors_precomp = (pc.get_features, None) if override_color is None else (None, override_color)
+    rendered_image, radii = rasterizer(means3D=xyz, means2D=screenspace_points, shs=shs,
+                                       colors_precomp=colors_precomp, opacities=pc.get_opacity,
+                                       scales=pc.get_scaling, rotations=pc.get_rotation, cov3D_precomp=None,
+                                       view2gaussian_precomp=None)
+    return {"render": rendered_image[:3], "viewspace_points": screenspace_points,
+            "visibility_filter": radii > 0, "radii": radii}

@@ -1,0 +1,165 @@
+/* gof_b200.h -- C ABI of libgof_b200.so, the B200 (sm_100a) GOF Gaussian rasterizer.
+ *
+ * This is the drop-in boundary for the hot path of W-Ted/F3D-Gaus: every entry point
+ * below replaces one function of the reference's native layer
+ * (RAST = src/gaussian-splatting/submodules/diff-gof-rasterization):
+ *
+ *   gof_forward          <- CudaRasterizer::Rasterizer::forward   RAST/cuda_rasterizer/rasterizer.h:30-59
+ *                           (bound by RasterizeGaussiansCUDA,      RAST/rasterize_points.cu:36-122)
+ *   gof_backward         <- CudaRasterizer::Rasterizer::backward  RAST/cuda_rasterizer/rasterizer.h:61-91
+ *                           (bound by RasterizeGaussiansBackwardCUDA, RAST/rasterize_points.cu:124-211)
+ *   gof_mark_visible     <- CudaRasterizer::Rasterizer::markVisible RAST/cuda_rasterizer/rasterizer.h:24-29
+ *                           (bound by markVisible,                 RAST/rasterize_points.cu:213-232)
+ *   gof_state_sizes      <- required<GeometryState/ImageState/BinningState>()
+ *                                                                  RAST/cuda_rasterizer/rasterizer_impl.h:80-87
+ *   gof_state_get        <- (test accessor) GeometryState/ImageState/BinningState::fromChunk
+ *                                                                  RAST/cuda_rasterizer/rasterizer_impl.cu:188-243
+ *   gof_render_epilogue  <- the torch post-processing of render_predicted_more_v2_gof
+ *                                                                  src/gaussian_renderer/__init__.py:881-909,1043-1053
+ *
+ * Conventions (same as the reference unless noted):
+ *   - plain pointers and sizes only; all array pointers are DEVICE pointers, float32 unless noted;
+ *   - "not provided" inputs are NULL (the reference passes data_ptr()==nullptr of an empty tensor);
+ *   - viewmatrix/projmatrix are 16 floats read as m[0..15] with p' = (m0 x+m4 y+m8 z+m12, ...)
+ *     (RAST/cuda_rasterizer/auxiliary.h:86-115);
+ *   - rotations are (r,x,y,z) and are NOT normalised (forward.cu:138,172);
+ *   - the three state blobs are opaque, caller-owned byte buffers that must not move between
+ *     forward and backward (rasterizer_impl.cu:444-446);
+ *   - every function returns 0 on success or a negative GOF_E* code; gof_last_error() gives the
+ *     message.  No C++ exception crosses this boundary;
+ *   - kernels are launched on the caller's `stream` (the reference uses the legacy default
+ *     stream only; passing 0 reproduces that).
+ */
+#ifndef GOF_B200_H_
+#define GOF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GOF_OK            0
+#define GOF_EINVAL       -1   /* bad argument (shape, NULL, unsupported combination) */
+#define GOF_ECUDA        -2   /* a CUDA runtime call failed */
+#define GOF_ENOMEM       -3   /* a state blob / allocation callback was too small */
+#define GOF_EOVERFLOW    -4   /* sync-free mode: num_rendered exceeded the binning capacity */
+
+#define GOF_OUTPUT_CHANNELS 9   /* rgb(3) normal(3) depth alpha distortion: auxiliary.h:21-24 */
+
+typedef struct GofContext GofContext;   /* per-device handle (scratch, pinned mailbox) */
+typedef void* gof_stream_t;             /* cudaStream_t */
+
+/* Scalar settings: GaussianRasterizationSettings_GOF (RAST/diff_gof_rasterization/__init__.py:168-182). */
+typedef struct GofParams {
+	int32_t P;              /* number of Gaussians */
+	int32_t D;              /* active SH degree (sh_degree) */
+	int32_t M;              /* SH coefficients per channel = sh.size(1), 0 if no SH */
+	int32_t W, H;           /* image_width, image_height */
+	float tan_fovx, tan_fovy;
+	float kernel_size;
+	float scale_modifier;
+	int32_t prefiltered;
+	int32_t debug;          /* !=0: synchronise + check after every stage (auxiliary.h:204-211) */
+} GofParams;
+
+/* Per-Gaussian inputs + camera (argument list of Rasterizer::forward). */
+typedef struct GofInputs {
+	const float* background;             /* [3] */
+	const float* means3D;                /* [P,3] */
+	const float* shs;                    /* [P,M,3] or NULL */
+	const float* colors_precomp;         /* [P,3]   or NULL */
+	const float* opacities;              /* [P] */
+	const float* scales;                 /* [P,3]   or NULL (then cov3D_precomp) */
+	const float* rotations;              /* [P,4]   or NULL */
+	const float* cov3D_precomp;          /* [P,6]   or NULL */
+	const float* view2gaussian_precomp;  /* [P,10]  or NULL */
+	const float* viewmatrix;             /* [16] */
+	const float* projmatrix;             /* [16] */
+	const float* campos;                 /* [3] */
+} GofInputs;
+
+/* Gradient outputs of Rasterizer::backward, in the order RasterizeGaussiansBackwardCUDA
+ * returns them (rasterize_points.cu:210).  All are fully written (no pre-zeroing needed). */
+typedef struct GofGrads {
+	float* dL_dmeans2D;        /* [P,3] */
+	float* dL_dcolors;         /* [P,3] */
+	float* dL_dopacity;        /* [P,1] */
+	float* dL_dmeans3D;        /* [P,3] */
+	float* dL_dcov3D;          /* [P,6]  (identically 0, as in the reference) */
+	float* dL_dsh;             /* [P,M,3] or NULL when M==0 */
+	float* dL_dscales;         /* [P,3] */
+	float* dL_drotations;      /* [P,4] */
+	float* dL_dview2gaussian;  /* [P,10] */
+} GofGrads;
+
+/* Binning-blob allocation callback (the reference's resizeFunctional, rasterize_points.cu:28-34):
+ * called once per forward, after num_rendered is known, with the number of bytes needed;
+ * must return a device pointer to at least that many bytes (256-byte aligned) or NULL. */
+typedef void* (*GofAllocFn)(void* user, size_t bytes);
+
+const char* gof_last_error(void);
+const char* gof_version(void);
+
+int gof_context_create(int device, GofContext** out);
+void gof_context_destroy(GofContext* ctx);
+
+/* Byte sizes of the three state blobs.  binning_bytes is for `num_rendered` duplicates
+ * (pass an upper bound for the sync-free mode). */
+int gof_state_sizes(int32_t P, int32_t W, int32_t H, int64_t num_rendered,
+                    size_t* geom_bytes, size_t* img_bytes, size_t* binning_bytes);
+
+/* Forward: preprocess -> tile binning -> per-tile front-to-back GOF blend.
+ *   geom, img      : caller-allocated blobs of at least gof_state_sizes() bytes.
+ *   binning        : if non-NULL, a caller-allocated blob of `binning_bytes` bytes is used and no
+ *                    host synchronisation happens (num_rendered is then read back lazily, see
+ *                    gof_num_rendered); GOF_EOVERFLOW is reported by gof_num_rendered if it was
+ *                    too small (outputs are then invalid).
+ *                    If NULL, `alloc`(`alloc_user`, bytes) is called after one stream
+ *                    synchronisation, exactly like the reference (rasterizer_impl.cu:336-340).
+ *   out_color      : [9,H,W], radii: [P] int32.  Both fully written.
+ *   num_rendered   : host pointer; receives R in the callback mode, -1 in the sync-free mode.
+ *   binning_out    : host pointer; receives the binning blob actually used. */
+int gof_forward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
+                void* geom, size_t geom_bytes, void* img, size_t img_bytes,
+                void* binning, size_t binning_bytes, GofAllocFn alloc, void* alloc_user,
+                float* out_color, int32_t* radii,
+                int32_t* num_rendered, void** binning_out, gof_stream_t stream);
+
+/* Sync-free mode: blocks on `stream` and returns the R of the last forward that used `geom`
+ * (or GOF_EOVERFLOW if the binning blob was too small for it). */
+int gof_num_rendered(GofContext* ctx, const void* geom, int32_t P, gof_stream_t stream, int32_t* num_rendered);
+
+/* Backward: replays the blend back-to-front and produces the reference's 9 gradient tensors. */
+int gof_backward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
+                 int32_t num_rendered, const int32_t* radii,
+                 const void* geom, const void* binning, const void* img,
+                 const float* dL_dout_color /* [9,H,W] */, const GofGrads* grads,
+                 gof_stream_t stream);
+
+int gof_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
+                     const float* projmatrix, uint8_t* present /* [P] bool */, gof_stream_t stream);
+
+/* Fused epilogue of render_predicted_more_v2_gof: from out_color[9,H,W] and the camera produce
+ *   normal_world[3,H,W] = R_c2w * normalize(out_color[3:6])   and
+ *   depth_normal[3,H,W] = normalize(cross(dP/dy, dP/dx)) of the back-projected median depth
+ *                         (border pixels 0), as depth_to_normal() does.
+ * viewmatrix is the same 16 floats passed to gof_forward; fovx/fovy in radians. */
+int gof_render_epilogue(const float* out_color, const float* viewmatrix, int32_t W, int32_t H,
+                        float fovx, float fovy, float* normal_world, float* depth_normal,
+                        gof_stream_t stream);
+
+/* Test accessor: copy one named array of the opaque state into dst (device pointer).
+ * Names: depths[P] f32, means2D[P,2] f32, conic_opacity[P,4] f32, view2gaussian[P,10] f32,
+ * rgb[P,3] f32, clamped[P,3] u8, tiles_touched[P] u32, point_offsets[P] u32,
+ * final_T[4,H,W] f32, n_contrib[2,H,W] u32, ranges[T,2] u32, point_list[R] u32,
+ * point_list_keys[R] u64.  Returns the byte size (>=0) or a negative error. */
+int64_t gof_state_get(const char* name, int32_t P, int32_t W, int32_t H, int64_t num_rendered,
+                      const void* geom, const void* binning, const void* img,
+                      void* dst, int64_t dst_bytes, gof_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOF_B200_H_ */
