@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""bench.py -- the hot-path benchmark (BASELINE.json: "256x256 NVS frames/sec @65k Gaussians;
+renderCUDA HBM GB/s vs roofline").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload nvs256]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload `nvs256` (BASELINE configs[1]): one seeded "f3d-like" scene of 65,536 Gaussians (SH degree 1)
+per GPU, rendered at 256x256 from the 8 orbit views of the cycle-aggregative loop.  One STEP = one
+pass of the hot path over that batch = 8 full forwards (preprocess -> binning -> blend).
+`value` = frames/s over all GPUs with the scene resident in HBM; `e2e` = the same frames through
+the reference-facing API (render_predicted_more_v2_gof) starting from pinned HOST buffers, with the
+H2D copy of the Gaussian set and the D2H copy of the rendered rgb/depth/alpha inside the timed
+region.  Timing: CUDA events per step on the launch stream, an L2 flush (256 MB write) between
+steps outside the events, max over ranks.
+
+`--impl reference` times the UNMODIFIED reference rasterizer (oracle/_ref/libgof_ref.so: its CUDA
+sources compiled for sm_100a -- the reference has no CPU implementation of this path) on the same
+workload; if that library is absent it falls back to the CPU oracle port.  The product arm never
+touches oracle/: only the `cpu_baseline` leg (rank 0, N=1) and the reference arm do.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+VIEWS = 8
+P_SIDE = 256            # 256*256 = 65,536 Gaussians
+RES = 256
+L2_FLUSH_BYTES = 256 << 20
+
+
+def dist_setup(n_gpus: int):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return rank, world, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x: float, world: int) -> float:
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(x: float, world: int) -> float:
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+class ClockSampler:
+    """nvidia-smi sampler running during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_workload(rank: int, device):
+    from f3d_gaus_b200 import cameras, synthetic
+    import cases
+    pc_cpu = synthetic.f3d_like(seed=rank, S=P_SIDE)
+    cams = cameras.orbit_cameras(VIEWS)
+    cfg = synthetic.cfg_for(RES)
+    flat = [cases.make_case(pc_cpu, cams.world_view[v], cams.full_proj[v], cams.centers[v], W=RES, H=RES,
+                            fov_deg=cfg["model"]["fov"], device=device) for v in range(VIEWS)]
+    return pc_cpu, cams, cfg, flat
+
+
+def algorithmic_bytes_render_fwd(P, R, W, H):
+    """A_render_fwd = 8 T + 60 R + 12 P + 60 N per frame."""
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    return 8 * T + 60 * R + 12 * P + 60 * W * H
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_from_profiles():
+    """dram bytes per render launch from the committed ncu --set full summary, if present."""
+    path = os.path.join(ROOT, "profiles", "render_fwd_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------ arms --------
+class OursArm:
+    name = "ours"
+
+    def __init__(self, device):
+        from f3d_gaus_b200 import _lib
+        from f3d_gaus_b200.diff_gof_rasterization import _C
+        self._lib, self._C, self.device = _lib, _C, device
+        self.empty = torch.Tensor([])
+        self.launches_per_frame = None
+
+    def frame(self, c):
+        e = self.empty
+        return self._C.rasterize_gaussians(c["bg"], c["means3D"], e, c["opacities"], c["scales"], c["rotations"],
+                                           c["scale_modifier"], e, e, c["viewmatrix"], c["projmatrix"], c["tanfovx"],
+                                           c["tanfovy"], c["kernel_size"], e, c["H"], c["W"], c["shs"], c["D"],
+                                           c["campos"], False, False)
+
+    def step(self, flat):
+        R = 0
+        for c in flat:
+            out = self.frame(c)
+            R += int(out[0])
+        return R
+
+    def profile(self, on):
+        self._lib.profile_enable(self.device.index, on)
+
+    def profile_read(self):
+        return self._lib.profile_read(self.device.index)
+
+    def e2e_step(self, host_pc, dev_pc, cams_dev, cfg, bg, out_dev, out_host):
+        from f3d_gaus_b200.gaussian_renderer import render_predicted_more_v2_gof
+        for k in host_pc:
+            dev_pc[k].copy_(host_pc[k], non_blocking=True)
+        with torch.no_grad():
+            for v in range(VIEWS):
+                o = render_predicted_more_v2_gof(dev_pc, 0, cams_dev[0][v:v + 1], cams_dev[1][v:v + 1],
+                                                 cams_dev[2][v:v + 1], bg, cfg)
+                out_dev[v, 0:3].copy_(o["render"])
+                out_dev[v, 3:4].copy_(o["rendered_depth"])
+                out_dev[v, 4:5].copy_(o["rendered_alpha"])
+        out_host.copy_(out_dev, non_blocking=True)
+
+
+class ReferenceArm:
+    """The unmodified reference rasterizer (CUDA, sm_100a build) through its own C++ entry points."""
+    name = "reference"
+
+    def __init__(self, device):
+        import refgpu
+        self.refgpu, self.device = refgpu, device
+        self.run = refgpu.RefRun()
+        self.lib = self.run.lib
+        self.out_color = None
+
+    def frame(self, c):
+        P, W, H = c["means3D"].shape[0], c["W"], c["H"]
+        # the reference glue allocates + fills these per call (rasterize_points.cu:72-73)
+        out_color = torch.full((9, H, W), 0.0, dtype=torch.float32, device=self.device)
+        radii = torch.full((P,), 0, dtype=torch.int32, device=self.device)
+        p = lambda t: t.data_ptr()
+        R = self.lib.ref_forward(self.run.state, P, c["D"], c["shs"].shape[1], p(c["bg"]), W, H, p(c["means3D"]),
+                                 p(c["shs"]), None, p(c["opacities"]), p(c["scales"]), c["scale_modifier"],
+                                 p(c["rotations"]), None, None, p(c["viewmatrix"]), p(c["projmatrix"]), p(c["campos"]),
+                                 c["tanfovx"], c["tanfovy"], c["kernel_size"], None, 0, p(out_color), p(radii), 0)
+        if R < 0:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+        return R, out_color, radii
+
+    def step(self, flat):
+        R = 0
+        for c in flat:
+            R += self.frame(c)[0]
+        return R
+
+    def profile(self, on):
+        pass
+
+    def profile_read(self):
+        return None
+
+    def e2e_step(self, host_pc, dev_pc, cams_dev, cfg, bg, out_dev, out_host):
+        import math
+        for k in host_pc:
+            dev_pc[k].copy_(host_pc[k], non_blocking=True)
+        tanfov = math.tan(cfg["model"]["fov"] * math.pi / 360)
+        shs = torch.cat([dev_pc["features_dc"][0], dev_pc["features_rest"][0]], dim=1).contiguous()
+        for v in range(VIEWS):
+            c = {"bg": bg, "means3D": dev_pc["xyz"][0], "shs": shs, "opacities": dev_pc["opacity"][0],
+                 "scales": dev_pc["scaling"][0], "rotations": dev_pc["rotation"][0], "scale_modifier": 1.0,
+                 "viewmatrix": cams_dev[0][v], "projmatrix": cams_dev[1][v], "campos": cams_dev[2][v],
+                 "tanfovx": tanfov, "tanfovy": tanfov, "kernel_size": 0.0, "W": RES, "H": RES,
+                 "D": cfg["model"]["max_sh_degree"]}
+            _, color, _ = self.frame(c)
+            out_dev[v, 0:3].copy_(color[0:3])
+            out_dev[v, 3:4].copy_(color[6:7])
+            out_dev[v, 4:5].copy_(color[7:8])
+        out_host.copy_(out_dev, non_blocking=True)
+
+
+def cpu_oracle_frames_per_s(flat_cpu, max_frames=2):
+    """CPU port (oracle/gof_oracle.c, OpenMP) on a bounded sample of the same workload."""
+    import oracle_cpu
+    cs = [oracle_cpu.case_to_numpy(c) for c in flat_cpu[:max_frames]]
+    oracle_cpu.forward_all(cs[0])          # warm (page-in, thread pool)
+    t0 = time.perf_counter()
+    for c in cs:
+        oracle_cpu.forward_all(c)
+    dt = time.perf_counter() - t0
+    return len(cs) / dt, int(oracle_cpu.lib().oracle_num_threads()), len(cs), dt
+
+
+def run_cpu_reference_arm(args):
+    """Reference arm when oracle/_ref/libgof_ref.so is absent: the CPU oracle port on host cores."""
+    import cases
+    from f3d_gaus_b200 import cameras, synthetic
+    pc_cpu = synthetic.f3d_like(seed=0, S=P_SIDE)
+    cams = cameras.orbit_cameras(VIEWS)
+    flat = [cases.make_case(pc_cpu, cams.world_view[v], cams.full_proj[v], cams.centers[v], W=RES, H=RES,
+                            fov_deg=13.164) for v in range(VIEWS)]
+    fps, cores, n, dt = cpu_oracle_frames_per_s(flat, max_frames=max(1, min(VIEWS, args.steps)))
+    line = {"impl": "reference", "metric": "nvs_frames_per_sec_256x256_65k_gaussians", "value": fps, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * VIEWS / fps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "nvs256: 65536 f3d-like Gaussians, 8 orbit views, 256x256, forward"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": f"{n} frames in {dt:.1f}s (oracle/gof_oracle.c, OpenMP)"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="nvs256")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+
+    if args.impl == "reference":
+        import refgpu
+        if not refgpu.ref_available():
+            if int(os.environ.get("RANK", "0")) == 0:
+                run_cpu_reference_arm(args)
+            return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path is CUDA-only (no CPU fallback)")
+
+    rank, world, local = dist_setup(args.gpus)
+    device = torch.device("cuda", local)
+    pc_cpu, cams, cfg, flat = build_workload(rank, device)
+    arm = OursArm(device) if args.impl == "ours" else ReferenceArm(device)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
+    P, K, W_ = P_SIDE * P_SIDE, args.steps, args.warmup
+
+    # ---------------- kernel-level throughput: inputs resident in HBM -------------------------
+    for _ in range(W_):
+        R_step = arm.step(flat)
+    torch.cuda.synchronize()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    arm.profile(True)
+    if args.impl == "ours":
+        arm.profile_read()
+    barrier(world)
+    sampler = ClockSampler(local) if rank == 0 else None
+    for i in range(K):
+        flush.zero_()                      # L2 flush between timed iterations, outside the events
+        starts[i].record()
+        arm.step(flat)
+        ends[i].record()
+    barrier(world)
+    clocks = sampler.stop() if sampler else None
+    prof = arm.profile_read()
+    arm.profile(False)
+    total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    total_ms = max_over_ranks(total_ms, world)
+    frames = VIEWS * K * world
+    value = frames / (total_ms * 1e-3)
+
+    # ---------------- end to end through the public API, host buffers -------------------------
+    host_pc = {k: v.pin_memory() for k, v in pc_cpu.items()}
+    dev_pc = {k: torch.empty_like(v, device=device) for k, v in pc_cpu.items()}
+    cams_dev = (cams.world_view.to(device), cams.full_proj.to(device), cams.centers.to(device))
+    bg = torch.zeros(3, device=device)
+    out_dev = torch.empty((VIEWS, 5, RES, RES), dtype=torch.float32, device=device)
+    out_host = torch.empty((VIEWS, 5, RES, RES), dtype=torch.float32).pin_memory()
+    for _ in range(W_):
+        arm.e2e_step(host_pc, dev_pc, cams_dev, cfg, bg, out_dev, out_host)
+    torch.cuda.synchronize()
+    barrier(world)
+    e2e_ms = 0.0
+    for i in range(K):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        arm.e2e_step(host_pc, dev_pc, cams_dev, cfg, bg, out_dev, out_host)
+        torch.cuda.synchronize()
+        e2e_ms += (time.perf_counter() - t0) * 1e3
+    barrier(world)
+    e2e_ms = max_over_ranks(e2e_ms, world)
+    e2e_value = frames / (e2e_ms * 1e-3)
+    h2d = sum(v.numel() * v.element_size() for v in pc_cpu.values())
+    d2h = out_host.numel() * out_host.element_size()
+
+    # ---------------- roofline of the dominant kernel (the forward blend) ---------------------
+    roofline = None
+    launches = None
+    peak, peak_src = measured_peak_gbs()
+    if args.impl == "ours" and prof and prof["fwd_calls"]:
+        n_calls = prof["fwd_calls"]
+        blend_ms = prof["fwd_ms"]["blend"] / n_calls
+        R_frame = R_step / VIEWS
+        abytes = algorithmic_bytes_render_fwd(P, R_frame, RES, RES)
+        achieved = abytes / (blend_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "render_fwd_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic_from_profiles(), "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": abytes, "avg_launch_ms": blend_ms,
+                    "num_rendered_per_frame": R_frame,
+                    "stage_ms_per_frame": {k: v / n_calls for k, v in prof["fwd_ms"].items()}}
+        # kernels of ours per frame: preprocess, scan(2: init+scan), duplicate, sort (histogram +
+        # exclusive-sum + 6 onesweep passes for 41 bits), ranges/gather, blend; + 1 memset
+        launches = K * VIEWS * (1 + 2 + 1 + 8 + 1 + 1)
+
+    if rank != 0:
+        return
+    line = {
+        "metric": "nvs_frames_per_sec_256x256_65k_gaussians", "value": value, "unit": "frames/s", "n_gpus": world,
+        "steps": K, "warmup": W_, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "nvs256: 65536 f3d-like Gaussians (SH deg 1) per GPU, 8 orbit views, 256x256, forward "
+                               "(BASELINE configs[1])", "frames_per_step": VIEWS, "num_rendered_per_step": R_step,
+                   "l2": "flushed (256 MB write) between timed steps"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / K},
+        "gpu_launches": launches,
+    }
+    if args.impl == "ours":
+        line["roofline"] = roofline
+        if world == 1 and not args.no_cpu_baseline:
+            import cases
+            flat_cpu = [cases.case_to(c, "cpu") for c in flat]
+            fps, cores, n, dt = cpu_oracle_frames_per_s(flat_cpu)
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                                    "sample": f"{n} of the {VIEWS} frames of one step in {dt:.1f}s "
+                                              "(oracle/gof_oracle.c, OpenMP)"}
+    else:
+        line["impl"] = "reference"
+        line["gpu_launches"] = None
+        line["cpu_baseline"] = {"value": value, "unit": "frames/s", "cores": 0, "kind": "reference",
+                                "sample": f"{K} steps x {VIEWS} frames; the reference path has no CPU implementation: "
+                                          "this is its unmodified CUDA source compiled for sm_100a "
+                                          "(oracle/_ref/libgof_ref.so), run on the GPU"}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

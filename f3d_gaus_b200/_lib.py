@@ -45,6 +45,8 @@ SIGNATURES = {
     "gof_version": (c_char_p, []),
     "gof_context_create": (c_int32, [c_int32, POINTER(c_void_p)]),
     "gof_context_destroy": (None, [c_void_p]),
+    "gof_profile_enable": (c_int32, [c_void_p, c_int32]),
+    "gof_profile_read": (c_int32, [c_void_p, POINTER(ctypes.c_double), POINTER(c_int64), POINTER(ctypes.c_double), POINTER(c_int64)]),
     "gof_state_sizes": (c_int32, [c_int32, c_int32, c_int32, c_int64, POINTER(c_size_t), POINTER(c_size_t), POINTER(c_size_t)]),
     "gof_forward": (c_int32, [c_void_p, POINTER(GofParams), POINTER(GofInputs), c_void_p, c_size_t, c_void_p, c_size_t,
                               c_void_p, c_size_t, ALLOC_FN, c_void_p, c_void_p, c_void_p,
@@ -95,3 +97,21 @@ def context(device_index: int) -> c_void_p:
         check(lib.gof_context_create(device_index, ctypes.byref(out)), "gof_context_create")
         ctx = _contexts[device_index] = out
     return ctx
+
+
+FWD_STAGES = ("preprocess", "scan", "num_rendered_handoff", "binning", "blend")
+BWD_STAGES = ("clear", "blend_backward", "preprocess_backward")
+
+
+def profile_enable(device_index: int, on: bool) -> None:
+    check(lib.gof_profile_enable(context(device_index), int(on)), "gof_profile_enable")
+
+
+def profile_read(device_index: int) -> dict:
+    """{'fwd_calls', 'bwd_calls', 'fwd_ms': {stage: total ms}, 'bwd_ms': {...}} since the last read."""
+    f = (ctypes.c_double * 5)()
+    b = (ctypes.c_double * 3)()
+    nf, nb = c_int64(0), c_int64(0)
+    check(lib.gof_profile_read(context(device_index), f, ctypes.byref(nf), b, ctypes.byref(nb)), "gof_profile_read")
+    return {"fwd_calls": nf.value, "bwd_calls": nb.value, "fwd_ms": dict(zip(FWD_STAGES, list(f))),
+            "bwd_ms": dict(zip(BWD_STAGES, list(b)))}

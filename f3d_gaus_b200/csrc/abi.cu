@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 namespace gof {
 
@@ -26,7 +27,21 @@ struct GofContext {
 	int32_t* pinned = nullptr;      // host mailbox for num_rendered (callback mode)
 	float* gacc = nullptr;          // backward gradient accumulator, grown on demand
 	size_t gacc_floats = 0;
+	// optional per-stage CUDA-event timing (gof_profile_*): one event per stage boundary
+	bool profiling = false;
+	std::vector<cudaEvent_t> pool;          // reusable events
+	std::vector<std::vector<cudaEvent_t>> calls[2];   // [0] forward calls, [1] backward calls
 };
+
+static cudaEvent_t prof_event(GofContext* c, cudaStream_t s)
+{
+	cudaEvent_t e;
+	if (!c->pool.empty()) { e = c->pool.back(); c->pool.pop_back(); }
+	else cudaEventCreate(&e);
+	cudaEventRecord(e, s);
+	return e;
+}
+#define GOF_PROF_MARK(ctx, vec, s) do { if ((ctx)->profiling) (vec).push_back(prof_event((ctx), (s))); } while (0)
 
 using namespace gof;
 
@@ -60,7 +75,46 @@ void gof_context_destroy(GofContext* c)
 	if (!c) return;
 	if (c->pinned) cudaFreeHost(c->pinned);
 	if (c->gacc) cudaFree(c->gacc);
+	for (cudaEvent_t e : c->pool) cudaEventDestroy(e);
+	for (int k = 0; k < 2; k++) for (auto& m : c->calls[k]) for (cudaEvent_t e : m) cudaEventDestroy(e);
 	delete c;
+}
+
+int gof_profile_enable(GofContext* ctx, int on)
+{
+	if (!ctx) { set_error("gof_profile_enable: NULL context"); return GOF_EINVAL; }
+	ctx->profiling = on != 0;
+	return GOF_OK;
+}
+
+// Sums the CUDA-event durations (ms) of every profiled call since the last read.
+//   fwd_ms[5]: preprocess, scan, num_rendered hand-off (D2H + sync), binning, blend
+//   bwd_ms[3]: accumulator clear, blend backward, preprocess backward
+int gof_profile_read(GofContext* ctx, double* fwd_ms, int64_t* fwd_calls, double* bwd_ms, int64_t* bwd_calls)
+{
+	if (!ctx) { set_error("gof_profile_read: NULL context"); return GOF_EINVAL; }
+	GOF_CUDA_CHECK(cudaDeviceSynchronize());
+	for (int k = 0; k < 2; k++) {
+		const int nst = k == 0 ? 5 : 3;
+		double* out = k == 0 ? fwd_ms : bwd_ms;
+		if (out) for (int i = 0; i < nst; i++) out[i] = 0.0;
+		int64_t n = 0;
+		for (auto& marks : ctx->calls[k]) {
+			if ((int)marks.size() == nst + 1) {
+				n++;
+				for (int i = 0; i < nst; i++) {
+					float ms = 0.f;
+					cudaEventElapsedTime(&ms, marks[i], marks[i + 1]);
+					if (out) out[i] += ms;
+				}
+			}
+			for (cudaEvent_t e : marks) ctx->pool.push_back(e);
+		}
+		ctx->calls[k].clear();
+		if (k == 0 && fwd_calls) *fwd_calls = n;
+		if (k == 1 && bwd_calls) *bwd_calls = n;
+	}
+	return GOF_OK;
 }
 
 int gof_state_sizes(int32_t P, int32_t W, int32_t H, int64_t num_rendered,
@@ -134,10 +188,14 @@ int gof_forward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
 	if (!img || im.total > img_bytes) { set_error("gof_forward: img blob too small (%zu < %zu)", img_bytes, im.total); return GOF_ENOMEM; }
 
 	int rc;
+	std::vector<cudaEvent_t> marks;
+	GOF_PROF_MARK(ctx, marks, s);
 	if ((rc = launch_preprocess(*prm, *in, focal_x, focal_y, tile_grid, g, radii, s)) != GOF_OK) return rc;
 	GOF_STAGE_CHECK(prm, s);
+	GOF_PROF_MARK(ctx, marks, s);
 	if ((rc = launch_scan(g, P, s)) != GOF_OK) return rc;
 	GOF_STAGE_CHECK(prm, s);
+	GOF_PROF_MARK(ctx, marks, s);
 
 	int R;
 	BinState b;
@@ -166,10 +224,14 @@ int gof_forward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
 	}
 	if (num_rendered) *num_rendered = R;
 
+	GOF_PROF_MARK(ctx, marks, s);   // after the num_rendered hand-off
 	if ((rc = launch_binning(*prm, tile_grid, g, im, b, radii, R, s)) != GOF_OK) return rc;
 	GOF_STAGE_CHECK(prm, s);
+	GOF_PROF_MARK(ctx, marks, s);
 	if ((rc = launch_render_fwd(*prm, tile_grid, focal_x, focal_y, im, b, in->background, out_color, s)) != GOF_OK) return rc;
 	GOF_STAGE_CHECK(prm, s);
+	GOF_PROF_MARK(ctx, marks, s);
+	if (ctx->profiling) ctx->calls[0].push_back(std::move(marks));
 	return GOF_OK;
 }
 
@@ -218,14 +280,20 @@ int gof_backward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
 		GOF_CUDA_CHECK(cudaMalloc(&ctx->gacc, need * sizeof(float)));
 		ctx->gacc_floats = need;
 	}
+	std::vector<cudaEvent_t> marks;
+	GOF_PROF_MARK(ctx, marks, s);
 	GOF_CUDA_CHECK(cudaMemsetAsync(ctx->gacc, 0, need * sizeof(float), s));
+	GOF_PROF_MARK(ctx, marks, s);
 	int rc;
 	if (num_rendered > 0) {
 		if ((rc = launch_render_bwd(*prm, tile_grid, focal_x, focal_y, g, im, b, in->background, dL_dout_color, ctx->gacc, s)) != GOF_OK) return rc;
 		GOF_STAGE_CHECK(prm, s);
 	}
+	GOF_PROF_MARK(ctx, marks, s);
 	if ((rc = launch_preprocess_bwd(*prm, *in, g, radii, ctx->gacc, *gr, s)) != GOF_OK) return rc;
 	GOF_STAGE_CHECK(prm, s);
+	GOF_PROF_MARK(ctx, marks, s);
+	if (ctx->profiling) ctx->calls[1].push_back(std::move(marks));
 	return GOF_OK;
 }
 

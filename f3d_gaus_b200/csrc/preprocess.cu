@@ -210,46 +210,64 @@ __device__ __forceinline__ void view2gaussian_quadric(const V3& scale, const V3&
 // SH -> RGB, degrees 0..3 (forward.cu:20-71).  lo holds coefficients 0..3 (already in
 // registers, [k][channel]); hi points at this Gaussian's [M,3] block in global memory and is
 // only dereferenced for coefficients >= 4.
+// The roundings are pinned with explicit intrinsics to what the reference's sm_100a build
+// evaluates (read off its SASS): c0 = C0*sh0 rounded, then one fused multiply-add per further
+// coefficient, with polynomial factors such as 3xx-yy themselves fused (fma(xx,3,-yy)).
 __device__ __forceinline__ V3 sh_to_rgb(int deg, const V3& pos, const V3& campos, const float (*lo)[3],
                                         const float* __restrict__ hi, uint8_t* clamped3)
 {
 	V3 dir = { pos.x - campos.x, pos.y - campos.y, pos.z - campos.z };
 	float len = sqrt(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
-	dir.x = dir.x / len; dir.y = dir.y / len; dir.z = dir.z / len;
-#define SHV(k, ch) hi[3 * (k) + (ch)]
+	const float x = dir.x / len, y = dir.y / len, z = dir.z / len;
+	float r[3];
+#pragma unroll
+	for (int ch = 0; ch < 3; ch++) r[ch] = __fmul_rn(lo[0][ch], kSH_C0);
+	if (deg > 0) {
+		const float a = __fmul_rn(y, kSH_C1), b = __fmul_rn(z, kSH_C1), c = __fmul_rn(x, kSH_C1);
+#pragma unroll
+		for (int ch = 0; ch < 3; ch++) {
+			r[ch] = __fmaf_rn(-a, lo[1][ch], r[ch]);
+			r[ch] = __fmaf_rn(b, lo[2][ch], r[ch]);
+			r[ch] = __fmaf_rn(-c, lo[3][ch], r[ch]);
+		}
+		if (deg > 1) {
+			const float xx = __fmul_rn(x, x), yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+			const float xy = __fmul_rn(x, y), yz = __fmul_rn(y, z), xz = __fmul_rn(x, z);
+			const float zz2 = __fadd_rn(zz, zz);
+			const float xx_yy = __fsub_rn(xx, yy);
+			float t[12];
+			t[0] = __fmul_rn(xy, kSH_C2[0]);
+			t[1] = __fmul_rn(yz, kSH_C2[1]);
+			t[2] = __fmul_rn(__fsub_rn(__fsub_rn(zz2, xx), yy), kSH_C2[2]);
+			t[3] = __fmul_rn(xz, kSH_C2[3]);
+			t[4] = __fmul_rn(xx_yy, kSH_C2[4]);
+			int nt = 5;
+			if (deg > 2) {
+				const float p4 = __fsub_rn(__fmaf_rn(zz, 4.0f, -xx), yy);          // 4zz - xx - yy
+				t[5] = __fmul_rn(__fmul_rn(y, kSH_C3[0]), __fmaf_rn(xx, 3.0f, -yy));
+				t[6] = __fmul_rn(z, __fmul_rn(xy, kSH_C3[1]));
+				t[7] = __fmul_rn(__fmul_rn(y, kSH_C3[2]), p4);
+				t[8] = __fmul_rn(__fmul_rn(z, kSH_C3[3]), __fmaf_rn(yy, -3.0f, __fmaf_rn(xx, -3.0f, zz2)));
+				t[9] = __fmul_rn(__fmul_rn(x, kSH_C3[4]), p4);
+				t[10] = __fmul_rn(__fmul_rn(z, kSH_C3[5]), xx_yy);
+				t[11] = __fmul_rn(__fmul_rn(x, kSH_C3[6]), __fmaf_rn(yy, -3.0f, xx));
+				nt = 12;
+			}
+#pragma unroll
+			for (int k = 0; k < 12; k++)
+				if (k < nt) {
+#pragma unroll
+					for (int ch = 0; ch < 3; ch++) r[ch] = __fmaf_rn(t[k], hi[3 * (4 + k) + ch], r[ch]);
+				}
+		}
+	}
 	float res[3];
 #pragma unroll
 	for (int ch = 0; ch < 3; ch++) {
-		float result = kSH_C0 * lo[0][ch];
-		if (deg > 0) {
-			float x = dir.x, y = dir.y, z = dir.z;
-			result = result - kSH_C1 * y * lo[1][ch] + kSH_C1 * z * lo[2][ch] - kSH_C1 * x * lo[3][ch];
-			if (deg > 1) {
-				float xx = x * x, yy = y * y, zz = z * z;
-				float xy = x * y, yz = y * z, xz = x * z;
-				result = result +
-					kSH_C2[0] * xy * SHV(4, ch) +
-					kSH_C2[1] * yz * SHV(5, ch) +
-					kSH_C2[2] * (2.0f * zz - xx - yy) * SHV(6, ch) +
-					kSH_C2[3] * xz * SHV(7, ch) +
-					kSH_C2[4] * (xx - yy) * SHV(8, ch);
-				if (deg > 2) {
-					result = result +
-						kSH_C3[0] * y * (3.0f * xx - yy) * SHV(9, ch) +
-						kSH_C3[1] * xy * z * SHV(10, ch) +
-						kSH_C3[2] * y * (4.0f * zz - xx - yy) * SHV(11, ch) +
-						kSH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * SHV(12, ch) +
-						kSH_C3[4] * x * (4.0f * zz - xx - yy) * SHV(13, ch) +
-						kSH_C3[5] * z * (xx - yy) * SHV(14, ch) +
-						kSH_C3[6] * x * (xx - 3.0f * yy) * SHV(15, ch);
-				}
-			}
-		}
-		result += 0.5f;
-		clamped3[ch] = (result < 0);
-		res[ch] = max(result, 0.0f);
+		const float v = __fadd_rn(r[ch], 0.5f);
+		clamped3[ch] = (v < 0);
+		res[ch] = (v < 0) ? 0.0f : v;
 	}
-#undef SHV
 	return { res[0], res[1], res[2] };
 }
 

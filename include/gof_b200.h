@@ -105,6 +105,14 @@ const char* gof_version(void);
 int gof_context_create(int device, GofContext** out);
 void gof_context_destroy(GofContext* ctx);
 
+/* Optional per-stage timing with CUDA events on the caller's stream (used by bench.py for the
+ * roofline line; no reference counterpart).  gof_profile_read synchronises the device and sums the
+ * stage durations (ms) of all calls since the previous read:
+ *   fwd_ms[5] = preprocess, scan, num_rendered hand-off, binning (duplicate+sort+ranges/gather), blend
+ *   bwd_ms[3] = accumulator clear, blend backward, preprocess backward */
+int gof_profile_enable(GofContext* ctx, int on);
+int gof_profile_read(GofContext* ctx, double* fwd_ms, int64_t* fwd_calls, double* bwd_ms, int64_t* bwd_calls);
+
 /* Byte sizes of the three state blobs.  binning_bytes is for `num_rendered` duplicates
  * (pass an upper bound for the sync-free mode). */
 int gof_state_sizes(int32_t P, int32_t W, int32_t H, int64_t num_rendered,

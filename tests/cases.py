@@ -58,8 +58,8 @@ def case_to(c: dict, device) -> dict:
 
 GOLDEN_CASES = {
     # name: builder (CPU tensors)
-    "f3d_s48_r256_view2": lambda: f3d_case(0, 48, 256, 2),
-    "unit_p1500_200x136_sh3": lambda: unit_case(1, 1500, 200, 136, sh_degree=3, bg=(0.2, 0.5, 0.9)),
-    "f3d_s32_r128_colors_ks": lambda: f3d_case(2, 32, 128, None, use_colors=True, kernel_size=0.1,
-                                               scale_modifier=1.3, bg=(1.0, 0.5, 0.25)),
+    "f3d_s48_r128_view2": lambda: f3d_case(0, 48, 128, 2),
+    "unit_p1200_120x88_sh3": lambda: unit_case(1, 1200, 120, 88, sh_degree=3, bg=(0.2, 0.5, 0.9)),
+    "f3d_s32_r96_colors_ks": lambda: f3d_case(2, 32, 96, None, use_colors=True, kernel_size=0.1,
+                                              scale_modifier=1.3, bg=(1.0, 0.5, 0.25)),
 }
