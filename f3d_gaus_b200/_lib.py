@@ -12,6 +12,14 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_si
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgof_b200.so")
 
+FLAG_EXACT_BLEND = 1
+
+
+def default_flags() -> int:
+    """Blend arithmetic mode: bit-exact contributing path iff GOF_EXACT_BLEND=1 (see gof_b200.h)."""
+    return FLAG_EXACT_BLEND if os.environ.get("GOF_EXACT_BLEND", "0") not in ("0", "", "false") else 0
+
+
 GOF_OK = 0
 GOF_EINVAL, GOF_ECUDA, GOF_ENOMEM, GOF_EOVERFLOW = -1, -2, -3, -4
 OUTPUT_CHANNELS = 9
@@ -21,7 +29,7 @@ class GofParams(Structure):
     _fields_ = [
         ("P", c_int32), ("D", c_int32), ("M", c_int32), ("W", c_int32), ("H", c_int32),
         ("tan_fovx", c_float), ("tan_fovy", c_float), ("kernel_size", c_float), ("scale_modifier", c_float),
-        ("prefiltered", c_int32), ("debug", c_int32),
+        ("prefiltered", c_int32), ("debug", c_int32), ("flags", c_int32),
     ]
 
 

@@ -47,6 +47,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
 {
 	uint32_t ok;
@@ -96,12 +100,21 @@ __device__ __forceinline__ PairGeom pair_geom(const float4& a, const float4& b, 
 	return g;
 }
 
+__device__ __forceinline__ float rcp_approx(float x)
+{
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));   // one MUFU.RCP, <= 1 ulp
+	return r;
+}
+
 // true  => the reference skips this pair (no side effects); false => run the exact path.
+// q32 = BB^2/(4 AA) from 3 roundings + a 1-ulp reciprocal: within 3e-7 relative of the exact
+// quotient of the float32 AA, BB the reference widens to double (1e-6 is the bound used).
 __device__ __forceinline__ bool pair_pretest_reject(const PairGeom& g, float C, float tau)
 {
-	const float q32 = __fdividef(__fmul_rn(__fmul_rn(g.BB, g.BB), 0.25f), g.AA);
+	const float q32 = __fmul_rn(__fmul_rn(__fmul_rn(g.BB, g.BB), 0.25f), rcp_approx(g.AA));
 	const float lower = __fmaf_rn(-1.000001f, q32, C);
-	return (g.AA > 0.0f) && (lower > tau);
+	return (g.AA > 1e-30f) && (lower > tau);
 }
 
 // Exact alpha of the pair.  Returns false if the reference `continue`s (t <= near plane or

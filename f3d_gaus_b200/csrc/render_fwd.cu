@@ -5,18 +5,25 @@
 // final_T[4,H,W] = (T, dist1, dist2, distortion_raw), n_contrib[2,H,W] = (last, max contributor).
 //
 // B200 design:
-//   * One CTA per 16x16 tile (the tile size is part of the binning contract), 8 warps, each
-//     warp owning an 8x4 pixel block so that a Gaussian's footprint diverges fewer warps than
-//     the reference's 16x2 strips.
-//   * The tile's sorted Gaussians arrive as a contiguous slab of 64-byte records (binning.cu);
-//     one elected thread streams it into a 4-stage shared-memory ring with TMA bulk copies
-//     (cp.async.bulk + mbarrier complete_tx), so the 256 pixel threads never issue a global
-//     load in the loop and the next chunks land while the current one is blended.
-//   * Each (pixel, Gaussian) pair first takes the conservative float32 pre-test of
-//     blend_math.cuh; only survivors pay for the FP64 ray-minimum and expf.  Pre-tests run
-//     4 records at a time for ILP, survivors are then blended in order.
-//   * Accumulation order and every rounding of the contributing path follow the reference's
-//     sm_100a build, so the forward outputs are bit-identical to it.
+//   * One CTA per 16x16 tile (the tile size is part of the binning contract): 8 consumer warps,
+//     each owning an 8x4 pixel block, plus one producer warp.
+//   * The tile's sorted Gaussians arrive as a contiguous slab of 64-byte records (binning.cu).
+//     The producer streams it into a 4-stage shared-memory ring with TMA bulk copies
+//     (cp.async.bulk, completion on a "full" mbarrier per stage); each consumer warp releases a
+//     stage by arriving on its "empty" mbarrier.  There is no CTA-wide barrier in the loop: warps
+//     drift up to three chunks apart, so a warp that has many contributors in one chunk does not
+//     stall the other seven (the reference, and our first version, synchronise every batch).
+//   * Per 32-record group, two passes.  Pass 1 is a branch-free sweep: every pixel runs the
+//     conservative float32 pre-test (blend_math.cuh) against the 32 records with warp-broadcast
+//     shared-memory reads and keeps the survivors as a bit mask.  Pass 2 is lane-private: each
+//     pixel walks ITS OWN survivors in order (exact FP64 ray minimum, expf, blend).  A warp spends
+//     pass-2 iterations equal to its busiest pixel's survivor count (~10% of the list) instead of
+//     running the expensive path for every record any of its 32 pixels touches.
+//   * Rounding: alpha, T, rgb, median depth, alpha channel and the contributor counters follow
+//     the reference's sm_100a build operation by operation and are bit-identical to it in both
+//     modes.  With GOF_FLAG_EXACT_BLEND the depth mapping and the normal normalisation also use
+//     its IEEE double divide / double sqrt / float divides (all nine channels bit-identical);
+//     without it they use float32 reciprocal arithmetic (normals, distortion within ~1e-6).
 #include "blend_math.cuh"
 
 namespace gof {
@@ -25,7 +32,6 @@ namespace {
 
 constexpr int CHUNK = 128;                 // records per pipeline stage (8 KB)
 constexpr int STAGES = 4;
-constexpr int CHUNK_BYTES = CHUNK * REC_BYTES;
 
 struct PixState {
 	float T;
@@ -36,6 +42,7 @@ struct PixState {
 
 // Blend one surviving pair into the pixel state (forward.cu:536-578).  Returns true when the
 // pixel saturates (test_T < 1e-4) -- the pair is then NOT blended, as in the reference.
+template <bool EXACT>
 __device__ __forceinline__ bool blend_pair(PixState& s, const PairGeom& g, float t, float alpha,
                                            const float4& d, uint32_t contributor)
 {
@@ -43,15 +50,24 @@ __device__ __forceinline__ bool blend_pair(PixState& s, const PairGeom& g, float
 	const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
 	if (test_T < 0.0001f) return true;
 
-	// 2DGS NDC depth mapping, in double: (far*t - far*near) / ((far - near) * t)
-	const double td = t;
-	const float m = (float)(fma(td, 100.0, -(100.0 * 0.2)) / ((100.0 - 0.2) * td));
-
+	float m, nn0, nn1, nn2;
 	const float len2 = __fmaf_rn(g.n2, g.n2, __fmaf_rn(g.n0, g.n0, __fmul_rn(g.n1, g.n1)));
-	const float length = (float)sqrt((double)len2 + 1e-7);
-	const float nn0 = __fdiv_rn(g.n0, length);
-	const float nn1 = __fdiv_rn(g.n1, length);
-	const float nn2 = __fdiv_rn(g.n2, length);
+	if (EXACT) {
+		// 2DGS NDC depth mapping, in double: (far*t - far*near) / ((far - near) * t)
+		const double td = t;
+		m = (float)(fma(td, 100.0, -(100.0 * 0.2)) / ((100.0 - 0.2) * td));
+		const float length = (float)sqrt((double)len2 + 1e-7);
+		nn0 = __fdiv_rn(g.n0, length);
+		nn1 = __fdiv_rn(g.n1, length);
+		nn2 = __fdiv_rn(g.n2, length);
+	} else {
+		// same quantities with float32 reciprocals: far/(far-near) - (far*near/(far-near)) / t
+		m = __fmaf_rn(-(float)((100.0 * 0.2) / (100.0 - 0.2)), rcp_approx(t), (float)(100.0 / (100.0 - 0.2)));
+		const float inv_len = rsqrtf(len2 + 1e-7f);
+		nn0 = g.n0 * inv_len;
+		nn1 = g.n1 * inv_len;
+		nn2 = g.n2 * inv_len;
+	}
 
 	const float A1 = __fsub_rn(1.0f, T);
 	const float m2 = __fmul_rn(m, m);
@@ -77,22 +93,21 @@ __device__ __forceinline__ bool blend_pair(PixState& s, const PairGeom& g, float
 	return false;
 }
 
-__global__ void __launch_bounds__(TILE_PIX)
+constexpr int CONSUMER_WARPS = TILE_PIX / 32;          // 8
+constexpr int FWD_THREADS = TILE_PIX + 32;             // + 1 producer warp
+
+template <bool EXACT>
+__global__ void __launch_bounds__(FWD_THREADS)
 render_fwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ slab, int W, int H,
                   float focal_x, float focal_y, const float* __restrict__ bg_color,
                   float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color)
 {
 	__shared__ __align__(128) float4 s_rec[STAGES][CHUNK * 4];
 	__shared__ __align__(8) uint64_t s_full[STAGES];
+	__shared__ __align__(8) uint64_t s_empty[STAGES];
 
 	const int tid = threadIdx.x;
 	const int warp = tid >> 5, lane = tid & 31;
-	const uint32_t px = blockIdx.x * TILE_X + (warp & 1) * 8 + (lane & 7);
-	const uint32_t py = blockIdx.y * TILE_Y + (warp >> 1) * 4 + (lane >> 3);
-	const bool inside = px < (uint32_t)W && py < (uint32_t)H;
-	const uint32_t pix_id = W * py + px;
-	const float rx = pixel_ray(px, W, focal_x);
-	const float ry = pixel_ray(py, H, focal_y);
 
 	const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
 	const int n = (int)(range.y - range.x);
@@ -101,22 +116,33 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 
 	if (tid == 0) {
 #pragma unroll
-		for (int s = 0; s < STAGES; s++) mbar_init(&s_full[s], 1);
+		for (int s = 0; s < STAGES; s++) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], CONSUMER_WARPS); }
 		mbar_fence_init();
 	}
 	__syncthreads();
 
-	auto issue = [&](int c) {
-		const int s = c % STAGES;
-		const int cnt = min(CHUNK, n - c * CHUNK);
-		const uint32_t bytes = (uint32_t)cnt * REC_BYTES;
-		mbar_arrive_expect_tx(&s_full[s], bytes);
-		tma_bulk_g2s(&s_rec[s][0], tile_slab + (size_t)c * CHUNK * REC_FLOATS, bytes, &s_full[s]);
-	};
-	if (tid == 0) {
-		const int pre = min(STAGES, nchunks);
-		for (int c = 0; c < pre; c++) issue(c);
+	if (warp == CONSUMER_WARPS) {
+		// ---------------- producer warp: one elected lane streams the slab ----------------------
+		if (lane == 0) {
+			for (int c = 0; c < nchunks; c++) {
+				const int s = c % STAGES;
+				if (c >= STAGES) mbar_wait(&s_empty[s], (uint32_t)(((c / STAGES) - 1) & 1));
+				const int cnt = min(CHUNK, n - c * CHUNK);
+				const uint32_t bytes = (uint32_t)cnt * REC_BYTES;
+				mbar_arrive_expect_tx(&s_full[s], bytes);
+				tma_bulk_g2s(&s_rec[s][0], tile_slab + (size_t)c * CHUNK * REC_FLOATS, bytes, &s_full[s]);
+			}
+		}
+		return;
 	}
+
+	// -------------------- consumer warps: 8x4 pixel block each --------------------------------
+	const uint32_t px = blockIdx.x * TILE_X + (warp & 1) * 8 + (lane & 7);
+	const uint32_t py = blockIdx.y * TILE_Y + (warp >> 1) * 4 + (lane >> 3);
+	const bool inside = px < (uint32_t)W && py < (uint32_t)H;
+	const uint32_t pix_id = W * py + px;
+	const float rx = pixel_ray(px, W, focal_x);
+	const float ry = pixel_ray(py, H, focal_y);
 
 	PixState st;
 	st.T = 1.0f;
@@ -126,50 +152,46 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 	st.last_contributor = 0;
 	st.max_contributor = 0xFFFFFFFFu;   // uint(-1), forward.cu:464
 	bool done = !inside;
+	bool warp_done = __all_sync(0xffffffffu, done);
 
-	int c = 0;
-	for (; c < nchunks; c++) {
+	for (int c = 0; c < nchunks; c++) {
 		const int s = c % STAGES;
 		mbar_wait(&s_full[s], (uint32_t)((c / STAGES) & 1));
-		const int cnt = min(CHUNK, n - c * CHUNK);
-		const float4* rec = &s_rec[s][0];
-		const uint32_t base = (uint32_t)c * CHUNK;
-
-		if (!done) {
-			for (int j0 = 0; j0 < cnt && !done; j0 += 4) {
-				// pre-test 4 records (independent -> ILP), collect survivors in a bit mask
-				uint32_t mask = 0;
+		if (!warp_done) {
+			const int cnt = min(CHUNK, n - c * CHUNK);
+			const float4* rec = &s_rec[s][0];
+			const uint32_t base = (uint32_t)c * CHUNK;
+			for (int w = 0; w < CHUNK / 32; w++) {
+				const int valid = cnt - 32 * w;
+				if (valid <= 0) break;
+				// ---- pass 1: branch-free pre-test sweep over 32 records (broadcast reads) ------
+				uint32_t bits = 0;
+				const float4* rw = rec + 4 * 32 * w;
 #pragma unroll
-				for (int k = 0; k < 4; k++) {
-					const int j = j0 + k;
-					if (j < cnt) {
-						const float4 a = rec[4 * j + 0], b = rec[4 * j + 1], cc = rec[4 * j + 2];
-						const PairGeom g = pair_geom(a, b, cc, rx, ry);
-						if (!pair_pretest_reject(g, cc.y, cc.z)) mask |= 1u << k;
-					}
+				for (int jj = 0; jj < 32; jj++) {
+					const float4 a = rw[4 * jj + 0], b = rw[4 * jj + 1], cc = rw[4 * jj + 2];
+					const PairGeom g = pair_geom(a, b, cc, rx, ry);
+					if (!pair_pretest_reject(g, cc.y, cc.z)) bits |= 1u << jj;
 				}
-				while (mask) {
-					const int k = __ffs(mask) - 1;
-					mask &= mask - 1;
-					const int j = j0 + k;
-					const float4 a = rec[4 * j + 0], b = rec[4 * j + 1], cc = rec[4 * j + 2];
+				if (valid < 32) bits &= (1u << valid) - 1u;   // stale records beyond the list end
+				if (done) bits = 0;
+				// ---- pass 2: each pixel blends its own survivors, in list order ----------------
+				while (bits != 0) {
+					const int jj = __ffs(bits) - 1;
+					bits &= bits - 1;
+					const float4* r = rw + 4 * jj;
+					const float4 a = r[0], b = r[1], cc = r[2];
 					const PairGeom g = pair_geom(a, b, cc, rx, ry);
 					float t, alpha, G;
 					if (!pair_alpha_exact(g, cc.y, cc.w, t, alpha, G)) continue;
-					const float4 d = rec[4 * j + 3];
-					if (blend_pair(st, g, t, alpha, d, base + j + 1)) { done = true; break; }
+					const float4 d = r[3];
+					if (blend_pair<EXACT>(st, g, t, alpha, d, base + 32 * w + jj + 1)) { done = true; bits = 0; }
 				}
 			}
+			warp_done = __all_sync(0xffffffffu, done);
 		}
-		// Everyone is past this stage: vote for early exit, then refill the stage.
-		const int num_done = __syncthreads_count(done);
-		if (num_done == TILE_PIX) break;
-		if (tid == 0 && c + STAGES < nchunks) issue(c + STAGES);
-	}
-	// Drain copies that were issued but never consumed (early exit) before the CTA retires.
-	if (tid == 0 && c < nchunks) {
-		const int issued = min(nchunks, c + STAGES);
-		for (int cc = c + 1; cc < issued; cc++) mbar_wait(&s_full[cc % STAGES], (uint32_t)((cc / STAGES) & 1));
+		__syncwarp();
+		if (lane == 0) mbar_arrive(&s_empty[s]);   // this warp is finished with stage s
 	}
 
 	if (inside) {
@@ -197,8 +219,12 @@ int launch_render_fwd(const GofParams& prm, dim3 tile_grid, float focal_x, float
                       const ImgState& im, const BinState& b, const float* background,
                       float* out_color, cudaStream_t s)
 {
-	render_fwd_kernel<<<tile_grid, TILE_PIX, 0, s>>>(im.ranges, b.slab, prm.W, prm.H, focal_x, focal_y,
-	                                                background, im.final_T, im.n_contrib, out_color);
+	if (prm.flags & GOF_FLAG_EXACT_BLEND)
+		render_fwd_kernel<true><<<tile_grid, FWD_THREADS, 0, s>>>(im.ranges, b.slab, prm.W, prm.H, focal_x, focal_y,
+		                                                          background, im.final_T, im.n_contrib, out_color);
+	else
+		render_fwd_kernel<false><<<tile_grid, FWD_THREADS, 0, s>>>(im.ranges, b.slab, prm.W, prm.H, focal_x, focal_y,
+		                                                           background, im.final_T, im.n_contrib, out_color);
 	GOF_CUDA_CHECK(cudaGetLastError());
 	return GOF_OK;
 }

@@ -84,7 +84,7 @@ class _CModule:
 
             alloc_cb = _lib.ALLOC_FN(_alloc)
             prm = _lib.GofParams(P, int(degree), M, W, H, float(tan_fovx), float(tan_fovy), float(kernel_size),
-                                 float(scale_modifier), int(bool(prefiltered)), int(bool(debug)))
+                                 float(scale_modifier), int(bool(prefiltered)), int(bool(debug)), _lib.default_flags())
             inp = _lib.GofInputs(
                 _dev_ptr(background, device, keep), _dev_ptr(means3D, device, keep), _dev_ptr(sh, device, keep),
                 _dev_ptr(colors, device, keep), _dev_ptr(opacity, device, keep), _dev_ptr(scales, device, keep),
@@ -125,7 +125,7 @@ class _CModule:
         with torch.cuda.device(device):
             stream = torch.cuda.current_stream(device).cuda_stream
             prm = _lib.GofParams(P, int(degree), M, W, H, float(tan_fovx), float(tan_fovy), float(kernel_size),
-                                 float(scale_modifier), 0, int(bool(debug)))
+                                 float(scale_modifier), 0, int(bool(debug)), _lib.default_flags())
             inp = _lib.GofInputs(
                 _dev_ptr(background, device, keep), _dev_ptr(means3D, device, keep), _dev_ptr(sh, device, keep),
                 _dev_ptr(colors, device, keep), None, _dev_ptr(scales, device, keep),

@@ -62,7 +62,16 @@ typedef struct GofParams {
 	float scale_modifier;
 	int32_t prefiltered;
 	int32_t debug;          /* !=0: synchronise + check after every stage (auxiliary.h:204-211) */
+	int32_t flags;          /* GOF_FLAG_* */
 } GofParams;
+
+/* GofParams.flags.
+ * GOF_FLAG_EXACT_BLEND: evaluate the per-contributor depth mapping and normal normalisation with
+ *   the reference's IEEE double divide / double sqrt / float divides, which makes all nine output
+ *   channels bit-identical to the reference's sm_100a build.  Without it those two quantities use
+ *   float32 reciprocal arithmetic (<= 4 ulp): rgb, median depth, alpha, T and the contributor
+ *   counts stay bit-identical, normals and distortion agree to ~1e-6 (north-star bar: 1e-4). */
+#define GOF_FLAG_EXACT_BLEND 1
 
 /* Per-Gaussian inputs + camera (argument list of Rasterizer::forward). */
 typedef struct GofInputs {
