@@ -247,6 +247,8 @@ int gof_num_rendered(GofContext* ctx, const void* geom, int32_t P, gof_stream_t 
 	return GOF_OK;
 }
 
+static int ensure_gacc(GofContext* ctx, size_t need, cudaStream_t s);
+
 int gof_backward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
                  int32_t num_rendered, const int32_t* radii,
                  const void* geom, const void* binning, const void* img,
@@ -275,16 +277,12 @@ int gof_backward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
 	}
 
 	const size_t need = (size_t)P * GACC_FLOATS;
-	if (ctx->gacc_floats < need) {
-		if (ctx->gacc) { GOF_CUDA_CHECK(cudaStreamSynchronize(s)); cudaFree(ctx->gacc); ctx->gacc = nullptr; ctx->gacc_floats = 0; }
-		GOF_CUDA_CHECK(cudaMalloc(&ctx->gacc, need * sizeof(float)));
-		ctx->gacc_floats = need;
-	}
+	int rc;
+	if ((rc = ensure_gacc(ctx, need, s)) != GOF_OK) return rc;
 	std::vector<cudaEvent_t> marks;
 	GOF_PROF_MARK(ctx, marks, s);
 	GOF_CUDA_CHECK(cudaMemsetAsync(ctx->gacc, 0, need * sizeof(float), s));
 	GOF_PROF_MARK(ctx, marks, s);
-	int rc;
 	if (num_rendered > 0) {
 		if ((rc = launch_render_bwd(*prm, tile_grid, focal_x, focal_y, g, im, b, in->background, dL_dout_color, ctx->gacc, s)) != GOF_OK) return rc;
 		GOF_STAGE_CHECK(prm, s);
@@ -295,6 +293,43 @@ int gof_backward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
 	GOF_PROF_MARK(ctx, marks, s);
 	if (ctx->profiling) ctx->calls[1].push_back(std::move(marks));
 	return GOF_OK;
+}
+
+// ---- stage entry: per-Gaussian backward (K10) on its own -------------------------------------
+__global__ void pack_gacc_kernel(int P, const float* __restrict__ dv2g, const float* __restrict__ dcol, float* __restrict__ gacc)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= P) return;
+	float* g = gacc + (size_t)i * GACC_FLOATS;
+	for (int k = 0; k < 10; k++) g[k] = dv2g[(size_t)i * 10 + k];
+	for (int k = 0; k < 3; k++) g[10 + k] = dcol ? dcol[(size_t)i * 3 + k] : 0.0f;
+	for (int k = 13; k < GACC_FLOATS; k++) g[k] = 0.0f;
+}
+
+static int ensure_gacc(GofContext* ctx, size_t need, cudaStream_t s)
+{
+	if (ctx->gacc_floats < need) {
+		if (ctx->gacc) { GOF_CUDA_CHECK(cudaStreamSynchronize(s)); cudaFree(ctx->gacc); ctx->gacc = nullptr; ctx->gacc_floats = 0; }
+		GOF_CUDA_CHECK(cudaMalloc(&ctx->gacc, need * sizeof(float)));
+		ctx->gacc_floats = need;
+	}
+	return GOF_OK;
+}
+
+int gof_preprocess_backward(GofContext* ctx, const GofParams* prm, const GofInputs* in, const int32_t* radii,
+                            const void* geom, const float* dL_dview2gaussian_in, const float* dL_dcolors_in,
+                            const GofGrads* gr, gof_stream_t stream)
+{
+	if (!ctx || !prm || !in || !gr || !geom || !radii || !dL_dview2gaussian_in) { set_error("gof_preprocess_backward: NULL argument"); return GOF_EINVAL; }
+	cudaStream_t s = (cudaStream_t)stream;
+	const int P = prm->P;
+	if (P <= 0) return GOF_OK;
+	GeomState g = GeomState::carve(align_base(const_cast<void*>(geom)), (size_t)P);
+	int rc;
+	if ((rc = ensure_gacc(ctx, (size_t)P * GACC_FLOATS, s)) != GOF_OK) return rc;
+	pack_gacc_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, dL_dview2gaussian_in, dL_dcolors_in, ctx->gacc);
+	GOF_CUDA_CHECK(cudaGetLastError());
+	return launch_preprocess_bwd(*prm, *in, g, radii, ctx->gacc, *gr, s);
 }
 
 // ---- test accessor ---------------------------------------------------------------------------

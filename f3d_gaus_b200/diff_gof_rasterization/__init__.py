@@ -195,6 +195,32 @@ def state_array(name: str, P: int, W: int, H: int, R: int, geom, binning, img):
     return out
 
 
+def preprocess_backward_stage(c_means3D, radii, sh, scales, rotations, viewmatrix, campos, degree, geom,
+                              dL_dview2gaussian, dL_dcolors):
+    """Stage accessor (gof_preprocess_backward): K10 alone on caller-provided dL/dview2gaussian and
+    dL/dcolor.  Returns (dL_dmeans3D, dL_dsh, dL_dscales, dL_drotations)."""
+    device = c_means3D.device
+    P = int(c_means3D.size(0))
+    M = int(sh.size(1)) if (sh is not None and sh.numel() != 0) else 0
+    e = lambda *shape: torch.empty(shape, dtype=torch.float32, device=device)
+    g2d, gcol, gop, gm3, gcov, gsh, gsc, grot, gv2g = (e(P, 3), e(P, 3), e(P, 1), e(P, 3), e(P, 6), e(P, M, 3),
+                                                       e(P, 3), e(P, 4), e(P, 10))
+    keep: list = []
+    with torch.cuda.device(device):
+        prm = _lib.GofParams(P, int(degree), M, 16, 16, 1.0, 1.0, 0.0, 1.0, 0, 0, 0)
+        inp = _lib.GofInputs(None, _dev_ptr(c_means3D, device, keep), _dev_ptr(sh, device, keep), None, None,
+                             _dev_ptr(scales, device, keep), _dev_ptr(rotations, device, keep), None, None,
+                             _dev_ptr(viewmatrix, device, keep), None, _dev_ptr(campos, device, keep))
+        grads = _lib.GofGrads(g2d.data_ptr(), gcol.data_ptr(), gop.data_ptr(), gm3.data_ptr(), gcov.data_ptr(),
+                              gsh.data_ptr() if M > 0 else None, gsc.data_ptr(), grot.data_ptr(), gv2g.data_ptr())
+        rc = _lib.lib.gof_preprocess_backward(
+            _lib.context(device.index), ctypes.byref(prm), ctypes.byref(inp), _dev_ptr(radii, device, keep, torch.int32),
+            geom.data_ptr(), _dev_ptr(dL_dview2gaussian, device, keep), _dev_ptr(dL_dcolors, device, keep),
+            ctypes.byref(grads), torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(rc, "gof_preprocess_backward")
+    return gm3, gsh, gsc, grot
+
+
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                         view2gaussian_precomp, raster_settings):
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,

@@ -8,6 +8,7 @@
  *                           (bound by RasterizeGaussiansCUDA,      RAST/rasterize_points.cu:36-122)
  *   gof_backward         <- CudaRasterizer::Rasterizer::backward  RAST/cuda_rasterizer/rasterizer.h:61-91
  *                           (bound by RasterizeGaussiansBackwardCUDA, RAST/rasterize_points.cu:124-211)
+ *   gof_preprocess_backward <- BACKWARD::preprocess             RAST/cuda_rasterizer/backward.cu:957-1033
  *   gof_mark_visible     <- CudaRasterizer::Rasterizer::markVisible RAST/cuda_rasterizer/rasterizer.h:24-29
  *                           (bound by markVisible,                 RAST/rasterize_points.cu:213-232)
  *   gof_state_sizes      <- required<GeometryState/ImageState/BinningState>()
@@ -154,6 +155,17 @@ int gof_backward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
                  const void* geom, const void* binning, const void* img,
                  const float* dL_dout_color /* [9,H,W] */, const GofGrads* grads,
                  gof_stream_t stream);
+
+/* Stage entry: the per-Gaussian backward alone (BACKWARD::preprocess, backward.cu:957-1033):
+ * from dL/dview2gaussian [P,10] and dL/dcolor [P,3] (may be NULL) produce dL/dmeans3D, dL/dscales,
+ * dL/drotations, dL/dsh (and copy the two inputs through to grads->dL_dview2gaussian/dL_dcolors;
+ * dL_dopacity/dL_dmeans2D/dL_dcov3D are zero-filled).  `geom` is the forward's geometry blob (for the
+ * SH clamp flags).  This map is ill-conditioned at F3D-Gaus scales (the reference's own outputs move
+ * by ~10% run to run under its unordered float atomics), so parity of this stage is tested on
+ * identical inputs rather than end to end. */
+int gof_preprocess_backward(GofContext* ctx, const GofParams* prm, const GofInputs* in, const int32_t* radii,
+                            const void* geom, const float* dL_dview2gaussian_in, const float* dL_dcolors_in,
+                            const GofGrads* grads, gof_stream_t stream);
 
 int gof_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
                      const float* projmatrix, uint8_t* present /* [P] bool */, gof_stream_t stream);

@@ -543,69 +543,114 @@ void oracle_render_backward(int P, int W, int H, float tan_fovx, float tan_fovy,
 }
 
 /* ------------------------------------------------------------------ backward preprocess */
-static void dnormvdv(const float* v, const float* dv, float* out)
+/* `real` is float in libgof_oracle.so (the reference's arithmetic) and double in
+ * libgof_oracle_f64.so (oracle/Makefile: -DORACLE_REAL=double): the same formulas evaluated
+ * without float32 rounding.  dL/dscale, dL/drot, dL/dmean are catastrophically ill-conditioned
+ * functions of dL/dview2gaussian at F3D-Gaus scales, so tests measure both the reference and the
+ * CUDA kernel against this float64 evaluation instead of against each other. */
+#ifndef ORACLE_REAL
+#define ORACLE_REAL float
+#endif
+typedef ORACLE_REAL real;
+typedef struct { real c[3][3]; } m3r;
+
+int oracle_real_bytes(void) { return (int)sizeof(real); }
+
+static m3r m3r_mul(m3r a, m3r b)
 {
-	const float sum2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
-	const float inv = 1.0f / sqrtf(sum2 * sum2 * sum2);
+	m3r r;
+	for (int i = 0; i < 3; i++)
+		for (int j = 0; j < 3; j++)
+			r.c[i][j] = a.c[0][j] * b.c[i][0] + a.c[1][j] * b.c[i][1] + a.c[2][j] * b.c[i][2];
+	return r;
+}
+static m3r m3r_t(m3r a)
+{
+	m3r r;
+	for (int i = 0; i < 3; i++)
+		for (int j = 0; j < 3; j++) r.c[i][j] = a.c[j][i];
+	return r;
+}
+static void g2v_r(const float* q, const float* mean, const float* vm, m3r* Rt, real* t)
+{
+	const real r = q[0], x = q[1], y = q[2], z = q[3];
+	m3r R;
+	R.c[0][0] = 1 - 2 * (y * y + z * z); R.c[0][1] = 2 * (x * y - r * z); R.c[0][2] = 2 * (x * z + r * y);
+	R.c[1][0] = 2 * (x * y + r * z); R.c[1][1] = 1 - 2 * (x * x + z * z); R.c[1][2] = 2 * (y * z - r * x);
+	R.c[2][0] = 2 * (x * z - r * y); R.c[2][1] = 2 * (y * z + r * x); R.c[2][2] = 1 - 2 * (x * x + y * y);
+	real G2V[4][3];
+	for (int c = 0; c < 3; c++)
+		for (int j = 0; j < 3; j++)
+			G2V[c][j] = (real)vm[0 + j] * R.c[0][c] + (real)vm[4 + j] * R.c[1][c] + (real)vm[8 + j] * R.c[2][c];
+	for (int j = 0; j < 3; j++)
+		G2V[3][j] = (real)vm[0 + j] * mean[0] + (real)vm[4 + j] * mean[1] + (real)vm[8 + j] * mean[2] + vm[12 + j];
+	for (int c = 0; c < 3; c++)
+		for (int rr = 0; rr < 3; rr++) Rt->c[c][rr] = G2V[rr][c];
+	t[0] = G2V[3][0]; t[1] = G2V[3][1]; t[2] = G2V[3][2];
+}
+
+static void dnormvdv(const real* v, const real* dv, real* out)
+{
+	const real sum2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+	const real inv = (real)1 / (real)sqrt((double)(sum2 * sum2 * sum2));
 	out[0] = ((+sum2 - v[0] * v[0]) * dv[0] - v[1] * v[0] * dv[1] - v[2] * v[0] * dv[2]) * inv;
 	out[1] = (-v[0] * v[1] * dv[0] + (sum2 - v[1] * v[1]) * dv[1] - v[2] * v[1] * dv[2]) * inv;
 	out[2] = (-v[0] * v[2] * dv[0] - v[1] * v[2] * dv[1] + (sum2 - v[2] * v[2]) * dv[2]) * inv;
 }
-
 /* All outputs zero-initialised by the caller ([P,*]); dL_dcolor is the blend's colour gradient.
  * dL_dmeans/dL_dscale/dL_drot are ASSIGNED for visible Gaussians (backward.cu:494-497,570-573,585). */
 void oracle_preprocess_backward(int P, int D, int M, const float* means3D, const int32_t* radii, const float* shs,
                                 const uint8_t* clamped, const float* scales, const float* rotations, const float* vm,
-                                const float* campos, const float* dL_dv2g, const float* dL_dcolor, float* dL_dmeans,
-                                float* dL_dsh, float* dL_dscale, float* dL_drot)
+                                const float* campos, const float* dL_dv2g, const float* dL_dcolor, real* dL_dmeans,
+                                real* dL_dsh, real* dL_dscale, real* dL_drot)
 {
 #pragma omp parallel for schedule(static)
 	for (int idx = 0; idx < P; idx++) {
 		if (!(radii[idx] > 0)) continue;
 		const float* dq = dL_dv2g + 10 * (size_t)idx;
 		const float* q = rotations + 4 * idx;
-		const float r = q[0], x = q[1], y = q[2], z = q[3];
-		m3 Rt;
-		float t[3];
-		g2v(q, means3D + 3 * idx, vm, &Rt, t);
-		float t2[3];
+		const real r = q[0], x = q[1], y = q[2], z = q[3];
+		m3r Rt;
+		real t[3];
+		g2v_r(q, means3D + 3 * idx, vm, &Rt, t);
+		real t2[3];
 		for (int k = 0; k < 3; k++) t2[k] = -(Rt.c[0][k] * t[0] + Rt.c[1][k] * t[1] + Rt.c[2][k] * t[2]);
 		double Sinv[3];
 		for (int k = 0; k < 3; k++) Sinv[k] = 1.0 / ((double)scales[3 * idx + k] * scales[3 * idx + k] + 1e-7);
-		m3 SR;
+		m3r SR;
 		for (int c = 0; c < 3; c++)
-			for (int k = 0; k < 3; k++) SR.c[c][k] = (float)(Sinv[k] * (double)Rt.c[c][k]);
-		m3 dSig;
-		dSig.c[0][0] = dq[0]; dSig.c[0][1] = 0.5f * dq[1]; dSig.c[0][2] = 0.5f * dq[2];
-		dSig.c[1][0] = 0.5f * dq[1]; dSig.c[1][1] = dq[3]; dSig.c[1][2] = 0.5f * dq[4];
-		dSig.c[2][0] = 0.5f * dq[2]; dSig.c[2][1] = 0.5f * dq[4]; dSig.c[2][2] = dq[5];
-		const float dB[3] = { dq[6], dq[7], dq[8] };
-		const float dC = dq[9];
-		m3 dSR = m3_mul(Rt, dSig);
+			for (int k = 0; k < 3; k++) SR.c[c][k] = (real)(Sinv[k] * (double)Rt.c[c][k]);
+		m3r dSig;
+		dSig.c[0][0] = dq[0]; dSig.c[0][1] = (real)0.5 * dq[1]; dSig.c[0][2] = (real)0.5 * dq[2];
+		dSig.c[1][0] = (real)0.5 * dq[1]; dSig.c[1][1] = dq[3]; dSig.c[1][2] = (real)0.5 * dq[4];
+		dSig.c[2][0] = (real)0.5 * dq[2]; dSig.c[2][1] = (real)0.5 * dq[4]; dSig.c[2][2] = dq[5];
+		const real dB[3] = { dq[6], dq[7], dq[8] };
+		const real dC = dq[9];
+		m3r dSR = m3r_mul(Rt, dSig);
 		for (int c = 0; c < 3; c++)
 			for (int k = 0; k < 3; k++) dSR.c[c][k] += t2[k] * dB[c];
-		m3 dRt = m3_t(m3_mul(dSig, m3_t(SR)));
+		m3r dRt = m3r_t(m3r_mul(dSig, m3r_t(SR)));
 		for (int c = 0; c < 3; c++)
-			for (int k = 0; k < 3; k++) dRt.c[c][k] += (float)(Sinv[k] * (double)dSR.c[c][k]);
-		float dSinv[3], dt2[3];
+			for (int k = 0; k < 3; k++) dRt.c[c][k] += (real)(Sinv[k] * (double)dSR.c[c][k]);
+		real dSinv[3], dt2[3];
 		for (int k = 0; k < 3; k++) {
 			dSinv[k] = dSR.c[0][k] * Rt.c[0][k] + dSR.c[1][k] * Rt.c[1][k] + dSR.c[2][k] * Rt.c[2][k];
-			dt2[k] = (float)(2 * t2[k] * Sinv[k] * dC + dB[0] * SR.c[0][k] + dB[1] * SR.c[1][k] + dB[2] * SR.c[2][k]);
+			dt2[k] = (real)(2 * t2[k] * Sinv[k] * dC + dB[0] * SR.c[0][k] + dB[1] * SR.c[1][k] + dB[2] * SR.c[2][k]);
 			dSinv[k] += dC * t2[k] * t2[k];
-			dL_dscale[3 * idx + k] = (float)(-2 / scales[3 * idx + k] * Sinv[k] * dSinv[k]);
+			dL_dscale[3 * idx + k] = (real)(-2 / scales[3 * idx + k] * Sinv[k] * dSinv[k]);
 		}
-		m3 dG2V_R = m3_t(dRt);
+		m3r dG2V_R = m3r_t(dRt);
 		for (int c = 0; c < 3; c++)
 			for (int k = 0; k < 3; k++) dG2V_R.c[c][k] += -dt2[c] * t[k];
-		float dG2V_t[3];
+		real dG2V_t[3];
 		for (int c = 0; c < 3; c++) dG2V_t[c] = Rt.c[c][0] * -dt2[0] + Rt.c[c][1] * -dt2[1] + Rt.c[c][2] * -dt2[2];
-		float dG2W[4][3];
+		real dG2W[4][3];
 		for (int c = 0; c < 3; c++)
 			for (int k = 0; k < 3; k++)
 				dG2W[c][k] = vm[4 * k + 0] * dG2V_R.c[c][0] + vm[4 * k + 1] * dG2V_R.c[c][1] + vm[4 * k + 2] * dG2V_R.c[c][2];
 		for (int k = 0; k < 3; k++)
 			dG2W[3][k] = vm[4 * k + 0] * dG2V_t[0] + vm[4 * k + 1] * dG2V_t[1] + vm[4 * k + 2] * dG2V_t[2];
-		float dmean[3] = { dG2W[3][0], dG2W[3][1], dG2W[3][2] };
+		real dmean[3] = { dG2W[3][0], dG2W[3][1], dG2W[3][2] };
 #define MT(a, b) dG2W[a][b]
 		dL_drot[4 * idx + 0] = 2 * z * (MT(0, 1) - MT(1, 0)) + 2 * y * (MT(2, 0) - MT(0, 2)) + 2 * x * (MT(1, 2) - MT(2, 1));
 		dL_drot[4 * idx + 1] = 2 * y * (MT(1, 0) + MT(0, 1)) + 2 * z * (MT(2, 0) + MT(0, 2)) + 2 * r * (MT(1, 2) - MT(2, 1)) - 4 * x * (MT(2, 2) + MT(1, 1));
@@ -615,15 +660,15 @@ void oracle_preprocess_backward(int P, int D, int M, const float* means3D, const
 
 		if (shs) {
 			const float* sh = shs + (size_t)idx * M * 3;
-			float* dsh = dL_dsh + (size_t)idx * M * 3;
-			const float dir_orig[3] = { means3D[3 * idx] - campos[0], means3D[3 * idx + 1] - campos[1], means3D[3 * idx + 2] - campos[2] };
-			const float len = sqrtf(dir_orig[0] * dir_orig[0] + dir_orig[1] * dir_orig[1] + dir_orig[2] * dir_orig[2]);
-			const float dx_ = dir_orig[0] / len, dy_ = dir_orig[1] / len, dz_ = dir_orig[2] / len;
-			const float X = dx_, Y = dy_, Z = dz_;
-			float ddir[3] = { 0, 0, 0 };
+			real* dsh = dL_dsh + (size_t)idx * M * 3;
+			const real dir_orig[3] = { (real)means3D[3 * idx] - campos[0], (real)means3D[3 * idx + 1] - campos[1], (real)means3D[3 * idx + 2] - campos[2] };
+			const real len = (real)sqrt((double)(dir_orig[0] * dir_orig[0] + dir_orig[1] * dir_orig[1] + dir_orig[2] * dir_orig[2]));
+			const real dx_ = dir_orig[0] / len, dy_ = dir_orig[1] / len, dz_ = dir_orig[2] / len;
+			const real X = dx_, Y = dy_, Z = dz_;
+			real ddir[3] = { 0, 0, 0 };
 			for (int ch = 0; ch < 3; ch++) {
-				const float g = dL_dcolor[3 * idx + ch] * (clamped[3 * idx + ch] ? 0.f : 1.f);
-				float ddx = 0, ddy = 0, ddz = 0;
+				const real g = dL_dcolor[3 * idx + ch] * (clamped[3 * idx + ch] ? 0.f : 1.f);
+				real ddx = 0, ddy = 0, ddz = 0;
 #define SHV(k) sh[3 * (k) + ch]
 #define DSH(k) dsh[3 * (k) + ch]
 				DSH(0) = SH_C0 * g;
@@ -631,7 +676,7 @@ void oracle_preprocess_backward(int P, int D, int M, const float* means3D, const
 					DSH(1) = -SH_C1 * Y * g; DSH(2) = SH_C1 * Z * g; DSH(3) = -SH_C1 * X * g;
 					ddx = -SH_C1 * SHV(3); ddy = -SH_C1 * SHV(1); ddz = SH_C1 * SHV(2);
 					if (D > 1) {
-						const float xx = X * X, yy = Y * Y, zz = Z * Z, xy = X * Y, yz = Y * Z, xz = X * Z;
+						const real xx = X * X, yy = Y * Y, zz = Z * Z, xy = X * Y, yz = Y * Z, xz = X * Z;
 						DSH(4) = SH_C2[0] * xy * g; DSH(5) = SH_C2[1] * yz * g; DSH(6) = SH_C2[2] * (2.f * zz - xx - yy) * g;
 						DSH(7) = SH_C2[3] * xz * g; DSH(8) = SH_C2[4] * (xx - yy) * g;
 						ddx += SH_C2[0] * Y * SHV(4) + SH_C2[2] * 2.f * -X * SHV(6) + SH_C2[3] * Z * SHV(7) + SH_C2[4] * 2.f * X * SHV(8);
@@ -659,7 +704,7 @@ void oracle_preprocess_backward(int P, int D, int M, const float* means3D, const
 #undef DSH
 				ddir[0] += ddx * g; ddir[1] += ddy * g; ddir[2] += ddz * g;
 			}
-			float add[3];
+			real add[3];
 			dnormvdv(dir_orig, ddir, add);
 			dmean[0] += add[0]; dmean[1] += add[1]; dmean[2] += add[2];
 		}

@@ -11,14 +11,16 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "oracle", "_ref", "libgof_oracle.so")
+LIB64 = os.path.join(ROOT, "oracle", "_ref", "libgof_oracle_f64.so")
 _lib = None
+_lib64 = None
 
 
 def lib():
     global _lib
     if _lib is None:
         src = os.path.join(ROOT, "oracle", "gof_oracle.c")
-        if not os.path.exists(LIB) or os.path.getmtime(src) > os.path.getmtime(LIB):
+        if not os.path.exists(LIB) or not os.path.exists(LIB64) or os.path.getmtime(src) > os.path.getmtime(LIB):
             subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True, capture_output=True)
         L = ctypes.CDLL(LIB)
         L.oracle_num_threads.restype = c_int
@@ -26,6 +28,16 @@ def lib():
         L.oracle_binning.restype = c_int
         _lib = L
     return _lib
+
+
+def lib64():
+    """The float64 build of the backward preprocess (conditioning reference)."""
+    global _lib64
+    if _lib64 is None:
+        lib()   # (re)builds both
+        _lib64 = ctypes.CDLL(LIB64)
+        assert _lib64.oracle_real_bytes() == 8
+    return _lib64
 
 
 def _p(a):
@@ -103,15 +115,17 @@ def render_backward(c, ranges, point_list, v2g, conic_opacity, means2D, features
     return out
 
 
-def preprocess_backward(c, radii, clamped, dL_dv2g, dL_dcolor) -> dict:
+def preprocess_backward(c, radii, clamped, dL_dv2g, dL_dcolor, f64: bool = False) -> dict:
+    """f64=True: same formulas, float32 inputs, arithmetic and outputs in double."""
     P = c["means3D"].shape[0]
     shs = _f(c.get("shs"))
     M = shs.shape[1] if shs is not None else 0
-    out = {"dL_dmeans3D": np.zeros((P, 3), np.float32), "dL_dsh": np.zeros((P, M, 3), np.float32),
-           "dL_dscales": np.zeros((P, 3), np.float32), "dL_drotations": np.zeros((P, 4), np.float32)}
+    dt = np.float64 if f64 else np.float32
+    out = {"dL_dmeans3D": np.zeros((P, 3), dt), "dL_dsh": np.zeros((P, M, 3), dt),
+           "dL_dscales": np.zeros((P, 3), dt), "dL_drotations": np.zeros((P, 4), dt)}
     keep = [_f(c["means3D"]), np.ascontiguousarray(radii, np.int32), shs, np.ascontiguousarray(clamped, np.uint8),
             _f(c["scales"]), _f(c["rotations"]), _f(c["viewmatrix"]), _f(c["campos"]), _f(dL_dv2g), _f(dL_dcolor)]
-    lib().oracle_preprocess_backward(c_int(P), c_int(int(c["D"])), c_int(M), *[_p(k) for k in keep],
+    (lib64() if f64 else lib()).oracle_preprocess_backward(c_int(P), c_int(int(c["D"])), c_int(M), *[_p(k) for k in keep],
                                      _p(out["dL_dmeans3D"]), _p(out["dL_dsh"]) if M else None,
                                      _p(out["dL_dscales"]), _p(out["dL_drotations"]))
     return out

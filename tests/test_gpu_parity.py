@@ -116,25 +116,72 @@ BWD_CASES = ["f3d_s64_r256_view2", "f3d_s256_r256_canon", "f3d_s256_r256_view2",
             ["golden_" + n for n in cases.GOLDEN_CASES]
 
 
+# Outputs of the backward BLEND (K9) are well-conditioned sums: 1e-3 relative, element-wise.
+BLEND_GRADS = ["dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dcov3D", "dL_dsh", "dL_dview2gaussian"]
+# Outputs of the backward PREPROCESS (K10) through the quadric are linear in dL/dview2gaussian but
+# catastrophically ill-conditioned at F3D-Gaus scales (cancellation of ~1e6): the reference differs
+# from ITSELF run to run by 4e-2..2e-1 relative L2 in dL/dscale because its float atomics are
+# unordered (test_reference_backward_self_consistency, tools/diag_bwd.py).
+QUADRIC_GRADS = ["dL_dmeans3D", "dL_dscales", "dL_drotations"]
+
+
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return (a - b).norm().item() / max(b.norm().item(), 1e-30)
+
+
 @needs_ref
 @pytest.mark.parametrize("name", BWD_CASES)
 def test_backward(name):
+    import oracle_cpu
+    from f3d_gaus_b200.diff_gof_rasterization import preprocess_backward_stage
     c = FWD_CASES[name]("cuda")
     dL = cases.grad_seed(c)
-    r = refgpu.RefRun()
-    r.forward(c, decode_state=False)
-    ref = r.backward(c, dL)
+    refs = []
+    for _ in range(2):
+        r = refgpu.RefRun()
+        r.forward(c, decode_state=False)
+        refs.append(r.backward(c, dL))
+    ref = refs[0]
     o = refgpu.OursRun()
-    o.forward(c, decode_state=False)
+    of = o.forward(c, decode_state=True)
     ours = o.backward(c, dL)
-    for k in refgpu.GRAD_NAMES:
+    # (1) blend backward: the north-star bar, element-wise
+    for k in BLEND_GRADS:
         grad_close(k, ours[k], ref[k])
+    # (2,3) per-Gaussian backward alone, on the REFERENCE's own dL/dview2gaussian and dL/dcolor (what its
+    #     K10 consumed): both implementations are measured against the same formulas evaluated in
+    #     double on the CPU (oracle/_ref/libgof_oracle_f64.so); ours must be as close as the reference.
+    if c.get("scales") is None:
+        return
+    e = torch.Tensor([])
+    _, radii, geom, _, _ = o.saved
+    gm3, gsh, gsc, grot = preprocess_backward_stage(c["means3D"], radii, c.get("shs", e), c["scales"], c["rotations"],
+                                                    c["viewmatrix"], c["campos"], c["D"], geom,
+                                                    ref["dL_dview2gaussian"], ref["dL_dcolors"])
+    torch.cuda.synchronize()
+    cn = oracle_cpu.case_to_numpy(c)
+    n = lambda t: t.detach().cpu().numpy()
+    clamped = n(of["clamped"]) if c.get("shs") is not None else n(torch.zeros_like(of["clamped"]))
+    ex = oracle_cpu.preprocess_backward(cn, n(radii), clamped, n(ref["dL_dview2gaussian"]), n(ref["dL_dcolors"]), f64=True)
+    stage = {"dL_dmeans3D": gm3, "dL_dscales": gsc, "dL_drotations": grot}
+    for k in QUADRIC_GRADS:
+        exact = torch.from_numpy(ex[k])
+        e_ref, e_ours = rel_l2(ref[k].cpu(), exact), rel_l2(stage[k].cpu(), exact)
+        assert e_ours <= 2 * e_ref + 1e-3, f"{k}: ours {e_ours:.3e} vs reference {e_ref:.3e} from the float64 value"
+        # (2) end to end: within the bar, or indistinguishable from the reference's own float32 noise
+        #     (run-to-run atomics order, and its rounding distance from the float64 value)
+        noise = max(rel_l2(refs[1][k], ref[k]), e_ref)
+        e = rel_l2(ours[k], ref[k])
+        assert e <= 1e-3 + 8 * noise, f"{k}: end-to-end rel L2 {e:.3e} vs reference float32 noise {noise:.3e}"
+    if c.get("shs") is not None:
+        grad_close("dL_dsh(stage)", gsh, ref["dL_dsh"])
 
 
 @needs_ref
 def test_reference_backward_self_consistency():
-    """How far the reference is from itself run-to-run (unordered float atomics): context for the
-    1e-3 bar above."""
+    """How far the reference is from itself run-to-run (unordered float atomics): the blend outputs
+    repeat to ~1e-7, the quadric outputs do not -- context for test_backward."""
     c = FWD_CASES["f3d_s256_r256_view2"]("cuda")
     dL = cases.grad_seed(c)
     outs = []
@@ -142,8 +189,10 @@ def test_reference_backward_self_consistency():
         r = refgpu.RefRun()
         r.forward(c, decode_state=False)
         outs.append(r.backward(c, dL))
-    for k in refgpu.GRAD_NAMES:
+    for k in BLEND_GRADS:
         grad_close(k, outs[0][k], outs[1][k])
+    for k in QUADRIC_GRADS:
+        print(k, "reference run-to-run rel L2:", rel_l2(outs[0][k], outs[1][k]))
 
 
 def test_all_culled_and_empty():

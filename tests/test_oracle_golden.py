@@ -108,9 +108,15 @@ def test_preprocess_backward_vs_golden(path):
     if "shs" in c:
         assert rel_l2(pb["dL_dsh"], g["bwd_dL_dsh"]) <= 1e-5
     assert rel_l2(pb["dL_dmeans3D"], g["bwd_dL_dmeans3D"]) <= 5e-3
-    # scale / rotation: same order of magnitude and sign pattern, tolerance = conditioning-limited
-    for k in ("dL_dscales", "dL_drotations"):
-        assert rel_l2(pb[k], g["bwd_" + k]) <= 0.5, k
+    # scale / rotation / mean: measure BOTH against the same formulas evaluated in double
+    # (libgof_oracle_f64.so).  The float32 restatement must be as close to that value as the
+    # reference's own float32 build is (x3 for the different contraction choices), plus the 1e-3 bar.
+    cl = g["fwd_clamped"] if "shs" in c else np.zeros((len(g["fwd_radii"]), 3), np.uint8)
+    ex = oracle_cpu.preprocess_backward(c, g["fwd_radii"], cl, g["bwd_dL_dview2gaussian"], g["bwd_dL_dcolors"], f64=True)
+    for k in ("dL_dmeans3D", "dL_dscales", "dL_drotations"):
+        e_ref, e_port = rel_l2(g["bwd_" + k], ex[k]), rel_l2(pb[k], ex[k])
+        assert e_port <= 3 * e_ref + 1e-3, (k, e_port, e_ref)
+        assert e_ref <= 0.2, (k, e_ref)      # the float64 evaluation really is the reference's formula
     # culled Gaussians get exactly zero
     hid = ~(g["fwd_radii"] > 0)
     for k in pb:

@@ -1,0 +1,18 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, both bench arms, kernel launch list, ncu full capture of the blends.
+# Usage (from the repo root, under gpurun): bash tools/gpu_round.sh [tag]
+TAG=${1:-r01}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.txt 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log
+tail -5 $OUT/pytest_gpu.log
+timeout 600 python bench.py --impl reference > $OUT/bench_reference.json 2> $OUT/bench_reference.err
+timeout 600 python bench.py > $OUT/bench_ours.json 2> $OUT/bench_ours.err
+cat $OUT/bench_reference.json $OUT/bench_ours.json
+timeout 300 python tools/quick_bench.py 256 256 50 > $OUT/quick_bench.log 2>&1; cat $OUT/quick_bench.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/launches_bench.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'render_fwd_kernel|render_bwd_kernel' -s 16 -c 4 \
+    -o $OUT/prof_blend python tools/quick_bench.py 256 256 3 > $OUT/ncu_full.log 2>&1
+ls -la $OUT
