@@ -64,7 +64,7 @@ int gof_context_create(int device, GofContext** out)
 	GOF_CUDA_CHECK(cudaSetDevice(device));
 	GofContext* c = new GofContext();
 	c->device = device;
-	cudaError_t e = cudaMallocHost(&c->pinned, 64);
+	cudaError_t e = cudaMallocHost(&c->pinned, (MAILBOX_HEAD + GOF_MAX_VIEWS) * sizeof(int32_t));
 	if (e != cudaSuccess) { delete c; set_error("cudaMallocHost failed: %s", cudaGetErrorString(e)); return GOF_ECUDA; }
 	*out = c;
 	return GOF_OK;
@@ -117,43 +117,64 @@ int gof_profile_read(GofContext* ctx, double* fwd_ms, int64_t* fwd_calls, double
 	return GOF_OK;
 }
 
-int gof_state_sizes(int32_t P, int32_t W, int32_t H, int64_t num_rendered,
-                    size_t* geom_bytes, size_t* img_bytes, size_t* binning_bytes)
+static Frame make_frame(const GofParams* prm, int V)
 {
-	if (P < 0 || W <= 0 || H <= 0 || num_rendered < 0) { set_error("gof_state_sizes: bad sizes"); return GOF_EINVAL; }
+	Frame f;
+	f.P = prm->P; f.V = V; f.W = prm->W; f.H = prm->H;
+	f.grid = dim3((prm->W + TILE_X - 1) / TILE_X, (prm->H + TILE_Y - 1) / TILE_Y, 1);
+	f.T = (int)(f.grid.x * f.grid.y);
+	f.focal_y = prm->H / (2.0f * prm->tan_fovy);
+	f.focal_x = prm->W / (2.0f * prm->tan_fovx);
+	return f;
+}
+
+int gof_state_sizes_batch(int32_t P, int32_t W, int32_t H, int32_t V, int64_t num_rendered,
+                          size_t* geom_bytes, size_t* img_bytes, size_t* binning_bytes)
+{
+	if (P < 0 || W <= 0 || H <= 0 || V <= 0 || num_rendered < 0) { set_error("gof_state_sizes: bad sizes"); return GOF_EINVAL; }
 	const size_t T = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
-	if (geom_bytes) *geom_bytes = GeomState::carve(nullptr, (size_t)P).total;
-	if (img_bytes) *img_bytes = ImgState::carve(nullptr, (size_t)W * H, T).total;
+	if (geom_bytes) *geom_bytes = GeomState::carve(nullptr, (size_t)P, (size_t)V).total;
+	if (img_bytes) *img_bytes = ImgState::carve(nullptr, (size_t)W * H, T, (size_t)V).total;
 	if (binning_bytes) *binning_bytes = BinState::carve(nullptr, (size_t)num_rendered).total;
 	return GOF_OK;
 }
 
-static char* align_base(void* p) { return reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(p))); }
-
-// Device-side hand-off of R for the sync-free mode: mailbox[0] = R, mailbox[1] = overflow.
-__global__ void publish_num_rendered(const uint32_t* point_offsets, int P, int64_t capacity, int32_t* mailbox)
+int gof_state_sizes(int32_t P, int32_t W, int32_t H, int64_t num_rendered,
+                    size_t* geom_bytes, size_t* img_bytes, size_t* binning_bytes)
 {
-	const uint32_t R = point_offsets[P - 1];
-	mailbox[0] = (int32_t)R;
-	mailbox[1] = ((int64_t)R > capacity) ? 1 : 0;
+	return gof_state_sizes_batch(P, W, H, 1, num_rendered, geom_bytes, img_bytes, binning_bytes);
 }
 
-int gof_forward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
-                void* geom, size_t geom_bytes, void* img, size_t img_bytes,
-                void* binning, size_t binning_bytes, GofAllocFn alloc, void* alloc_user,
-                float* out_color, int32_t* radii,
-                int32_t* num_rendered, void** binning_out, gof_stream_t stream)
+static char* align_base(const void* p) { return reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(p))); }
+
+// Largest R whose binning layout fits in `bytes` (host arithmetic only).
+static int64_t binning_capacity(size_t bytes)
+{
+	int64_t lo = 0, hi = (int64_t)1 << 31;
+	while (lo + 1 < hi) {
+		const int64_t mid = (lo + hi) / 2;
+		if (BinState::carve(nullptr, (size_t)mid).total <= bytes) lo = mid; else hi = mid;
+	}
+	return lo;
+}
+
+int gof_forward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* in, int32_t V, int32_t bg_stride,
+                      void* geom, size_t geom_bytes, void* img, size_t img_bytes,
+                      void* binning, size_t binning_bytes, GofAllocFn alloc, void* alloc_user,
+                      float* out_color, int32_t* radii,
+                      int32_t* num_rendered, void** binning_out, gof_stream_t stream)
 {
 	if (!ctx || !prm || !in) { set_error("gof_forward: NULL argument"); return GOF_EINVAL; }
 	cudaStream_t s = (cudaStream_t)stream;
 	const int P = prm->P, W = prm->W, H = prm->H;
-	if (W <= 0 || H <= 0 || P < 0) { set_error("gof_forward: bad sizes P=%d W=%d H=%d", P, W, H); return GOF_EINVAL; }
+	if (W <= 0 || H <= 0 || P < 0 || V <= 0) { set_error("gof_forward: bad sizes P=%d W=%d H=%d V=%d", P, W, H, V); return GOF_EINVAL; }
+	if (V > GOF_MAX_VIEWS) { set_error("gof_forward: at most %d views per batch", GOF_MAX_VIEWS); return GOF_EINVAL; }
 	if (!out_color) { set_error("gof_forward: out_color is NULL"); return GOF_EINVAL; }
-	if (num_rendered) *num_rendered = 0;
+	if (num_rendered) for (int v = 0; v < V; v++) num_rendered[v] = 0;
 	if (binning_out) *binning_out = binning;
 	const size_t N = (size_t)W * H;
 	if (P == 0) {   // rasterize_points.cu:85: nothing is launched, outputs stay zero
-		GOF_CUDA_CHECK(cudaMemsetAsync(out_color, 0, N * OUT_CH * sizeof(float), s));
+		GOF_CUDA_CHECK(cudaMemsetAsync(out_color, 0, (size_t)V * N * OUT_CH * sizeof(float), s));
 		return GOF_OK;
 	}
 	if (!in->means3D || !in->opacities || !in->viewmatrix || !in->projmatrix || !in->campos || !in->background || !radii) {
@@ -172,77 +193,83 @@ int gof_forward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
 		set_error("gof_forward: cov3D_precomp needs view2gaussian_precomp (no scales/rotations to build the quadric)");
 		return GOF_EINVAL;
 	}
+	if (in->view2gaussian_precomp && V > 1) {
+		set_error("gof_forward_batch: view2gaussian_precomp is per view; use V == 1");
+		return GOF_EINVAL;
+	}
 	if (in->shs && prm->M < (prm->D + 1) * (prm->D + 1)) {
 		set_error("gof_forward: sh has %d coefficients, degree %d needs %d", prm->M, prm->D, (prm->D + 1) * (prm->D + 1));
 		return GOF_EINVAL;
 	}
 
-	const dim3 tile_grid((W + TILE_X - 1) / TILE_X, (H + TILE_Y - 1) / TILE_Y, 1);
-	const size_t T = (size_t)tile_grid.x * tile_grid.y;
-	const float focal_y = H / (2.0f * prm->tan_fovy);
-	const float focal_x = W / (2.0f * prm->tan_fovx);
-
-	GeomState g = GeomState::carve(align_base(geom), (size_t)P);
-	ImgState im = ImgState::carve(align_base(img), N, T);
+	const Frame f = make_frame(prm, V);
+	GeomState g = GeomState::carve(align_base(geom), (size_t)P, (size_t)V);
+	ImgState im = ImgState::carve(align_base(img), N, (size_t)f.T, (size_t)V);
 	if (!geom || g.total > geom_bytes) { set_error("gof_forward: geom blob too small (%zu < %zu)", geom_bytes, g.total); return GOF_ENOMEM; }
 	if (!img || im.total > img_bytes) { set_error("gof_forward: img blob too small (%zu < %zu)", img_bytes, im.total); return GOF_ENOMEM; }
 
 	int rc;
 	std::vector<cudaEvent_t> marks;
 	GOF_PROF_MARK(ctx, marks, s);
-	if ((rc = launch_preprocess(*prm, *in, focal_x, focal_y, tile_grid, g, radii, s)) != GOF_OK) return rc;
-	GOF_STAGE_CHECK(prm, s);
-	GOF_PROF_MARK(ctx, marks, s);
-	if ((rc = launch_scan(g, P, s)) != GOF_OK) return rc;
+	if ((rc = launch_preprocess(*prm, *in, f, g, im, radii, s)) != GOF_OK) return rc;
 	GOF_STAGE_CHECK(prm, s);
 	GOF_PROF_MARK(ctx, marks, s);
 
-	int R;
+	int64_t capacity;
 	BinState b;
 	if (binning != nullptr) {
-		// sync-free mode: capacity is whatever fits in the caller's blob
-		int64_t lo = 0, hi = (int64_t)1 << 31;
-		while (lo + 1 < hi) {   // largest R whose layout fits (host arithmetic only)
-			const int64_t mid = (lo + hi) / 2;
-			if (BinState::carve(nullptr, (size_t)mid).total <= binning_bytes) lo = mid; else hi = mid;
-		}
-		R = (int)lo;
-		publish_num_rendered<<<1, 1, 0, s>>>(g.point_offsets, P, lo, g.mailbox);
-		GOF_CUDA_CHECK(cudaGetLastError());
-		set_error("gof_forward: sync-free binning is not available in this build");
-		return GOF_EINVAL;
+		// sync-free mode: capacity is whatever fits in the caller's blob; R stays on the device
+		capacity = binning_capacity(binning_bytes - (size_t)(align_base(binning) - (char*)binning));
+		if ((rc = launch_tile_scan(f, g, im, capacity, s)) != GOF_OK) return rc;
+		GOF_STAGE_CHECK(prm, s);
+		GOF_PROF_MARK(ctx, marks, s);
+		b = BinState::carve(align_base(binning), (size_t)capacity);
+		if (num_rendered) for (int v = 0; v < V; v++) num_rendered[v] = -1;
 	} else {
 		if (!alloc) { set_error("gof_forward: neither a binning blob nor an allocation callback"); return GOF_EINVAL; }
-		GOF_CUDA_CHECK(cudaMemcpyAsync(ctx->pinned, g.point_offsets + P - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+		if ((rc = launch_tile_scan(f, g, im, (int64_t)1 << 40, s)) != GOF_OK) return rc;
+		GOF_STAGE_CHECK(prm, s);
+		GOF_PROF_MARK(ctx, marks, s);
+		GOF_CUDA_CHECK(cudaMemcpyAsync(ctx->pinned, g.mailbox, (MAILBOX_HEAD + V) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
 		GOF_CUDA_CHECK(cudaStreamSynchronize(s));
-		R = ctx->pinned[0];
-		const size_t need = BinState::carve(nullptr, (size_t)R).total;
+		capacity = ctx->pinned[0];
+		if (num_rendered) for (int v = 0; v < V; v++) num_rendered[v] = ctx->pinned[MAILBOX_HEAD + v];
+		const size_t need = BinState::carve(nullptr, (size_t)capacity).total;
 		void* blob = alloc(alloc_user, need);
 		if (!blob) { set_error("gof_forward: binning allocation callback returned NULL for %zu bytes", need); return GOF_ENOMEM; }
 		if (binning_out) *binning_out = blob;
-		b = BinState::carve(align_base(blob), (size_t)R);
+		b = BinState::carve(align_base(blob), (size_t)capacity);
 	}
-	if (num_rendered) *num_rendered = R;
 
 	GOF_PROF_MARK(ctx, marks, s);   // after the num_rendered hand-off
-	if ((rc = launch_binning(*prm, tile_grid, g, im, b, radii, R, s)) != GOF_OK) return rc;
+	if ((rc = launch_binning(f, g, im, b, capacity, s)) != GOF_OK) return rc;
 	GOF_STAGE_CHECK(prm, s);
 	GOF_PROF_MARK(ctx, marks, s);
-	if ((rc = launch_render_fwd(*prm, tile_grid, focal_x, focal_y, im, b, in->background, out_color, s)) != GOF_OK) return rc;
+	if ((rc = launch_render_fwd(*prm, f, im, b, in->background, bg_stride, out_color, s)) != GOF_OK) return rc;
 	GOF_STAGE_CHECK(prm, s);
 	GOF_PROF_MARK(ctx, marks, s);
 	if (ctx->profiling) ctx->calls[0].push_back(std::move(marks));
 	return GOF_OK;
 }
 
-int gof_num_rendered(GofContext* ctx, const void* geom, int32_t P, gof_stream_t stream, int32_t* num_rendered)
+int gof_forward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
+                void* geom, size_t geom_bytes, void* img, size_t img_bytes,
+                void* binning, size_t binning_bytes, GofAllocFn alloc, void* alloc_user,
+                float* out_color, int32_t* radii,
+                int32_t* num_rendered, void** binning_out, gof_stream_t stream)
 {
-	if (!ctx || !geom || !num_rendered || P <= 0) { set_error("gof_num_rendered: bad argument"); return GOF_EINVAL; }
+	return gof_forward_batch(ctx, prm, in, 1, 0, geom, geom_bytes, img, img_bytes, binning, binning_bytes, alloc, alloc_user,
+	                         out_color, radii, num_rendered, binning_out, stream);
+}
+
+int gof_num_rendered(GofContext* ctx, const void* geom, int32_t P, int32_t V, gof_stream_t stream, int32_t* num_rendered)
+{
+	if (!ctx || !geom || !num_rendered || P <= 0 || V <= 0 || V > GOF_MAX_VIEWS) { set_error("gof_num_rendered: bad argument"); return GOF_EINVAL; }
 	cudaStream_t s = (cudaStream_t)stream;
-	GeomState g = GeomState::carve(align_base(const_cast<void*>(geom)), (size_t)P);
-	GOF_CUDA_CHECK(cudaMemcpyAsync(ctx->pinned, g.mailbox, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+	GeomState g = GeomState::carve(align_base(geom), (size_t)P, (size_t)V);
+	GOF_CUDA_CHECK(cudaMemcpyAsync(ctx->pinned, g.mailbox, (MAILBOX_HEAD + V) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
 	GOF_CUDA_CHECK(cudaStreamSynchronize(s));
-	*num_rendered = ctx->pinned[0];
+	for (int v = 0; v < V; v++) num_rendered[v] = ctx->pinned[MAILBOX_HEAD + v];
 	if (ctx->pinned[1]) { set_error("num_rendered=%d exceeded the binning capacity", ctx->pinned[0]); return GOF_EOVERFLOW; }
 	return GOF_OK;
 }
@@ -264,16 +291,13 @@ int gof_backward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
 		set_error("gof_backward: a gradient output pointer is NULL");
 		return GOF_EINVAL;
 	}
-	const dim3 tile_grid((W + TILE_X - 1) / TILE_X, (H + TILE_Y - 1) / TILE_Y, 1);
-	const size_t T = (size_t)tile_grid.x * tile_grid.y;
-	const float focal_y = H / (2.0f * prm->tan_fovy);
-	const float focal_x = W / (2.0f * prm->tan_fovx);
-	GeomState g = GeomState::carve(align_base(const_cast<void*>(geom)), (size_t)P);
-	ImgState im = ImgState::carve(align_base(const_cast<void*>(img)), (size_t)W * H, T);
+	const Frame f = make_frame(prm, 1);
+	GeomState g = GeomState::carve(align_base(geom), (size_t)P, 1);
+	ImgState im = ImgState::carve(align_base(img), (size_t)W * H, (size_t)f.T, 1);
 	BinState b{};
 	if (num_rendered > 0) {
 		if (!binning) { set_error("gof_backward: binning blob is NULL but num_rendered=%d", num_rendered); return GOF_EINVAL; }
-		b = BinState::carve(align_base(const_cast<void*>(binning)), (size_t)num_rendered);
+		b = BinState::carve(align_base(binning), (size_t)num_rendered);
 	}
 
 	const size_t need = (size_t)P * GACC_FLOATS;
@@ -284,7 +308,7 @@ int gof_backward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
 	GOF_CUDA_CHECK(cudaMemsetAsync(ctx->gacc, 0, need * sizeof(float), s));
 	GOF_PROF_MARK(ctx, marks, s);
 	if (num_rendered > 0) {
-		if ((rc = launch_render_bwd(*prm, tile_grid, focal_x, focal_y, g, im, b, in->background, dL_dout_color, ctx->gacc, s)) != GOF_OK) return rc;
+		if ((rc = launch_render_bwd(*prm, f, g, im, b, in->background, dL_dout_color, ctx->gacc, s)) != GOF_OK) return rc;
 		GOF_STAGE_CHECK(prm, s);
 	}
 	GOF_PROF_MARK(ctx, marks, s);
@@ -324,7 +348,7 @@ int gof_preprocess_backward(GofContext* ctx, const GofParams* prm, const GofInpu
 	cudaStream_t s = (cudaStream_t)stream;
 	const int P = prm->P;
 	if (P <= 0) return GOF_OK;
-	GeomState g = GeomState::carve(align_base(const_cast<void*>(geom)), (size_t)P);
+	GeomState g = GeomState::carve(align_base(geom), (size_t)P, 1);
 	int rc;
 	if ((rc = ensure_gacc(ctx, (size_t)P * GACC_FLOATS, s)) != GOF_OK) return rc;
 	pack_gacc_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, dL_dview2gaussian_in, dL_dcolors_in, ctx->gacc);
@@ -333,63 +357,69 @@ int gof_preprocess_backward(GofContext* ctx, const GofParams* prm, const GofInpu
 }
 
 // ---- test accessor ---------------------------------------------------------------------------
-__global__ void extract_v2g_kernel(int P, const float* rec, float* v2g, float* rgb)
+int64_t gof_state_get_batch(const char* name, int32_t P, int32_t W, int32_t H, int32_t V, int64_t R,
+                            const void* geom, const void* binning, const void* img,
+                            void* dst, int64_t dst_bytes, gof_stream_t stream)
 {
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= P) return;
-	if (v2g) for (int k = 0; k < 10; k++) v2g[(size_t)i * 10 + k] = rec[(size_t)i * REC_FLOATS + k];
-	if (rgb) for (int k = 0; k < 3; k++) rgb[(size_t)i * 3 + k] = rec[(size_t)i * REC_FLOATS + REC_RGB + k];
+	if (!name) { set_error("gof_state_get: NULL name"); return GOF_EINVAL; }
+	if (P < 0 || W <= 0 || H <= 0 || V <= 0 || R < 0) { set_error("gof_state_get: bad sizes"); return GOF_EINVAL; }
+	cudaStream_t s = (cudaStream_t)stream;
+	GofParams prm{};
+	prm.P = P; prm.W = W; prm.H = H; prm.tan_fovx = prm.tan_fovy = 1.0f;
+	const Frame f = make_frame(&prm, V);
+	const size_t N = (size_t)W * H, n = (size_t)P * V, VT = (size_t)V * f.T;
+	GeomState g = GeomState::carve(align_base(geom), (size_t)P, (size_t)V);
+	ImgState im = ImgState::carve(align_base(img), N, (size_t)f.T, (size_t)V);
+	BinState b = BinState::carve(align_base(binning), (size_t)R);
+	const std::string nm(name);
+	const void* src = nullptr;
+	size_t bytes = 0;
+	bool kernel = false;
+	if (nm == "depths") { src = g.depths; bytes = n * 4; }
+	else if (nm == "means2D") { src = g.means2D; bytes = n * 8; }
+	else if (nm == "conic_opacity") { src = g.conic_opacity; bytes = n * 16; }
+	else if (nm == "clamped") { src = g.clamped; bytes = n * 3; }
+	else if (nm == "tiles_touched") { src = g.tiles_touched; bytes = n * 4; }
+	else if (nm == "final_T") { src = im.final_T; bytes = (size_t)V * N * 16; }
+	else if (nm == "n_contrib") { src = im.n_contrib; bytes = (size_t)V * N * 8; }
+	else if (nm == "ranges") { src = im.ranges; bytes = VT * 8; }
+	else if (nm == "point_list") { src = b.point_list; bytes = (size_t)R * 4; }
+	else if (nm == "point_offsets") { kernel = true; bytes = n * 4; }
+	else if (nm == "point_list_keys") { kernel = true; bytes = (size_t)R * 8; }
+	else if (nm == "view2gaussian") { kernel = true; bytes = n * 40; }
+	else if (nm == "rgb") { kernel = true; bytes = n * 12; }
+	else { set_error("gof_state_get: unknown array '%s'", name); return GOF_EINVAL; }
+	if (dst && bytes) {
+		if ((int64_t)bytes > dst_bytes) { set_error("gof_state_get: dst too small"); return GOF_ENOMEM; }
+		if (kernel) {
+			const char* what = nm == "point_offsets" ? "o" : nm == "point_list_keys" ? "k" : nm == "view2gaussian" ? "v" : "r";
+			const int rc = launch_extract(what, f, g, im, b, R, dst, s);
+			if (rc != GOF_OK) return rc;
+		} else {
+			GOF_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
+		}
+	}
+	return (int64_t)bytes;
 }
 
 int64_t gof_state_get(const char* name, int32_t P, int32_t W, int32_t H, int64_t R,
                       const void* geom, const void* binning, const void* img,
                       void* dst, int64_t dst_bytes, gof_stream_t stream)
 {
-	if (!name) { set_error("gof_state_get: NULL name"); return GOF_EINVAL; }
-	cudaStream_t s = (cudaStream_t)stream;
-	const size_t N = (size_t)W * H;
-	const size_t T = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
-	GeomState g = GeomState::carve(align_base(const_cast<void*>(geom)), (size_t)P);
-	ImgState im = ImgState::carve(align_base(const_cast<void*>(img)), N, T);
-	BinState b = BinState::carve(align_base(const_cast<void*>(binning)), (size_t)R);
-	const std::string n(name);
-	const void* src = nullptr;
-	size_t bytes = 0;
-	if (n == "depths") { src = g.depths; bytes = (size_t)P * 4; }
-	else if (n == "means2D") { src = g.means2D; bytes = (size_t)P * 8; }
-	else if (n == "conic_opacity") { src = g.conic_opacity; bytes = (size_t)P * 16; }
-	else if (n == "clamped") { src = g.clamped; bytes = (size_t)P * 3; }
-	else if (n == "tiles_touched") { src = g.tiles_touched; bytes = (size_t)P * 4; }
-	else if (n == "point_offsets") { src = g.point_offsets; bytes = (size_t)P * 4; }
-	else if (n == "final_T") { src = im.final_T; bytes = N * 16; }
-	else if (n == "n_contrib") { src = im.n_contrib; bytes = N * 8; }
-	else if (n == "ranges") { src = im.ranges; bytes = T * 8; }
-	else if (n == "point_list") { src = b.point_list; bytes = (size_t)R * 4; }
-	else if (n == "point_list_keys") { src = b.keys; bytes = (size_t)R * 8; }
-	else if (n == "view2gaussian" || n == "rgb") {
-		bytes = (size_t)P * (n == "rgb" ? 12 : 40);
-		if (dst) {
-			if ((int64_t)bytes > dst_bytes) { set_error("gof_state_get: dst too small"); return GOF_ENOMEM; }
-			if (P > 0) {
-				extract_v2g_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, g.rec, n == "rgb" ? nullptr : (float*)dst, n == "rgb" ? (float*)dst : nullptr);
-				GOF_CUDA_CHECK(cudaGetLastError());
-			}
-		}
-		return (int64_t)bytes;
-	} else { set_error("gof_state_get: unknown array '%s'", name); return GOF_EINVAL; }
-	if (dst) {
-		if ((int64_t)bytes > dst_bytes) { set_error("gof_state_get: dst too small"); return GOF_ENOMEM; }
-		if (bytes) GOF_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
-	}
-	return (int64_t)bytes;
+	return gof_state_get_batch(name, P, W, H, 1, R, geom, binning, img, dst, dst_bytes, stream);
 }
 
 // ---- fused L2 epilogue -----------------------------------------------------------------------
 // One thread per pixel; see gof_b200.h.  c2w = inverse of the (column-vector) world->view
 // matrix A|t with A[r][c] = vm[4c+r], t[r] = vm[12+r]  (src/gaussian_renderer/__init__.py:881-909).
-__global__ void epilogue_kernel(const float* __restrict__ out_color, const float* __restrict__ vm, int W, int H,
-                                float fx, float fy, float* __restrict__ normal_world, float* __restrict__ depth_normal)
+__global__ void epilogue_kernel(const float* __restrict__ out_color_all, const float* __restrict__ vm_all, int W, int H,
+                                float fx, float fy, float* __restrict__ normal_world_all, float* __restrict__ depth_normal_all)
 {
+	const size_t NN = (size_t)W * H;
+	const float* out_color = out_color_all + (size_t)blockIdx.z * OUT_CH * NN;
+	const float* vm = vm_all + 16 * blockIdx.z;
+	float* normal_world = normal_world_all ? normal_world_all + (size_t)blockIdx.z * 3 * NN : nullptr;
+	float* depth_normal = depth_normal_all ? depth_normal_all + (size_t)blockIdx.z * 3 * NN : nullptr;
 	__shared__ float s_Ai[9], s_o[3];
 	if (threadIdx.x == 0) {
 		float A[3][3];
@@ -455,10 +485,16 @@ __global__ void epilogue_kernel(const float* __restrict__ out_color, const float
 int gof_render_epilogue(const float* out_color, const float* viewmatrix, int32_t W, int32_t H,
                         float fovx, float fovy, float* normal_world, float* depth_normal, gof_stream_t stream)
 {
-	if (!out_color || !viewmatrix || W <= 0 || H <= 0) { set_error("gof_render_epilogue: bad argument"); return GOF_EINVAL; }
+	return gof_render_epilogue_batch(out_color, viewmatrix, 1, W, H, fovx, fovy, normal_world, depth_normal, stream);
+}
+
+int gof_render_epilogue_batch(const float* out_color, const float* viewmatrix, int32_t V, int32_t W, int32_t H,
+                              float fovx, float fovy, float* normal_world, float* depth_normal, gof_stream_t stream)
+{
+	if (!out_color || !viewmatrix || W <= 0 || H <= 0 || V <= 0) { set_error("gof_render_epilogue: bad argument"); return GOF_EINVAL; }
 	const float fx = W / (2.f * tanf(fovx / 2.f));
 	const float fy = H / (2.f * tanf(fovy / 2.f));
-	dim3 grid((W + 127) / 128, H);
+	dim3 grid((W + 127) / 128, H, V);
 	epilogue_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(out_color, viewmatrix, W, H, fx, fy, normal_world, depth_normal);
 	GOF_CUDA_CHECK(cudaGetLastError());
 	return GOF_OK;

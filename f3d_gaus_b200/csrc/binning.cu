@@ -1,35 +1,30 @@
-// binning.cu -- tile binning: offsets scan (K2), key/value duplication (K4), stable radix
-// sort (K5), tile ranges (K6/K7) and the tile-ordered slab gather.
+// binning.cu -- tile binning for a batch of V views: tile-count scan (K2/K6/K7), bucket scatter
+// (K4) and per-tile sort fused with the slab gather (K5 + the tile-ordered record stream).
 //
-// Replaces cub::DeviceScan::InclusiveSum + duplicateWithKeys + cub::DeviceRadixSort::SortPairs
-// + identifyTileRanges of the reference (RAST/cuda_rasterizer/rasterizer_impl.cu:70-111,
-// 149-171,332-373).  Integer contract (bit-exact): key = (tile_id << 32) | float_bits(depth),
-// value = Gaussian index, emitted y-major per Gaussian in index order; stable sort on the low
-// 32+bit bits (bit = "higher MSB" of the tile count, rasterizer_impl.cu:35-50); ranges[tile] =
-// [first,last+1), (0,0) for untouched tiles.
-//
-// On top of the reference's outputs this stage writes the tile-ordered *slab*: the 64-byte
-// blend record of every sorted duplicate, contiguous per tile, so that the blend kernels can
-// stream a tile's Gaussians with TMA bulk copies instead of gathering through point_list.
+// Replaces cub::DeviceScan::InclusiveSum + duplicateWithKeys + cub::DeviceRadixSort::SortPairs +
+// identifyTileRanges of the reference (RAST/cuda_rasterizer/rasterizer_impl.cu:70-111,149-171,
+// 332-373).  The reference's contract is the ORDER of each tile's list: the 64-bit key
+// (tile << 32 | float_bits(depth)) sorted ascending by a stable sort, ties keeping the emission
+// order, which is ascending Gaussian index.  That order is reproduced exactly, but not by a
+// global radix sort over 41..43 key bits:
+//   1. the preprocess already counted, per tile, how many Gaussians touch it (one atomic per
+//      duplicate); tile_scan_kernel turns the counts into ranges[tile] = [first, last+1) -- the
+//      result identifyTileRanges extracts from the sorted keys -- plus the batch's num_rendered;
+//   2. scatter_kernel drops (float_bits(depth) << 32 | index) of every duplicate into its tile's
+//      bucket (slot claimed with an atomic; arrival order is irrelevant because)
+//   3. tile_sort_gather_kernel sorts each bucket by that 64-bit value: depth first, index second.
+//      All values of a bucket are distinct, so the result is THE stable order of the reference.
+//      A bucket is ~700 entries at F3D-Gaus sizes: one CTA sorts it in shared memory with a
+//      bitonic network (buckets above the shared-memory capacity are sorted in place in global
+//      memory by the same network).  The same CTA then writes point_list and the tile-ordered
+//      96-byte slab records, including the tile-local conic pre-test coefficients (conic.cuh).
+// HBM/L2 traffic per duplicate: 8 B written + 8 B read for the bucket entry, 64 B gathered,
+// 100 B written -- versus ~13 passes over 12-byte pairs for the 6-pass LSD sort it replaces, and
+// three launches instead of twelve.
 #include "gof_common.cuh"
-#include <cub/cub.cuh>
+#include "conic.cuh"
 
 namespace gof {
-
-size_t scan_temp_bytes(size_t P)
-{
-	size_t bytes = 0;
-	cub::DeviceScan::InclusiveSum(nullptr, bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)P);
-	return bytes;
-}
-
-size_t sort_temp_bytes(size_t R)
-{
-	size_t bytes = 0;
-	cub::DeviceRadixSort::SortPairs(nullptr, bytes, (uint64_t*)nullptr, (uint64_t*)nullptr,
-	                                (uint32_t*)nullptr, (uint32_t*)nullptr, (int)R);
-	return bytes;
-}
 
 template <typename T>
 static void take(char*& p, T*& ptr, size_t count)
@@ -39,31 +34,32 @@ static void take(char*& p, T*& ptr, size_t count)
 	p += count * sizeof(T);
 }
 
-GeomState GeomState::carve(char* base, size_t P)
+GeomState GeomState::carve(char* base, size_t P, size_t V)
 {
 	GeomState g;
 	char* p = base;
-	take(p, g.depths, P);
-	take(p, g.means2D, P);
-	take(p, g.conic_opacity, P);
-	take(p, g.rec, P * REC_FLOATS);
-	take(p, g.tiles_touched, P);
-	take(p, g.point_offsets, P);
-	take(p, g.clamped, P * 3);
-	take(p, g.mailbox, 4);
-	g.scan_temp_bytes = gof::scan_temp_bytes(P);
-	take(p, g.scan_temp, g.scan_temp_bytes);
+	const size_t n = P * V;
+	take(p, g.depths, n);
+	take(p, g.means2D, n);
+	take(p, g.conic_opacity, n);
+	take(p, g.rec, n * REC_FLOATS);
+	take(p, g.tiles_touched, n);
+	take(p, g.rect, n);
+	take(p, g.clamped, n * 3);
+	take(p, g.mailbox, MAILBOX_HEAD + V);
 	g.total = align_up((size_t)(p - base)) + ALIGN;
 	return g;
 }
 
-ImgState ImgState::carve(char* base, size_t N, size_t T)
+ImgState ImgState::carve(char* base, size_t N, size_t T, size_t V)
 {
 	ImgState im;
 	char* p = base;
-	take(p, im.final_T, 4 * N);
-	take(p, im.n_contrib, 2 * N);
-	take(p, im.ranges, T);
+	take(p, im.final_T, 4 * N * V);
+	take(p, im.n_contrib, 2 * N * V);
+	take(p, im.ranges, T * V);
+	take(p, im.tile_counts, T * V);
+	take(p, im.tile_cursor, T * V);
 	im.total = align_up((size_t)(p - base)) + ALIGN;
 	return im;
 }
@@ -72,100 +68,245 @@ BinState BinState::carve(char* base, size_t R)
 {
 	BinState b;
 	char* p = base;
-	take(p, b.keys_unsorted, R);
-	take(p, b.keys, R);
-	take(p, b.vals_unsorted, R);
+	take(p, b.entries, R);
 	take(p, b.point_list, R);
-	take(p, b.slab, R * REC_FLOATS);
-	b.sort_temp_bytes = gof::sort_temp_bytes(R);
-	take(p, b.sort_temp, b.sort_temp_bytes);
+	take(p, b.slab, R * SLAB_FLOATS);
 	b.total = align_up((size_t)(p - base)) + ALIGN;
 	return b;
 }
 
 namespace {
 
-// Smallest b with (n >> b) == 0 found by the reference's halving search
-// (rasterizer_impl.cu:35-50); restated, it returns floor(log2 n) + 1 for n >= 1.
-uint32_t higher_msb(uint32_t n)
+constexpr int SCAN_THREADS = 1024;
+
+// One CTA: exclusive scan of the V*T tile counts.  ranges[t] = (start, start+count), (0,0) for empty
+// tiles (the reference memsets ranges and only touched tiles are written, rasterizer_impl.cu:365).
+// mailbox = {R_total, overflow, max count, 0, R_view[0..V-1]}.
+__global__ void __launch_bounds__(SCAN_THREADS)
+tile_scan_kernel(int VT, int T, int V, const uint32_t* __restrict__ counts, uint2* __restrict__ ranges,
+                 uint32_t* __restrict__ cursor, int32_t* __restrict__ mailbox, long long capacity)
 {
-	uint32_t msb = sizeof(n) * 4, step = msb;
-	while (step > 1) {
-		step /= 2;
-		if (n >> msb) msb += step; else msb -= step;
+	__shared__ uint32_t s_part[SCAN_THREADS];
+	__shared__ uint32_t s_max[SCAN_THREADS / 32];
+	const int tid = threadIdx.x;
+	const int per = (VT + SCAN_THREADS - 1) / SCAN_THREADS;
+	const int lo = min(VT, tid * per), hi = min(VT, lo + per);
+	uint32_t sum = 0, mx = 0;
+	for (int i = lo; i < hi; i++) { const uint32_t c = counts[i]; sum += c; mx = max(mx, c); }
+	s_part[tid] = sum;
+	mx = __reduce_max_sync(0xffffffffu, mx);
+	if ((tid & 31) == 0) s_max[tid >> 5] = mx;
+	__syncthreads();
+	// Hillis-Steele inclusive scan over the 1024 partials
+	for (int off = 1; off < SCAN_THREADS; off <<= 1) {
+		const uint32_t v = (tid >= off) ? s_part[tid - off] : 0;
+		__syncthreads();
+		s_part[tid] += v;
+		__syncthreads();
 	}
-	if (n >> msb) msb++;
-	return msb;
+	uint32_t run = s_part[tid] - sum;   // exclusive prefix of this thread's chunk
+	for (int i = lo; i < hi; i++) {
+		const uint32_t c = counts[i];
+		ranges[i] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
+		cursor[i] = run;
+		run += c;
+		// a view's last tile: R of that view = end of its last tile - start of its first
+		if ((i + 1) % T == 0) mailbox[MAILBOX_HEAD + i / T] = (int32_t)run;   // inclusive prefix; differenced below
+	}
+	__syncthreads();
+	if (tid == 0) {
+		const uint32_t total = s_part[SCAN_THREADS - 1];
+		uint32_t m = 0;
+		for (int k = 0; k < SCAN_THREADS / 32; k++) m = max(m, s_max[k]);
+		mailbox[0] = (int32_t)total;
+		mailbox[1] = ((long long)total > capacity) ? 1 : 0;
+		mailbox[2] = (int32_t)m;
+		mailbox[3] = 0;
+		int32_t prev = 0;
+		for (int v = 0; v < V; v++) {   // per-view R from the inclusive prefixes written above
+			const int32_t inc = mailbox[MAILBOX_HEAD + v];
+			mailbox[MAILBOX_HEAD + v] = inc - prev;
+			prev = inc;
+		}
+	}
 }
 
-__global__ void duplicate_kernel(int P, const float2* __restrict__ means2D, const float* __restrict__ depths,
-                                 const uint32_t* __restrict__ offsets, uint64_t* __restrict__ keys,
-                                 uint32_t* __restrict__ vals, const int* __restrict__ radii, dim3 grid)
+// One thread per (view, Gaussian): claim a slot in every touched tile's bucket.
+__global__ void __launch_bounds__(256)
+scatter_kernel(int P, int T, dim3 grid, const uint32_t* __restrict__ tiles_touched, const ushort4* __restrict__ rect,
+               const float* __restrict__ depths, uint32_t* __restrict__ cursor, uint64_t* __restrict__ entries,
+               const int32_t* __restrict__ mailbox)
 {
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= P) return;
-	const int rad = radii[idx];
-	if (rad <= 0) return;
-	uint32_t off = (idx == 0) ? 0 : offsets[idx - 1];
-	const float2 p = means2D[idx];
-	const uint32_t x0 = min(grid.x, max((int)0, (int)((p.x - rad) / TILE_X)));
-	const uint32_t y0 = min(grid.y, max((int)0, (int)((p.y - rad) / TILE_Y)));
-	const uint32_t x1 = min(grid.x, max((int)0, (int)((p.x + rad + TILE_X - 1) / TILE_X)));
-	const uint32_t y1 = min(grid.y, max((int)0, (int)((p.y + rad + TILE_Y - 1) / TILE_Y)));
-	const uint64_t dbits = __float_as_uint(depths[idx]);
-	for (uint32_t y = y0; y < y1; y++)
-		for (uint32_t x = x0; x < x1; x++) {
-			keys[off] = ((uint64_t)(y * grid.x + x) << 32) | dbits;
-			vals[off] = idx;
-			off++;
+	if (mailbox[1]) return;   // binning capacity exceeded (sync-free mode): outputs are invalid, write nothing
+	const int view = blockIdx.y;
+	const size_t g = (size_t)view * P + idx;
+	if (tiles_touched[g] == 0) return;
+	const ushort4 r = rect[g];
+	const uint64_t e = ((uint64_t)__float_as_uint(depths[g]) << 32) | (uint32_t)idx;
+	uint32_t* cur = cursor + (size_t)view * T;
+	for (uint32_t y = r.y; y < r.w; y++)
+		for (uint32_t x = r.x; x < r.z; x++) {
+			const uint32_t slot = atomicAdd(&cur[y * grid.x + x], 1u);
+			entries[slot] = e;
 		}
 }
 
-// One thread per sorted duplicate: tile-range boundaries + gather of the blend record.
-__global__ void ranges_gather_kernel(int L, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ point_list,
-                                     const float* __restrict__ rec, uint2* __restrict__ ranges, float* __restrict__ slab)
-{
-	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= L) return;
-	const uint32_t tile = keys[idx] >> 32;
-	if (idx == 0) ranges[tile].x = 0;
-	else {
-		const uint32_t prev = keys[idx - 1] >> 32;
-		if (tile != prev) { ranges[prev].y = idx; ranges[tile].x = idx; }
-	}
-	if (idx == L - 1) ranges[tile].y = L;
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_CAP = 4096;   // bucket entries sorted in shared memory (32 KB)
 
-	const uint32_t id = point_list[idx];
-	const float4* src = reinterpret_cast<const float4*>(rec + (size_t)id * REC_FLOATS);
-	float4* dst = reinterpret_cast<float4*>(slab + (size_t)idx * REC_FLOATS);
-	float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3);
-	dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = d;
+// Bitonic network with the "flip" first stage of every merge, so that every compare-exchange puts
+// the smaller value at the lower index.  Entries at index >= n are virtual +inf and never move,
+// which makes the network valid for any n (no padding writes).
+__device__ __forceinline__ void bitonic_sort(uint64_t* a, int n, int npad)
+{
+	for (int k = 2; k <= npad; k <<= 1) {
+		for (int j = k >> 1; j > 0; j >>= 1) {
+			for (int t = threadIdx.x; t < (npad >> 1); t += SORT_THREADS) {
+				// t-th compare-exchange of this step: i = lower index, l = partner
+				const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+				const int l = (j == (k >> 1)) ? (i ^ (k - 1)) : (i | j);
+				if (l < n) {
+					const uint64_t x = a[i], y = a[l];
+					if (x > y) { a[i] = y; a[l] = x; }
+				}
+			}
+			__syncthreads();
+		}
+	}
+}
+
+// One CTA per tile of the batch: sort the bucket, write point_list and the slab.
+__global__ void __launch_bounds__(SORT_THREADS)
+tile_sort_gather_kernel(int P, int T, dim3 grid, int W, int H, float focal_x, float focal_y,
+                        const uint2* __restrict__ ranges, uint64_t* __restrict__ entries,
+                        const float* __restrict__ rec_all, uint32_t* __restrict__ point_list,
+                        float* __restrict__ slab, const int32_t* __restrict__ mailbox)
+{
+	__shared__ uint64_t s_e[SORT_CAP];
+	if (mailbox[1]) return;
+	const int gt = blockIdx.x;            // global tile index: view * T + tile
+	const uint2 range = ranges[gt];
+	const int n = (int)(range.y - range.x);
+	if (n <= 0) return;
+	const int view = gt / T, tile = gt - view * T;
+	const int ty = tile / grid.x, tx = tile - ty * grid.x;
+	uint64_t* bucket = entries + range.x;
+
+	int npad = 1;
+	while (npad < n) npad <<= 1;
+	uint64_t* a;
+	if (n <= SORT_CAP) {
+		for (int i = threadIdx.x; i < n; i += SORT_THREADS) s_e[i] = bucket[i];
+		a = s_e;
+	} else {
+		a = bucket;   // oversized bucket: same network, in place in global memory
+	}
+	__syncthreads();
+	if (n > 1) bitonic_sort(a, n, npad);
+
+	const TileRays tr = tile_rays(tx, ty, W, H, focal_x, focal_y);
+	const float* rec = rec_all + (size_t)view * P * REC_FLOATS;
+	for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
+		const uint64_t e = a[i];
+		const uint32_t id = (uint32_t)e;
+		if (n <= SORT_CAP) bucket[i] = e;        // keep the sorted keys (test accessor: point_list_keys)
+		point_list[range.x + i] = id;
+		const float4* src = reinterpret_cast<const float4*>(rec + (size_t)id * REC_FLOATS);
+		const float4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2), q3 = __ldg(src + 3);
+		float c[6];
+		conic_coefficients(q0, q1, q2, tr, c);
+		float4* dst = reinterpret_cast<float4*>(slab + (size_t)(range.x + i) * SLAB_FLOATS);
+		dst[0] = make_float4(c[0], c[1], c[2], c[3]);
+		dst[1] = make_float4(c[4], c[5], q2.z, q2.w);          // tau, w
+		dst[2] = q0;                                           // Sxx Sxy Sxz Syy
+		dst[3] = q1;                                           // Syz Szz Bx By
+		dst[4] = make_float4(q2.x, q2.y, q3.x, q3.y);          // Bz C r g
+		dst[5] = make_float4(q3.z, q3.w, 0.0f, 0.0f);          // b id
+	}
+}
+
+// ---- test accessors --------------------------------------------------------------------------
+__global__ void extract_rec_kernel(size_t n, const float* __restrict__ rec, float* __restrict__ v2g, float* __restrict__ rgb)
+{
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	if (v2g) for (int k = 0; k < 10; k++) v2g[i * 10 + k] = rec[i * REC_FLOATS + k];
+	if (rgb) for (int k = 0; k < 3; k++) rgb[i * 3 + k] = rec[i * REC_FLOATS + REC_RGB + k];
+}
+
+// point_list_keys as the reference stores them: (tile << 32) | float_bits(depth), per view tile ids.
+__global__ void extract_keys_kernel(int VT, int T, const uint2* __restrict__ ranges, const uint64_t* __restrict__ entries,
+                                    uint64_t* __restrict__ keys)
+{
+	const int gt = blockIdx.x;
+	const uint2 r = ranges[gt];
+	const uint64_t tile = (uint64_t)(gt % T);
+	for (uint32_t i = r.x + threadIdx.x; i < r.y; i += blockDim.x) keys[i] = (tile << 32) | (entries[i] >> 32);
+}
+
+// Inclusive scan of tiles_touched per view (the reference's point_offsets); single CTA per view.
+__global__ void __launch_bounds__(1024)
+extract_offsets_kernel(int P, const uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ offsets)
+{
+	__shared__ uint32_t s_part[1024];
+	const int tid = threadIdx.x;
+	const uint32_t* tt = tiles_touched + (size_t)blockIdx.x * P;
+	uint32_t* out = offsets + (size_t)blockIdx.x * P;
+	const int per = (P + 1023) / 1024;
+	const int lo = min(P, tid * per), hi = min(P, lo + per);
+	uint32_t sum = 0;
+	for (int i = lo; i < hi; i++) sum += tt[i];
+	s_part[tid] = sum;
+	__syncthreads();
+	for (int off = 1; off < 1024; off <<= 1) {
+		const uint32_t v = (tid >= off) ? s_part[tid - off] : 0;
+		__syncthreads();
+		s_part[tid] += v;
+		__syncthreads();
+	}
+	uint32_t run = s_part[tid] - sum;
+	for (int i = lo; i < hi; i++) { run += tt[i]; out[i] = run; }
 }
 
 }  // namespace
 
-int launch_scan(const GeomState& g, int P, cudaStream_t s)
+int launch_tile_scan(const Frame& f, const GeomState& g, const ImgState& im, int64_t capacity, cudaStream_t s)
 {
-	size_t bytes = g.scan_temp_bytes;
-	GOF_CUDA_CHECK(cub::DeviceScan::InclusiveSum(g.scan_temp, bytes, g.tiles_touched, g.point_offsets, P, s));
+	tile_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(f.V * f.T, f.T, f.V, im.tile_counts, im.ranges, im.tile_cursor, g.mailbox,
+	                                            (long long)capacity);
+	GOF_CUDA_CHECK(cudaGetLastError());
 	return GOF_OK;
 }
 
-int launch_binning(const GofParams& prm, dim3 tile_grid, const GeomState& g, const ImgState& im,
-                   const BinState& b, const int32_t* radii, int R, cudaStream_t s)
+int launch_binning(const Frame& f, const GeomState& g, const ImgState& im, const BinState& b, int64_t capacity,
+                   cudaStream_t s)
 {
-	const int P = prm.P;
-	const int T = tile_grid.x * tile_grid.y;
-	GOF_CUDA_CHECK(cudaMemsetAsync(im.ranges, 0, (size_t)T * sizeof(uint2), s));
-	if (R <= 0) return GOF_OK;
-	duplicate_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, g.means2D, g.depths, g.point_offsets, b.keys_unsorted,
-	                                                 b.vals_unsorted, radii, tile_grid);
+	if (capacity <= 0) return GOF_OK;
+	dim3 blocks((f.P + 255) / 256, f.V);
+	scatter_kernel<<<blocks, 256, 0, s>>>(f.P, f.T, f.grid, g.tiles_touched, g.rect, g.depths, im.tile_cursor, b.entries,
+	                                      g.mailbox);
 	GOF_CUDA_CHECK(cudaGetLastError());
-	const int bit = higher_msb(T);
-	size_t bytes = b.sort_temp_bytes;
-	GOF_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(b.sort_temp, bytes, b.keys_unsorted, b.keys, b.vals_unsorted,
-	                                               b.point_list, R, 0, 32 + bit, s));
-	ranges_gather_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, b.keys, b.point_list, g.rec, im.ranges, b.slab);
+	tile_sort_gather_kernel<<<f.V * f.T, SORT_THREADS, 0, s>>>(f.P, f.T, f.grid, f.W, f.H, f.focal_x, f.focal_y, im.ranges,
+	                                                           b.entries, g.rec, b.point_list, b.slab, g.mailbox);
+	GOF_CUDA_CHECK(cudaGetLastError());
+	return GOF_OK;
+}
+
+int launch_extract(const char* what, const Frame& f, const GeomState& g, const ImgState& im, const BinState& b,
+                   int64_t R, void* dst, cudaStream_t s)
+{
+	const size_t n = (size_t)f.P * f.V;
+	const char w = what[0];
+	if (w == 'v' || w == 'r') {          // view2gaussian / rgb
+		if (n) extract_rec_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, g.rec, w == 'v' ? (float*)dst : nullptr,
+		                                                                      w == 'r' ? (float*)dst : nullptr);
+	} else if (w == 'k') {               // point_list_keys
+		if (R > 0) extract_keys_kernel<<<f.V * f.T, 128, 0, s>>>(f.V * f.T, f.T, im.ranges, b.entries, (uint64_t*)dst);
+	} else if (w == 'o') {               // point_offsets
+		if (n) extract_offsets_kernel<<<f.V, 1024, 0, s>>>(f.P, g.tiles_touched, (uint32_t*)dst);
+	}
 	GOF_CUDA_CHECK(cudaGetLastError());
 	return GOF_OK;
 }

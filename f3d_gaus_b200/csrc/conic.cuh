@@ -1,0 +1,136 @@
+// conic.cuh -- the tile-local conic pre-test of the blend kernels.
+//
+// For one (Gaussian, tile) duplicate the reference evaluates, at every pixel of the tile
+// (forward.cu:502-535), mv = C - BB^2/(4 AA) from float32 AA = r^T Sigma r and BB = 2 b.r with the
+// pixel ray r = (rx, ry, 1), and the pair can only contribute if mv <= tau (tau: record field,
+// see blend_math.cuh).  With AA > 0 that is
+//        f(r) = (b.r)^2 - (C - tau') (r^T Sigma r) >= 0,
+// a CONIC in the ray, hence a quadratic polynomial in the tile-local pixel coordinates
+// (x, y) in [0,15]^2 because rx = x/fx + const, ry = y/fy + const.  Its six coefficients are
+// computed here once per duplicate, in double (the difference of the two ~1e9 terms is resolved
+// before anything is rounded to float32), normalised by AA at the tile centre, and the blend
+// evaluates g(x,y) = c0 + x (c1 + c3 x + c4 y) + y (c2 + c5 y) with five FMAs per pixel and skips
+// the pair iff g < 0.
+//
+// Soundness (a pair the reference blends is never skipped).  Let mv_ref be the value the
+// reference computes and mv* the exact value of the same expression at the exact affine ray.
+//   (1) mv_ref <= tau is necessary for contributing (blend_math.cuh).
+//   (2) |mv_ref - mv*| <= E, with E a forward error bound of the reference's float32 evaluation
+//       (3 roundings per n_k, 3 more for AA, 4 for BB, 1 ulp for each ray component):
+//           |dAA| <= 10u Abar,  |dBB| <= 5u Bbar,  u = 2^-24,
+//           Abar = sum_k N_k rho_k, N_k = sum_j |S_kj| rho_j, Bbar = 2 sum_j |B_j| rho_j  (rho = max |ray| in the tile)
+//           |dq|  <= (bmax dBB + dBB^2/4)/AAlo + Q' dAA/(AAlo - dAA),   Q' = (bmax + dBB/2)^2/AAlo
+//       with AAlo / bmax rigorous bounds of AA / |b.r| over the tile's ray box (q = BB^2/(4AA));
+//       E = 1.25x that.  tau' = tau + E, so mv_ref <= tau  =>  mv* <= tau'  =>  f >= 0.
+//   (3) the float32 evaluation of g differs from its exact value by at most eta (5 FMAs on
+//       coefficients rounded once, |x|,|y| <= 15), which is added to c0.
+// Whenever a bound cannot be established (AAlo <= 0, relative perturbations not small, non-finite
+// values) the coefficients are set to "never skip" (c0 = +big, others 0); NaNs make `g < 0` false.
+#pragma once
+#include "gof_common.cuh"
+
+namespace gof {
+
+struct TileRays {
+	double ax, bx, ay, by;     // rx = ax * x + bx, ry = ay * y + by for tile-local pixel x, y in [0, 15]
+	double rcx, rcy, hx, hy;   // centre and half-widths of the tile's ray box
+	double rhox, rhoy;         // max |rx|, max |ry| over the tile
+};
+
+__device__ __forceinline__ TileRays tile_rays(int tx, int ty, int W, int H, float focal_x, float focal_y)
+{
+	TileRays t;
+	t.ax = 1.0 / (double)focal_x;
+	t.ay = 1.0 / (double)focal_y;
+	t.bx = ((double)(tx * TILE_X) + 0.5 - W / 2.) / (double)focal_x;
+	t.by = ((double)(ty * TILE_Y) + 0.5 - H / 2.) / (double)focal_y;
+	const double rxh = t.bx + (TILE_X - 1) * t.ax, ryh = t.by + (TILE_Y - 1) * t.ay;
+	t.rcx = 0.5 * (t.bx + rxh);
+	t.rcy = 0.5 * (t.by + ryh);
+	t.hx = 0.5 * (rxh - t.bx);
+	t.hy = 0.5 * (ryh - t.by);
+	t.rhox = fmax(fabs(t.bx), fabs(rxh));
+	t.rhoy = fmax(fabs(t.by), fabs(ryh));
+	return t;
+}
+
+// q0 = (Sxx, Sxy, Sxz, Syy), q1 = (Syz, Szz, Bx, By), q2 = (Bz, C, tau, w)
+__device__ __forceinline__ void conic_coefficients(const float4& q0, const float4& q1, const float4& q2,
+                                                   const TileRays& t, float* c)
+{
+	const double u = 5.9604644775390625e-08;   // 2^-24
+	const double Sxx = q0.x, Sxy = q0.y, Sxz = q0.z, Syy = q0.w, Syz = q1.x, Szz = q1.y;
+	const double Bx = q1.z, By = q1.w, Bz = q2.x, C = q2.y, tau = q2.z;
+
+	// AA at the tile centre and a lower bound over the tile's ray box
+	const double n0c = Sxx * t.rcx + Sxy * t.rcy + Sxz;
+	const double n1c = Sxy * t.rcx + Syy * t.rcy + Syz;
+	const double n2c = Sxz * t.rcx + Syz * t.rcy + Szz;
+	const double AAc = n0c * t.rcx + n1c * t.rcy + n2c;
+	const double AAlo = AAc - 2.0 * (t.hx * fabs(n0c) + t.hy * fabs(n1c))
+	                    - (fabs(Sxx) * t.hx * t.hx + 2.0 * fabs(Sxy) * t.hx * t.hy + fabs(Syy) * t.hy * t.hy);
+	// magnitudes that scale the reference's float32 rounding errors
+	const double N0 = fabs(Sxx) * t.rhox + fabs(Sxy) * t.rhoy + fabs(Sxz);
+	const double N1 = fabs(Sxy) * t.rhox + fabs(Syy) * t.rhoy + fabs(Syz);
+	const double N2 = fabs(Sxz) * t.rhox + fabs(Syz) * t.rhoy + fabs(Szz);
+	const double Abar = N0 * t.rhox + N1 * t.rhoy + N2;
+	const double Bbar = 2.0 * (fabs(Bx) * t.rhox + fabs(By) * t.rhoy + fabs(Bz));
+	const double bmax = fabs(Bx * t.rcx + By * t.rcy + Bz) + t.hx * fabs(Bx) + t.hy * fabs(By);
+
+	bool ok = (AAlo > 0.0) && (AAc > 0.0) && (tau < 1.0e37);
+	const double dAA = 10.0 * u * Abar, dBB = 5.0 * u * Bbar;
+	ok = ok && (dAA < 0.5 * AAlo);
+	const double AAl = ok ? AAlo : 1.0;
+	// |q_ref - q*| for q = BB^2/(4 AA), |BB| <= 2 bmax, AA >= AAl, perturbed by (dBB, dAA): exact, not first order
+	const double E_bb = (bmax * dBB + 0.25 * dBB * dBB) / AAl;
+	const double Qp = (bmax + 0.5 * dBB) * (bmax + 0.5 * dBB) / AAl;
+	const double E_aa = Qp * dAA / (AAl - (ok ? dAA : 0.0));
+	const double E = 1.25 * (E_bb + E_aa);
+	const double K = C - (tau + E);
+
+	// polynomial expansion in tile-local pixel coordinates
+	const double p = Bx * t.ax, q = By * t.ay, r0 = Bx * t.bx + By * t.by + Bz;
+	const double a_xx = Sxx * t.ax * t.ax, a_xy = 2.0 * Sxy * t.ax * t.ay, a_yy = Syy * t.ay * t.ay;
+	const double a_x = 2.0 * t.ax * (Sxx * t.bx + Sxy * t.by + Sxz);
+	const double a_y = 2.0 * t.ay * (Syy * t.by + Sxy * t.bx + Syz);
+	const double a_0 = Sxx * t.bx * t.bx + 2.0 * Sxy * t.bx * t.by + Syy * t.by * t.by + 2.0 * Sxz * t.bx + 2.0 * Syz * t.by + Szz;
+	const double inv = 1.0 / (ok ? AAc : 1.0);
+	const double c0 = (r0 * r0 - K * a_0) * inv;
+	const double c1 = (2.0 * p * r0 - K * a_x) * inv;
+	const double c2 = (2.0 * q * r0 - K * a_y) * inv;
+	const double c3 = (p * p - K * a_xx) * inv;
+	const double c4 = (2.0 * p * q - K * a_xy) * inv;
+	const double c5 = (q * q - K * a_yy) * inv;
+	const double m = 15.0;
+	// float32 evaluation error of g (+ the double rounding of the expansion itself, which works on
+	// terms of magnitude (r0^2 + |K| a_0)/AAc and their x, y analogues)
+	const double eta = 8.0 * u * (fabs(c0) + m * (fabs(c1) + fabs(c2)) + m * m * (fabs(c3) + fabs(c4) + fabs(c5)))
+	                 + 1.0e-13 * inv * ((r0 * r0 + fabs(K) * fabs(a_0)) + m * (fabs(2.0 * p * r0) + fabs(K * a_x) + fabs(2.0 * q * r0) + fabs(K * a_y))
+	                                    + m * m * (p * p + q * q + fabs(2.0 * p * q) + fabs(K) * (fabs(a_xx) + fabs(a_xy) + fabs(a_yy))));
+	const double c0e = c0 + eta;
+	const double big = 1.0e30;
+	ok = ok && (fabs(c0e) < big) && (fabs(c1) < big) && (fabs(c2) < big) && (fabs(c3) < big) && (fabs(c4) < big) && (fabs(c5) < big);
+	if (tau < -1.0e37) {
+		// w < 1/255: alpha <= w can never reach 1/255 (power <= 0) -- always skip
+		c[0] = -1.0f;
+		c[1] = c[2] = c[3] = c[4] = c[5] = 0.0f;
+	} else if (ok) {
+		// round the constant term up, so that rounding to float32 cannot lower it
+		c[0] = __double2float_ru(c0e);
+		c[1] = (float)c1; c[2] = (float)c2; c[3] = (float)c3; c[4] = (float)c4; c[5] = (float)c5;
+	} else {
+		c[0] = 3.0e38f;
+		c[1] = c[2] = c[3] = c[4] = c[5] = 0.0f;
+	}
+}
+
+// g(x, y) < 0  =>  the reference skips the pair.
+__device__ __forceinline__ bool conic_reject(float c0, float c1, float c2, float c3, float c4, float c5, float x, float y)
+{
+	const float t1 = __fmaf_rn(c3, x, __fmaf_rn(c4, y, c1));
+	const float t2 = __fmaf_rn(c5, y, c2);
+	const float g = __fmaf_rn(y, t2, __fmaf_rn(x, t1, c0));
+	return g < 0.0f;
+}
+
+}  // namespace gof

@@ -18,54 +18,59 @@ constexpr int TILE_PIX = TILE_X * TILE_Y;
 constexpr int OUT_CH = GOF_OUTPUT_CHANNELS;
 constexpr int CH_DEPTH = 6, CH_ALPHA = 7, CH_DIST = 8;
 
-// One per-Gaussian "blend record": everything the per-tile blend needs, 64 B so that a
-// tile's sorted slab is a contiguous run of 64-byte records that TMA bulk copies can stream.
+// Per-(view, Gaussian) "geometry record" written by the preprocess, 64 B:
 //  [0..5] Sigma_v (xx,xy,xz,yy,yz,zz)  [6..8] B  [9] C      (view2gaussian, forward.cu:268-277)
-//  [10] tau: conservative reject threshold on the ray-minimum value (see blend_math.cuh)
+//  [10] tau: conservative reject threshold on the ray-minimum value (blend_math.cuh)
 //  [11] w = opacity*coef (conic_opacity.w)  [12..14] rgb  [15] Gaussian index (int bits)
-// The first three float4 are all the float32 pre-test needs; the fourth only feeds
-// contributing pairs.
 constexpr int REC_FLOATS = 16;
-constexpr int REC_BYTES = 64;
 constexpr int REC_TAU = 10, REC_W = 11, REC_RGB = 12, REC_ID = 15;
+
+// Per-duplicate "slab record", 96 B, written in tile order by the tile sort so that a tile's
+// sorted Gaussians are one contiguous run that TMA bulk copies can stream:
+//  float4 #0  c0 c1 c2 c3     tile-local conic pre-test  g(x,y) = c0 + x(c1 + c3 x + c4 y) + y(c2 + c5 y)
+//  float4 #1  c4 c5 tau w
+//  float4 #2  Sxx Sxy Sxz Syy
+//  float4 #3  Syz Szz Bx  By
+//  float4 #4  Bz  C   r   g
+//  float4 #5  b   id  -   -
+constexpr int SLAB_FLOATS = 24;
+constexpr int SLAB_BYTES = 96;
 
 constexpr size_t ALIGN = 256;
 __host__ __device__ inline size_t align_up(size_t x, size_t a = ALIGN) { return (x + a - 1) / a * a; }
 
+constexpr int MAILBOX_HEAD = 4;   // mailbox ints: {R_total, overflow, max tile count, -, R_view[0..V-1]}
+
 // ---- opaque state layouts (our own; the reference's are rasterizer_impl.cu:188-243) -------
+// All per-Gaussian arrays are [V, P] (view-major); V = 1 for the single-frame entry points.
 struct GeomState {
-	float* depths;          // [P]
-	float2* means2D;        // [P]
-	float4* conic_opacity;  // [P]
-	float* rec;             // [P,16]
-	uint32_t* tiles_touched;// [P]
-	uint32_t* point_offsets;// [P]  inclusive scan of tiles_touched
-	uint8_t* clamped;       // [P,3]
-	int32_t* mailbox;       // [4]: {num_rendered, overflow flag, -, -}
-	char* scan_temp; size_t scan_temp_bytes;
+	float* depths;          // [V,P]
+	float2* means2D;        // [V,P]
+	float4* conic_opacity;  // [V,P]
+	float* rec;             // [V,P,16]
+	uint32_t* tiles_touched;// [V,P]
+	ushort4* rect;          // [V,P]  tile rectangle (x0,y0,x1,y1), valid where tiles_touched > 0
+	uint8_t* clamped;       // [V,P,3]
+	int32_t* mailbox;       // [MAILBOX_HEAD + V]
 	size_t total;
-	static GeomState carve(char* base, size_t P);
+	static GeomState carve(char* base, size_t P, size_t V);
 };
 struct ImgState {
-	float* final_T;         // [4,N]  T, dist1, dist2, distortion_raw  (forward.cu:591-594)
-	uint32_t* n_contrib;    // [2,N]  last_contributor, max_contributor (forward.cu:596-597)
-	uint2* ranges;          // [T]
+	float* final_T;         // [V,4,N]  T, dist1, dist2, distortion_raw  (forward.cu:591-594)
+	uint32_t* n_contrib;    // [V,2,N]  last_contributor, max_contributor (forward.cu:596-597)
+	uint2* ranges;          // [V*T]    (0,0) for untouched tiles, offsets into the whole batch's list
+	uint32_t* tile_counts;  // [V*T]
+	uint32_t* tile_cursor;  // [V*T]
 	size_t total;
-	static ImgState carve(char* base, size_t N, size_t T);
+	static ImgState carve(char* base, size_t N, size_t T, size_t V);
 };
 struct BinState {
-	uint64_t* keys_unsorted;   // [R]
-	uint64_t* keys;            // [R]
-	uint32_t* vals_unsorted;   // [R]
-	uint32_t* point_list;      // [R]
-	float* slab;               // [R,16] tile-ordered blend records
-	char* sort_temp; size_t sort_temp_bytes;
+	uint64_t* entries;         // [R]  (depth bits << 32) | Gaussian index, bucketed by tile, then sorted in place
+	uint32_t* point_list;      // [R]  sorted Gaussian indices (the reference's point_list)
+	float* slab;               // [R,24] tile-ordered slab records
 	size_t total;
 	static BinState carve(char* base, size_t R);
 };
-
-size_t scan_temp_bytes(size_t P);
-size_t sort_temp_bytes(size_t R);
 
 // ---- error plumbing ---------------------------------------------------------------------
 void set_error(const char* fmt, ...);
@@ -78,21 +83,30 @@ void set_error(const char* fmt, ...);
 		}                                                                                \
 	} while (0)
 
+// Camera-dependent scalars shared by the stages.
+struct Frame {
+	int P, V, W, H;
+	dim3 grid;          // tiles in x, y
+	int T;              // tiles per view
+	float focal_x, focal_y;
+};
+
 // ---- stage launchers (one .cu each) ---------------------------------------------------------
-int launch_preprocess(const GofParams& prm, const GofInputs& in, float focal_x, float focal_y,
-                      dim3 tile_grid, const GeomState& g, int32_t* radii, cudaStream_t s);
-int launch_scan(const GeomState& g, int P, cudaStream_t s);
-int launch_binning(const GofParams& prm, dim3 tile_grid, const GeomState& g, const ImgState& im,
-                   const BinState& b, const int32_t* radii, int R, cudaStream_t s);
-int launch_render_fwd(const GofParams& prm, dim3 tile_grid, float focal_x, float focal_y,
-                      const ImgState& im, const BinState& b, const float* background,
-                      float* out_color, cudaStream_t s);
-int launch_render_bwd(const GofParams& prm, dim3 tile_grid, float focal_x, float focal_y,
-                      const GeomState& g, const ImgState& im, const BinState& b,
-                      const float* background, const float* dL_dpix, float* gacc, cudaStream_t s);
+int launch_preprocess(const GofParams& prm, const GofInputs& in, const Frame& f, const GeomState& g,
+                      const ImgState& im, int32_t* radii, cudaStream_t s);
+int launch_tile_scan(const Frame& f, const GeomState& g, const ImgState& im, int64_t capacity, cudaStream_t s);
+int launch_binning(const Frame& f, const GeomState& g, const ImgState& im, const BinState& b, int64_t capacity,
+                   cudaStream_t s);
+int launch_render_fwd(const GofParams& prm, const Frame& f, const ImgState& im, const BinState& b,
+                      const float* background, int bg_stride, float* out_color, cudaStream_t s);
+int launch_render_bwd(const GofParams& prm, const Frame& f, const GeomState& g, const ImgState& im,
+                      const BinState& b, const float* background, const float* dL_dpix, float* gacc, cudaStream_t s);
 int launch_preprocess_bwd(const GofParams& prm, const GofInputs& in, const GeomState& g,
                           const int32_t* radii, const float* gacc, const GofGrads& grads,
                           cudaStream_t s);
+// test accessors that need kernels
+int launch_extract(const char* what, const Frame& f, const GeomState& g, const ImgState& im, const BinState& b,
+                   int64_t R, void* dst, cudaStream_t s);
 
 // Per-Gaussian packed gradient accumulator written by the backward blend (atomics) and
 // unpacked by the backward preprocess: [0..9] dL/dview2gaussian, [10..12] dL/dcolor,

@@ -295,17 +295,34 @@ preprocess_kernel(int P, int D, int M,
 	const float* __restrict__ means3D, const float* __restrict__ scales, const float scale_modifier,
 	const float* __restrict__ rotations, const float* __restrict__ opacities, const float* __restrict__ shs,
 	const float* __restrict__ cov3D_precomp, const float* __restrict__ colors_precomp,
-	const float* __restrict__ v2g_precomp, const float* __restrict__ viewmatrix,
-	const float* __restrict__ projmatrix, const float* __restrict__ cam_pos,
+	const float* __restrict__ v2g_precomp, const float* __restrict__ viewmatrices,
+	const float* __restrict__ projmatrices, const float* __restrict__ cam_positions,
 	const int W, const int H, const float tan_fovx, const float tan_fovy,
 	const float focal_x, const float focal_y, const float kernel_size,
-	int* __restrict__ radii, float2* __restrict__ means2D, float* __restrict__ depths,
-	float* __restrict__ rec, float4* __restrict__ conic_opacity, uint8_t* __restrict__ clamped,
-	const dim3 grid, uint32_t* __restrict__ tiles_touched, bool prefiltered)
+	int* __restrict__ radii_all, float2* __restrict__ means2D_all, float* __restrict__ depths_all,
+	float* __restrict__ rec_all, float4* __restrict__ conic_opacity_all, uint8_t* __restrict__ clamped_all,
+	const dim3 grid, uint32_t* __restrict__ tiles_touched_all, ushort4* __restrict__ rect_all,
+	uint32_t* __restrict__ tile_counts_all, bool prefiltered)
 {
 	__shared__ float s_xyz[PRE_THREADS * 3];
 	__shared__ float s_scl[PRE_THREADS * 3];
 	__shared__ float s_vm[16], s_pm[16], s_cam[3];
+
+	// blockIdx.y = view of the batch: per-view camera, per-view slice of every state array
+	const int view = blockIdx.y;
+	const size_t voff = (size_t)view * P;
+	const float* viewmatrix = viewmatrices + 16 * view;
+	const float* projmatrix = projmatrices + 16 * view;
+	const float* cam_pos = cam_positions + 3 * view;
+	int* radii = radii_all + voff;
+	float2* means2D = means2D_all + voff;
+	float* depths = depths_all + voff;
+	float* rec = rec_all + voff * REC_FLOATS;
+	float4* conic_opacity = conic_opacity_all + voff;
+	uint8_t* clamped = clamped_all + voff * 3;
+	uint32_t* tiles_touched = tiles_touched_all + voff;
+	ushort4* rects = rect_all + voff;
+	uint32_t* tile_counts = tile_counts_all + (size_t)view * grid.x * grid.y;
 
 	const int base = blockIdx.x * PRE_THREADS;
 	const int cnt = min(PRE_THREADS, P - base);
@@ -418,6 +435,11 @@ preprocess_kernel(int P, int D, int M,
 	const float w = opacities[idx] * cov.w;
 	conic_opacity[idx] = { conic.x, conic.y, conic.z, w };
 	tiles_touched[idx] = (rect_max.y - rect_min.y) * (rect_max.x - rect_min.x);
+	// Tile histogram for the bucketed binning (binning.cu): one count per (tile, Gaussian) duplicate.
+	rects[idx] = make_ushort4((unsigned short)rect_min.x, (unsigned short)rect_min.y, (unsigned short)rect_max.x,
+	                          (unsigned short)rect_max.y);
+	for (uint32_t y = rect_min.y; y < rect_max.y; y++)
+		for (uint32_t x = rect_min.x; x < rect_max.x; x++) atomicAdd(&tile_counts[y * grid.x + x], 1u);
 
 	float q[10];
 	if (v2g_precomp == nullptr) {
@@ -455,16 +477,19 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, co
 
 }  // namespace
 
-int launch_preprocess(const GofParams& prm, const GofInputs& in, float focal_x, float focal_y,
-                      dim3 tile_grid, const GeomState& g, int32_t* radii, cudaStream_t s)
+int launch_preprocess(const GofParams& prm, const GofInputs& in, const Frame& f, const GeomState& g,
+                      const ImgState& im, int32_t* radii, cudaStream_t s)
 {
 	const int P = prm.P;
-	preprocess_kernel<<<(P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, s>>>(
+	if (f.grid.x > 65535u || f.grid.y > 65535u) { set_error("image too large: more than 65535 tiles along one axis"); return GOF_EINVAL; }
+	GOF_CUDA_CHECK(cudaMemsetAsync(im.tile_counts, 0, (size_t)f.V * f.T * sizeof(uint32_t), s));
+	dim3 blocks((P + PRE_THREADS - 1) / PRE_THREADS, f.V);
+	preprocess_kernel<<<blocks, PRE_THREADS, 0, s>>>(
 		P, prm.D, prm.M, in.means3D, in.scales, prm.scale_modifier, in.rotations, in.opacities, in.shs,
 		in.cov3D_precomp, in.colors_precomp, in.view2gaussian_precomp, in.viewmatrix, in.projmatrix,
-		in.campos, prm.W, prm.H, prm.tan_fovx, prm.tan_fovy, focal_x, focal_y, prm.kernel_size,
-		radii, g.means2D, g.depths, g.rec, g.conic_opacity, g.clamped, tile_grid, g.tiles_touched,
-		prm.prefiltered != 0);
+		in.campos, prm.W, prm.H, prm.tan_fovx, prm.tan_fovy, f.focal_x, f.focal_y, prm.kernel_size,
+		radii, g.means2D, g.depths, g.rec, g.conic_opacity, g.clamped, f.grid, g.tiles_touched, g.rect,
+		im.tile_counts, prm.prefiltered != 0);
 	GOF_CUDA_CHECK(cudaGetLastError());
 	return GOF_OK;
 }

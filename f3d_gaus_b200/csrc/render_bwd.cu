@@ -18,13 +18,15 @@
 //     reductions (red.global.add.v4.f32) into a packed 80-byte per-Gaussian accumulator.
 //     Warps with <= 2 contributing lanes skip the shuffle tree and reduce directly.
 #include "blend_math.cuh"
+#include "conic.cuh"
 
 namespace gof {
 
 namespace {
 
 constexpr int CHUNK = 128;
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
+constexpr int REC_F4 = SLAB_FLOATS / 4;
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d)
 {
@@ -42,29 +44,40 @@ __device__ __forceinline__ float warp_sum(float v)
 }
 
 __global__ void __launch_bounds__(TILE_PIX)
-render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ slab, int W, int H,
-                  float focal_x, float focal_y, const float* __restrict__ bg_color,
-                  const float2* __restrict__ means2D, const float4* __restrict__ conic_opacity,
-                  const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
-                  const float* __restrict__ dL_dpixels, float* __restrict__ gacc)
+render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ slab, int P, int W, int H,
+                  float focal_x, float focal_y, const float* __restrict__ bg_colors, int bg_stride,
+                  const float2* __restrict__ means2D_all, const float4* __restrict__ conic_opacity_all,
+                  const float* __restrict__ final_Ts_all, const uint32_t* __restrict__ n_contrib_all,
+                  const float* __restrict__ dL_dpixels_all, float* __restrict__ gacc_all)
 {
-	__shared__ __align__(128) float4 s_rec[STAGES][CHUNK * 4];
+	__shared__ __align__(128) float4 s_rec[STAGES][CHUNK * REC_F4];
 	__shared__ __align__(8) uint64_t s_full[STAGES];
 	__shared__ uint32_t s_max[TILE_PIX / 32];
 
 	const int tid = threadIdx.x;
 	const int warp = tid >> 5, lane = tid & 31;
-	const uint32_t px = blockIdx.x * TILE_X + (warp & 1) * 8 + (lane & 7);
-	const uint32_t py = blockIdx.y * TILE_Y + (warp >> 1) * 4 + (lane >> 3);
+	const int view = blockIdx.z;
+	const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
+	const uint32_t px = blockIdx.x * TILE_X + lx;
+	const uint32_t py = blockIdx.y * TILE_Y + ly;
 	const bool inside = px < (uint32_t)W && py < (uint32_t)H;
 	const uint32_t pix_id = W * py + px;
 	const size_t N = (size_t)W * H;
 	const float rx = pixel_ray(px, W, focal_x);
 	const float ry = pixel_ray(py, H, focal_y);
+	const float fx = (float)lx, fy = (float)ly;
 
-	const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
+	const float* bg_color = bg_colors + (size_t)view * bg_stride;
+	const float2* means2D = means2D_all + (size_t)view * P;
+	const float4* conic_opacity = conic_opacity_all + (size_t)view * P;
+	const float* final_Ts = final_Ts_all + (size_t)view * 4 * N;
+	const uint32_t* n_contrib = n_contrib_all + (size_t)view * 2 * N;
+	const float* dL_dpixels = dL_dpixels_all + (size_t)view * OUT_CH * N;
+	float* gacc = gacc_all + (size_t)view * P * GACC_FLOATS;
+
+	const uint2 range = ranges[((size_t)view * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x];
 	const int n = (int)(range.y - range.x);
-	const float* tile_slab = slab + (size_t)range.x * REC_FLOATS;
+	const float* tile_slab = slab + (size_t)range.x * SLAB_FLOATS;
 
 	const uint32_t last_contributor = inside ? n_contrib[pix_id] : 0;
 	const uint32_t max_contributor = inside ? n_contrib[pix_id + N] : 0;
@@ -89,9 +102,9 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 		const int c = nchunks - 1 - i;
 		const int s = i % STAGES;
 		const int cnt = min(CHUNK, m - c * CHUNK);
-		const uint32_t bytes = (uint32_t)cnt * REC_BYTES;
+		const uint32_t bytes = (uint32_t)cnt * SLAB_BYTES;
 		mbar_arrive_expect_tx(&s_full[s], bytes);
-		tma_bulk_g2s(&s_rec[s][0], tile_slab + (size_t)c * CHUNK * REC_FLOATS, bytes, &s_full[s]);
+		tma_bulk_g2s(&s_rec[s][0], tile_slab + (size_t)c * CHUNK * SLAB_FLOATS, bytes, &s_full[s]);
 	};
 	if (tid == 0) {
 		const int pre = min(STAGES, nchunks);
@@ -136,9 +149,9 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 			for (int k = 0; k < 4; k++) {
 				const int j = j1 - 1 - k;
 				if (j >= 0 && base + j < last_contributor) {
-					const float4 a = rec[4 * j + 0], b = rec[4 * j + 1], cc = rec[4 * j + 2];
-					const PairGeom g = pair_geom(a, b, cc, rx, ry);
-					if (!pair_pretest_reject(g, cc.y, cc.z)) mask |= 1u << k;
+					const float4 k0 = rec[REC_F4 * j];
+					const float2 k1 = *reinterpret_cast<const float2*>(&rec[REC_F4 * j + 1]);
+					if (!conic_reject(k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, fx, fy)) mask |= 1u << k;
 				}
 			}
 			uint32_t wmask = __reduce_or_sync(0xffffffffu, mask);
@@ -146,12 +159,13 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 				const int k = __ffs(wmask) - 1;
 				wmask &= wmask - 1;
 				const int j = j1 - 1 - k;
-				const float4 a = rec[4 * j + 0], b = rec[4 * j + 1], cc = rec[4 * j + 2];
-				const float4 d = rec[4 * j + 3];
+				const float4 k1 = rec[REC_F4 * j + 1], a = rec[REC_F4 * j + 2], b = rec[REC_F4 * j + 3], cc = rec[REC_F4 * j + 4];
+				const float4 k5 = rec[REC_F4 * j + 5];
+				const float4 d = make_float4(cc.z, cc.w, k5.x, k5.y);   // rgb, id
 				const PairGeom g = pair_geom(a, b, cc, rx, ry);
 				float t = 0, alpha = 0, G = 0;
 				bool contrib = false;
-				if (mask & (1u << k)) contrib = pair_alpha_exact(g, cc.y, cc.w, t, alpha, G);
+				if ((mask & (1u << k)) && !pair_pretest_reject(g, cc.y, k1.z)) contrib = pair_alpha_exact(g, cc.y, k1.w, t, alpha, G);
 				const uint32_t cmask = __ballot_sync(0xffffffffu, contrib);
 				if (cmask == 0) continue;
 
@@ -203,7 +217,7 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 					last_alpha = alpha;
 					dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
 
-					const float w = cc.w;
+					const float w = k1.w;
 					const float dL_dG = w * dL_dalpha;
 					const float2 xy = means2D[gid];
 					const float4 con = conic_opacity[gid];
@@ -270,12 +284,12 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 
 }  // namespace
 
-int launch_render_bwd(const GofParams& prm, dim3 tile_grid, float focal_x, float focal_y,
-                      const GeomState& g, const ImgState& im, const BinState& b,
-                      const float* background, const float* dL_dpix, float* gacc, cudaStream_t s)
+int launch_render_bwd(const GofParams& prm, const Frame& f, const GeomState& g, const ImgState& im,
+                      const BinState& b, const float* background, const float* dL_dpix, float* gacc, cudaStream_t s)
 {
-	render_bwd_kernel<<<tile_grid, TILE_PIX, 0, s>>>(im.ranges, b.slab, prm.W, prm.H, focal_x, focal_y, background,
-	                                                g.means2D, g.conic_opacity, im.final_T, im.n_contrib, dL_dpix, gacc);
+	const dim3 grid(f.grid.x, f.grid.y, f.V);
+	render_bwd_kernel<<<grid, TILE_PIX, 0, s>>>(im.ranges, b.slab, f.P, prm.W, prm.H, f.focal_x, f.focal_y, background, 0,
+	                                           g.means2D, g.conic_opacity, im.final_T, im.n_contrib, dL_dpix, gacc);
 	GOF_CUDA_CHECK(cudaGetLastError());
 	return GOF_OK;
 }

@@ -7,30 +7,32 @@
 // B200 design:
 //   * One CTA per 16x16 tile (the tile size is part of the binning contract): 8 consumer warps,
 //     each owning an 8x4 pixel block, plus one producer warp.
-//   * The tile's sorted Gaussians arrive as a contiguous slab of 64-byte records (binning.cu).
+//   * The tile's sorted Gaussians arrive as a contiguous slab of 96-byte records (binning.cu).
 //     The producer streams it into a 4-stage shared-memory ring with TMA bulk copies
 //     (cp.async.bulk, completion on a "full" mbarrier per stage); each consumer warp releases a
 //     stage by arriving on its "empty" mbarrier.  There is no CTA-wide barrier in the loop: warps
 //     drift up to three chunks apart, so a warp that has many contributors in one chunk does not
 //     stall the other seven (the reference, and our first version, synchronise every batch).
-//   * Per 32-record group, two passes.  Pass 1 is a branch-free sweep: every pixel runs the
-//     conservative float32 pre-test (blend_math.cuh) against the 32 records with warp-broadcast
-//     shared-memory reads and keeps the survivors as a bit mask.  Pass 2 is lane-private: each
-//     pixel walks ITS OWN survivors in order (exact FP64 ray minimum, expf, blend).  A warp spends
-//     pass-2 iterations equal to its busiest pixel's survivor count (~10% of the list) instead of
-//     running the expensive path for every record any of its 32 pixels touches.
+//   * Per 128-record chunk, two passes.  Pass 1 is a branch-free sweep: every pixel evaluates the
+//     tile-local CONIC pre-test (conic.cuh: a quadratic in the pixel's tile coordinates, five FMAs,
+//     coefficients broadcast from shared memory) for the 128 records and keeps the survivors as a
+//     128-bit mask.  Pass 2 is lane-private: each pixel walks ITS OWN survivors in list order
+//     (float32 quadric, the tight float32 pre-test, exact FP64 ray minimum, expf, blend).  A warp
+//     spends pass-2 iterations equal to its busiest pixel's survivor count over the whole chunk
+//     (~11% of the list) instead of running the expensive path for every record any pixel touches.
 //   * Rounding: alpha, T, rgb, median depth, alpha channel and the contributor counters follow
 //     the reference's sm_100a build operation by operation and are bit-identical to it in both
 //     modes.  With GOF_FLAG_EXACT_BLEND the depth mapping and the normal normalisation also use
 //     its IEEE double divide / double sqrt / float divides (all nine channels bit-identical);
 //     without it they use float32 reciprocal arithmetic (normals, distortion within ~1e-6).
 #include "blend_math.cuh"
+#include "conic.cuh"
 
 namespace gof {
 
 namespace {
 
-constexpr int CHUNK = 128;                 // records per pipeline stage (8 KB)
+constexpr int CHUNK = 128;                 // records per pipeline stage (12 KB)
 constexpr int STAGES = 4;
 
 struct PixState {
@@ -95,24 +97,28 @@ __device__ __forceinline__ bool blend_pair(PixState& s, const PairGeom& g, float
 
 constexpr int CONSUMER_WARPS = TILE_PIX / 32;          // 8
 constexpr int FWD_THREADS = TILE_PIX + 32;             // + 1 producer warp
+constexpr int REC_F4 = SLAB_FLOATS / 4;                // float4 per slab record (6)
 
 template <bool EXACT>
 __global__ void __launch_bounds__(FWD_THREADS)
 render_fwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ slab, int W, int H,
-                  float focal_x, float focal_y, const float* __restrict__ bg_color,
-                  float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, float* __restrict__ out_color)
+                  float focal_x, float focal_y, const float* __restrict__ bg_colors, int bg_stride,
+                  float* __restrict__ final_T_all, uint32_t* __restrict__ n_contrib_all, float* __restrict__ out_color_all)
 {
-	__shared__ __align__(128) float4 s_rec[STAGES][CHUNK * 4];
-	__shared__ __align__(8) uint64_t s_full[STAGES];
-	__shared__ __align__(8) uint64_t s_empty[STAGES];
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	float4 (*s_rec)[CHUNK * REC_F4] = reinterpret_cast<float4 (*)[CHUNK * REC_F4]>(smem_raw);
+	uint64_t* s_full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * CHUNK * SLAB_BYTES);
+	uint64_t* s_empty = s_full + STAGES;
 
 	const int tid = threadIdx.x;
 	const int warp = tid >> 5, lane = tid & 31;
+	const int view = blockIdx.z;
+	const size_t N = (size_t)W * H;
 
-	const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
+	const uint2 range = ranges[((size_t)view * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x];
 	const int n = (int)(range.y - range.x);
 	const int nchunks = (n + CHUNK - 1) / CHUNK;
-	const float* tile_slab = slab + (size_t)range.x * REC_FLOATS;
+	const float* tile_slab = slab + (size_t)range.x * SLAB_FLOATS;
 
 	if (tid == 0) {
 #pragma unroll
@@ -128,21 +134,23 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 				const int s = c % STAGES;
 				if (c >= STAGES) mbar_wait(&s_empty[s], (uint32_t)(((c / STAGES) - 1) & 1));
 				const int cnt = min(CHUNK, n - c * CHUNK);
-				const uint32_t bytes = (uint32_t)cnt * REC_BYTES;
+				const uint32_t bytes = (uint32_t)cnt * SLAB_BYTES;
 				mbar_arrive_expect_tx(&s_full[s], bytes);
-				tma_bulk_g2s(&s_rec[s][0], tile_slab + (size_t)c * CHUNK * REC_FLOATS, bytes, &s_full[s]);
+				tma_bulk_g2s(&s_rec[s][0], tile_slab + (size_t)c * CHUNK * SLAB_FLOATS, bytes, &s_full[s]);
 			}
 		}
 		return;
 	}
 
 	// -------------------- consumer warps: 8x4 pixel block each --------------------------------
-	const uint32_t px = blockIdx.x * TILE_X + (warp & 1) * 8 + (lane & 7);
-	const uint32_t py = blockIdx.y * TILE_Y + (warp >> 1) * 4 + (lane >> 3);
+	const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);   // tile-local pixel
+	const uint32_t px = blockIdx.x * TILE_X + lx;
+	const uint32_t py = blockIdx.y * TILE_Y + ly;
 	const bool inside = px < (uint32_t)W && py < (uint32_t)H;
 	const uint32_t pix_id = W * py + px;
 	const float rx = pixel_ray(px, W, focal_x);
 	const float ry = pixel_ray(py, H, focal_y);
+	const float fx = (float)lx, fy = (float)ly;
 
 	PixState st;
 	st.T = 1.0f;
@@ -161,32 +169,38 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 			const int cnt = min(CHUNK, n - c * CHUNK);
 			const float4* rec = &s_rec[s][0];
 			const uint32_t base = (uint32_t)c * CHUNK;
+			// ---- pass 1: branch-free conic sweep over the chunk (broadcast reads, 5 FMAs per pair) ----
+			unsigned long long m_lo = 0, m_hi = 0;   // survivors among records [0,64) and [64,128)
+#pragma unroll 1
 			for (int w = 0; w < CHUNK / 32; w++) {
 				const int valid = cnt - 32 * w;
 				if (valid <= 0) break;
-				// ---- pass 1: branch-free pre-test sweep over 32 records (broadcast reads) ------
 				uint32_t bits = 0;
-				const float4* rw = rec + 4 * 32 * w;
+				const float4* rw = rec + REC_F4 * 32 * w;
 #pragma unroll
 				for (int jj = 0; jj < 32; jj++) {
-					const float4 a = rw[4 * jj + 0], b = rw[4 * jj + 1], cc = rw[4 * jj + 2];
-					const PairGeom g = pair_geom(a, b, cc, rx, ry);
-					if (!pair_pretest_reject(g, cc.y, cc.z)) bits |= 1u << jj;
+					const float4 k0 = rw[REC_F4 * jj];
+					const float2 k1 = *reinterpret_cast<const float2*>(&rw[REC_F4 * jj + 1]);
+					if (!conic_reject(k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, fx, fy)) bits |= 1u << jj;
 				}
 				if (valid < 32) bits &= (1u << valid) - 1u;   // stale records beyond the list end
-				if (done) bits = 0;
-				// ---- pass 2: each pixel blends its own survivors, in list order ----------------
-				while (bits != 0) {
-					const int jj = __ffs(bits) - 1;
-					bits &= bits - 1;
-					const float4* r = rw + 4 * jj;
-					const float4 a = r[0], b = r[1], cc = r[2];
-					const PairGeom g = pair_geom(a, b, cc, rx, ry);
-					float t, alpha, G;
-					if (!pair_alpha_exact(g, cc.y, cc.w, t, alpha, G)) continue;
-					const float4 d = r[3];
-					if (blend_pair<EXACT>(st, g, t, alpha, d, base + 32 * w + jj + 1)) { done = true; bits = 0; }
-				}
+				if (w < 2) m_lo |= (unsigned long long)bits << (32 * w);
+				else m_hi |= (unsigned long long)bits << (32 * (w - 2));
+			}
+			if (done) { m_lo = 0; m_hi = 0; }
+			// ---- pass 2: each pixel blends its own survivors, in list order -------------------------
+			while ((m_lo | m_hi) != 0) {
+				int j;
+				if (m_lo != 0) { j = __ffsll((long long)m_lo) - 1; m_lo &= m_lo - 1; }
+				else { j = 64 + __ffsll((long long)m_hi) - 1; m_hi &= m_hi - 1; }
+				const float4* r = rec + REC_F4 * j;
+				const float4 k1 = r[1], a = r[2], b = r[3], cc = r[4];
+				const PairGeom g = pair_geom(a, b, cc, rx, ry);
+				if (pair_pretest_reject(g, cc.y, k1.z)) continue;
+				float t, alpha, G;
+				if (!pair_alpha_exact(g, cc.y, k1.w, t, alpha, G)) continue;
+				const float4 d = make_float4(cc.z, cc.w, r[5].x, 0.0f);
+				if (blend_pair<EXACT>(st, g, t, alpha, d, base + j + 1)) { done = true; m_lo = 0; m_hi = 0; }
 			}
 			warp_done = __all_sync(0xffffffffu, done);
 		}
@@ -195,7 +209,10 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 	}
 
 	if (inside) {
-		const size_t N = (size_t)W * H;
+		float* final_T = final_T_all + (size_t)view * 4 * N;
+		uint32_t* n_contrib = n_contrib_all + (size_t)view * 2 * N;
+		float* out_color = out_color_all + (size_t)view * OUT_CH * N;
+		const float* bg_color = bg_colors + (size_t)view * bg_stride;
 		const float T = st.T;
 		const float om = __fsub_rn(1.0f, T);
 		const float dnorm = (float)((double)st.distortion / ((double)__fmul_rn(om, om) + 1e-7));
@@ -215,16 +232,23 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 
 }  // namespace
 
-int launch_render_fwd(const GofParams& prm, dim3 tile_grid, float focal_x, float focal_y,
-                      const ImgState& im, const BinState& b, const float* background,
-                      float* out_color, cudaStream_t s)
+int launch_render_fwd(const GofParams& prm, const Frame& f, const ImgState& im, const BinState& b,
+                      const float* background, int bg_stride, float* out_color, cudaStream_t s)
 {
+	const dim3 grid(f.grid.x, f.grid.y, f.V);
+	const size_t smem = (size_t)STAGES * CHUNK * SLAB_BYTES + 2 * STAGES * sizeof(uint64_t);
+	static bool attr_set = false;
+	if (!attr_set) {
+		GOF_CUDA_CHECK(cudaFuncSetAttribute(render_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		GOF_CUDA_CHECK(cudaFuncSetAttribute(render_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		attr_set = true;
+	}
 	if (prm.flags & GOF_FLAG_EXACT_BLEND)
-		render_fwd_kernel<true><<<tile_grid, FWD_THREADS, 0, s>>>(im.ranges, b.slab, prm.W, prm.H, focal_x, focal_y,
-		                                                          background, im.final_T, im.n_contrib, out_color);
+		render_fwd_kernel<true><<<grid, FWD_THREADS, smem, s>>>(im.ranges, b.slab, prm.W, prm.H, f.focal_x, f.focal_y,
+		                                                     background, bg_stride, im.final_T, im.n_contrib, out_color);
 	else
-		render_fwd_kernel<false><<<tile_grid, FWD_THREADS, 0, s>>>(im.ranges, b.slab, prm.W, prm.H, focal_x, focal_y,
-		                                                           background, im.final_T, im.n_contrib, out_color);
+		render_fwd_kernel<false><<<grid, FWD_THREADS, smem, s>>>(im.ranges, b.slab, prm.W, prm.H, f.focal_x, f.focal_y,
+		                                                      background, bg_stride, im.final_T, im.n_contrib, out_color);
 	GOF_CUDA_CHECK(cudaGetLastError());
 	return GOF_OK;
 }

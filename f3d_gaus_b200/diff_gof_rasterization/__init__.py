@@ -21,7 +21,7 @@ from .. import _lib
 
 __all__ = [
     "GaussianRasterizationSettings_GOF", "GaussianRasterizer_GOF", "GaussianRasterizationSettings",
-    "GaussianRasterizer", "rasterize_gaussians", "NumRendered",
+    "GaussianRasterizer", "rasterize_gaussians", "NumRendered", "rasterize_views", "BatchWorkspace",
 ]
 
 
@@ -170,6 +170,145 @@ class _CModule:
 
 
 _C = _CModule()
+
+
+class BatchWorkspace:
+    """Reusable device buffers for `rasterize_views` (the batched entry point, gof_forward_batch).
+
+    With a workspace the forward is SYNC-FREE: the binning blob is a cached buffer (capacity = 1.5x
+    the largest batch seen so far) and `num_rendered` stays on the device until `finish()` reads the
+    mailbox -- call it after your own synchronisation point (e.g. after the D2H copy of the frames).
+    `finish()` returns the per-view R, or None if the blob was too small for this batch, in which case
+    the buffers have been grown and the caller must re-run the batch (`rasterize_views` does that)."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.geom = self.img = self.binning = None
+        self.key = None
+        self.capacity_hint = 0
+
+    def _ensure(self, P, W, H, V):
+        gsz, isz, bsz = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+        if self.capacity_hint == 0:
+            self.capacity_hint = max(4 * P * V, 1 << 16)      # first call: generous (4 tiles per Gaussian)
+        _lib.check(_lib.lib.gof_state_sizes_batch(P, W, H, V, self.capacity_hint, ctypes.byref(gsz), ctypes.byref(isz),
+                                                  ctypes.byref(bsz)), "gof_state_sizes_batch")
+        opts = dict(dtype=torch.uint8, device=self.device)
+        if self.key != (P, W, H, V) or self.geom is None:
+            self.geom = torch.empty(gsz.value, **opts)
+            self.img = torch.empty(isz.value, **opts)
+            self.key = (P, W, H, V)
+        if self.binning is None or self.binning.numel() < bsz.value:
+            self.binning = torch.empty(bsz.value, **opts)
+
+    def finish(self):
+        P, W, H, V = self.key
+        out = (ctypes.c_int32 * V)()
+        with torch.cuda.device(self.device):
+            rc = _lib.lib.gof_num_rendered(_lib.context(self.device.index), self.geom.data_ptr(), P, V,
+                                           torch.cuda.current_stream(self.device).cuda_stream, out)
+        R = [int(x) for x in out]
+        if rc == _lib.GOF_EOVERFLOW:
+            self.capacity_hint = int(1.5 * sum(R)) + 1024
+            self.binning = None
+            return None
+        _lib.check(rc, "gof_num_rendered")
+        if 1.25 * sum(R) > self.capacity_hint:                 # keep some head-room for the next batch
+            self.capacity_hint = int(1.5 * sum(R)) + 1024
+        return R
+
+
+def rasterize_views(background, means3D, colors, opacity, scales, rotations, scale_modifier, viewmatrices, projmatrices,
+                    tan_fovx, tan_fovy, kernel_size, image_height, image_width, sh, degree, campos, prefiltered=False,
+                    debug=False, workspace: BatchWorkspace | None = None, out_color=None):
+    """V views of one Gaussian set in ONE pass of the pipeline (gof_forward_batch).
+
+    viewmatrices/projmatrices: [V,4,4] (or [V,1,4,4]), campos: [V,3]; background [3] or [V,3].
+    Returns (num_rendered, color[V,9,H,W], radii[V,P], geom, binning, img).  Frame v is bit-identical
+    to `_C.rasterize_gaussians` with camera v.  Without a workspace num_rendered is a list of ints and
+    one host synchronisation happens (as in the reference); with one, it is None until
+    `workspace.finish()`."""
+    if means3D.dim() != 2 or means3D.size(1) != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    if not means3D.is_cuda:
+        raise RuntimeError("diff_gof_rasterization (B200): tensors must be on a CUDA device; there is no CPU path")
+    device = means3D.device
+    P, H, W = int(means3D.size(0)), int(image_height), int(image_width)
+    V = int(viewmatrices.reshape(-1, 16).size(0))
+    M = int(sh.size(1)) if (sh is not None and sh.numel() != 0 and sh.size(0) != 0) else 0
+    keep: list = []
+    f32 = dict(dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream(device).cuda_stream
+        if out_color is None:
+            out_color = torch.empty((V, _lib.OUTPUT_CHANNELS, H, W), **f32)
+        if P == 0:
+            out_color.zero_()
+            e = torch.empty(0, dtype=torch.uint8, device=device)
+            return [0] * V, out_color, torch.zeros((V, 0), dtype=torch.int32, device=device), e, e.clone(), e.clone()
+        radii = torch.empty((V, P), dtype=torch.int32, device=device)
+        bg = background.reshape(-1)
+        bg_stride = 3 if bg.numel() == 3 * V and V > 1 else 0
+        prm = _lib.GofParams(P, int(degree), M, W, H, float(tan_fovx), float(tan_fovy), float(kernel_size),
+                             float(scale_modifier), int(bool(prefiltered)), int(bool(debug)), _lib.default_flags())
+        inp = _lib.GofInputs(
+            _dev_ptr(bg, device, keep), _dev_ptr(means3D, device, keep), _dev_ptr(sh, device, keep),
+            _dev_ptr(colors, device, keep), _dev_ptr(opacity, device, keep), _dev_ptr(scales, device, keep),
+            _dev_ptr(rotations, device, keep), None, None, _dev_ptr(viewmatrices.reshape(V, 16), device, keep),
+            _dev_ptr(projmatrices.reshape(V, 16), device, keep), _dev_ptr(campos.reshape(V, 3), device, keep))
+        Rv = (ctypes.c_int32 * V)()
+        bin_out = ctypes.c_void_p()
+        ctx = _lib.context(device.index)
+        if workspace is None:
+            gsz, isz, bsz = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+            _lib.check(_lib.lib.gof_state_sizes_batch(P, W, H, V, 0, ctypes.byref(gsz), ctypes.byref(isz),
+                                                      ctypes.byref(bsz)), "gof_state_sizes_batch")
+            byte_opts = dict(dtype=torch.uint8, device=device)
+            geom, img = torch.empty(gsz.value, **byte_opts), torch.empty(isz.value, **byte_opts)
+            holder = {}
+
+            def _alloc(_user, nbytes):
+                holder["binning"] = torch.empty(int(nbytes), **byte_opts)
+                return holder["binning"].data_ptr()
+
+            rc = _lib.lib.gof_forward_batch(ctx, ctypes.byref(prm), ctypes.byref(inp), V, bg_stride, geom.data_ptr(),
+                                            geom.numel(), img.data_ptr(), img.numel(), None, 0, _lib.ALLOC_FN(_alloc),
+                                            None, out_color.data_ptr(), radii.data_ptr(), Rv, ctypes.byref(bin_out),
+                                            stream)
+            _lib.check(rc, "rasterize_views")
+            binning = holder.get("binning", torch.empty(0, **byte_opts))
+            return [int(x) for x in Rv], out_color, radii, geom, binning, img
+        workspace._ensure(P, W, H, V)
+        rc = _lib.lib.gof_forward_batch(ctx, ctypes.byref(prm), ctypes.byref(inp), V, bg_stride,
+                                        workspace.geom.data_ptr(), workspace.geom.numel(), workspace.img.data_ptr(),
+                                        workspace.img.numel(), workspace.binning.data_ptr(), workspace.binning.numel(),
+                                        _lib.ALLOC_FN(), None, out_color.data_ptr(), radii.data_ptr(), Rv,
+                                        ctypes.byref(bin_out), stream)
+        _lib.check(rc, "rasterize_views")
+        return None, out_color, radii, workspace.geom, workspace.binning, workspace.img
+
+
+def state_array_batch(name: str, P: int, W: int, H: int, V: int, R: int, geom, binning, img):
+    """Test accessor on the state of a V-view batch (gof_state_get_batch)."""
+    device = geom.device
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    spec = {
+        "depths": (torch.float32, (V, P)), "means2D": (torch.float32, (V, P, 2)),
+        "conic_opacity": (torch.float32, (V, P, 4)), "view2gaussian": (torch.float32, (V, P, 10)),
+        "rgb": (torch.float32, (V, P, 3)), "clamped": (torch.uint8, (V, P, 3)),
+        "tiles_touched": (torch.int32, (V, P)), "point_offsets": (torch.int32, (V, P)),
+        "final_T": (torch.float32, (V, 4, H, W)), "n_contrib": (torch.int32, (V, 2, H, W)),
+        "ranges": (torch.int32, (V * T, 2)), "point_list": (torch.int32, (R,)), "point_list_keys": (torch.int64, (R,)),
+    }[name]
+    out = torch.empty(spec[1], dtype=spec[0], device=device)
+    with torch.cuda.device(device):
+        n = _lib.lib.gof_state_get_batch(name.encode(), P, W, H, V, R, geom.data_ptr(),
+                                         binning.data_ptr() if binning.numel() else None, img.data_ptr(),
+                                         out.data_ptr() if out.numel() else None, out.numel() * out.element_size(),
+                                         torch.cuda.current_stream(device).cuda_stream)
+    if n < 0:
+        raise RuntimeError(f"gof_state_get_batch({name}) failed: {_lib.last_error()}")
+    return out
 
 
 def state_array(name: str, P: int, W: int, H: int, R: int, geom, binning, img):

@@ -2,6 +2,7 @@
 
   render_predicted_more_v2_gof   (:915-1067)  dict-of-tensors -> rasterizer -> output dict
   depths_to_points / depth_to_normal (:881-909)
+  render_views                    all V views of a scene in one batched pass (what the reference's render loops do frame by frame)
   render                          the vanilla signature (src/gaussian-splatting/gaussian_renderer/__init__.py:18-100)
 
 Same arguments, same output keys.  Differences are internal: the rasterizer is libgof_b200,
@@ -18,7 +19,8 @@ import numpy as np
 import torch
 
 from .. import _lib
-from ..diff_gof_rasterization import GaussianRasterizationSettings_GOF, GaussianRasterizer_GOF
+from ..diff_gof_rasterization import (BatchWorkspace, GaussianRasterizationSettings_GOF, GaussianRasterizer_GOF,
+                                     rasterize_views)
 
 _EMPTY_OFFSET: dict = {}
 
@@ -143,6 +145,53 @@ def render_predicted_more_v2_gof(pc: dict, bs, world_view_transform, full_proj_t
             "viewspace_points": screenspace_points,
             "visibility_filter": radii > 0,
             "radii": radii}
+
+
+def render_views(pc: dict, bs, world_view_transforms, full_proj_transforms, camera_centers, bg_color: torch.Tensor, cfg,
+                 kernel_size=0.0, scaling_modifier=1.0, override_color=None, workspace: BatchWorkspace | None = None,
+                 epilogue: bool = True, out_color: torch.Tensor | None = None):
+    """All V views of scene `bs` in one pass of the pipeline: the batched form of the reference's
+    `for th in range(num_frames): render_predicted_more_v2_gof(pc, bs, wvt[th:th+1], ...)` loops
+    (visualize.py:293-306,387-402).  Inference only (no autograd graph).
+
+    world_view_transforms / full_proj_transforms: [V,4,4] or [V,1,4,4]; camera_centers: [V,3] or [V,1,3].
+    Returns the keys of `render_predicted_more_v2_gof` with a leading view dimension
+    (render[V,3,H,W], rendered_depth[V,1,H,W], rendered_alpha[V,1,H,W], distortion_map[V,1,H,W],
+    radii[V,P], visibility_filter[V,P]; rendered_normal / depth_normal [V,3,H,W] when `epilogue`),
+    plus `raster` = the full [V,9,H,W] rasterizer output.  Frame v is bit-identical to the per-view call.
+    With a `workspace` the call does not synchronise the host (see BatchWorkspace)."""
+    xyz = pc["xyz"][bs]
+    device = xyz.device
+    fov = cfg['model']['fov']
+    tanfov = math.tan(fov * np.pi / 360)
+    Fov = fov * np.pi / 180
+    H = W = int(cfg['model']['training_resolution'])
+    V = int(world_view_transforms.reshape(-1, 16).shape[0])
+    if override_color is None:
+        shs = torch.cat([pc["features_dc"][bs], pc["features_rest"][bs]], dim=1).contiguous()
+        colors = None
+    else:
+        shs, colors = None, pc["rgbs"][bs]
+    with torch.no_grad():
+        R, raster, radii, _, _, _ = rasterize_views(
+            bg_color, xyz, colors, pc["opacity"][bs], pc["scaling"][bs], pc["rotation"][bs], scaling_modifier,
+            world_view_transforms, full_proj_transforms, tanfov, tanfov, kernel_size, H, W, shs,
+            cfg['model']['max_sh_degree'], camera_centers, workspace=workspace, out_color=out_color)
+        out = {"raster": raster, "render": raster[:, 0:3], "rendered_depth": raster[:, 6:7],
+               "rendered_alpha": raster[:, 7:8], "distortion_map": raster[:, 8:9], "radii": radii,
+               "visibility_filter": radii > 0, "num_rendered": R}
+        if epilogue:
+            normal_world = torch.empty((V, 3, H, W), dtype=torch.float32, device=device)
+            depth_normal = torch.empty((V, 3, H, W), dtype=torch.float32, device=device)
+            vm = world_view_transforms.reshape(V, 16).contiguous()
+            with torch.cuda.device(device):
+                rc = _lib.lib.gof_render_epilogue_batch(raster.data_ptr(), vm.data_ptr(), V, W, H, ctypes.c_float(Fov),
+                                                        ctypes.c_float(Fov), normal_world.data_ptr(),
+                                                        depth_normal.data_ptr(),
+                                                        torch.cuda.current_stream(device).cuda_stream)
+            _lib.check(rc, "gof_render_epilogue_batch")
+            out["rendered_normal"], out["depth_normal"] = normal_world, depth_normal
+    return out
 
 
 def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None,

@@ -5,6 +5,7 @@
  * (RAST = src/gaussian-splatting/submodules/diff-gof-rasterization):
  *
  *   gof_forward          <- CudaRasterizer::Rasterizer::forward   RAST/cuda_rasterizer/rasterizer.h:30-59
+ *   gof_forward_batch    <- the per-frame render loops around it  visualize.py:293-306,387-402
  *                           (bound by RasterizeGaussiansCUDA,      RAST/rasterize_points.cu:36-122)
  *   gof_backward         <- CudaRasterizer::Rasterizer::backward  RAST/cuda_rasterizer/rasterizer.h:61-91
  *                           (bound by RasterizeGaussiansBackwardCUDA, RAST/rasterize_points.cu:124-211)
@@ -48,6 +49,7 @@ extern "C" {
 #define GOF_EOVERFLOW    -4   /* sync-free mode: num_rendered exceeded the binning capacity */
 
 #define GOF_OUTPUT_CHANNELS 9   /* rgb(3) normal(3) depth alpha distortion: auxiliary.h:21-24 */
+#define GOF_MAX_VIEWS      64   /* views per gof_forward_batch call */
 
 typedef struct GofContext GofContext;   /* per-device handle (scratch, pinned mailbox) */
 typedef void* gof_stream_t;             /* cudaStream_t */
@@ -127,6 +129,9 @@ int gof_profile_read(GofContext* ctx, double* fwd_ms, int64_t* fwd_calls, double
  * (pass an upper bound for the sync-free mode). */
 int gof_state_sizes(int32_t P, int32_t W, int32_t H, int64_t num_rendered,
                     size_t* geom_bytes, size_t* img_bytes, size_t* binning_bytes);
+/* Same for a batch of V views (gof_forward_batch); num_rendered is the batch total. */
+int gof_state_sizes_batch(int32_t P, int32_t W, int32_t H, int32_t V, int64_t num_rendered,
+                          size_t* geom_bytes, size_t* img_bytes, size_t* binning_bytes);
 
 /* Forward: preprocess -> tile binning -> per-tile front-to-back GOF blend.
  *   geom, img      : caller-allocated blobs of at least gof_state_sizes() bytes.
@@ -145,9 +150,23 @@ int gof_forward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
                 float* out_color, int32_t* radii,
                 int32_t* num_rendered, void** binning_out, gof_stream_t stream);
 
-/* Sync-free mode: blocks on `stream` and returns the R of the last forward that used `geom`
- * (or GOF_EOVERFLOW if the binning blob was too small for it). */
-int gof_num_rendered(GofContext* ctx, const void* geom, int32_t P, gof_stream_t stream, int32_t* num_rendered);
+/* Batched forward: V views of ONE Gaussian set in a single pass of the pipeline -- what the render
+ * loops of the reference do one frame at a time (`for th in views: for bb in scenes: render(...)`,
+ * visualize.py:293-306,387-402).  in->viewmatrix / projmatrix / campos point to V consecutive cameras
+ * ([V,16], [V,16], [V,3]); in->background to [3] (bg_stride 0) or [V,3] (bg_stride 3).  Every kernel
+ * covers the whole batch (grid.y/z = view), the tile lists of all views are binned together and the
+ * num_rendered hand-off happens once.  out_color is [V,9,H,W], radii [V,P], num_rendered a host
+ * array [V]; state blobs are sized by gof_state_sizes_batch.  Frame v of the batch is bit-identical
+ * to gof_forward with camera v.  view2gaussian_precomp is per view and needs V == 1. */
+int gof_forward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* in, int32_t V, int32_t bg_stride,
+                      void* geom, size_t geom_bytes, void* img, size_t img_bytes,
+                      void* binning, size_t binning_bytes, GofAllocFn alloc, void* alloc_user,
+                      float* out_color, int32_t* radii,
+                      int32_t* num_rendered, void** binning_out, gof_stream_t stream);
+
+/* Sync-free mode: blocks on `stream` and returns the per-view R ([V]) of the last forward that used
+ * `geom` (or GOF_EOVERFLOW if the binning blob was too small for it). */
+int gof_num_rendered(GofContext* ctx, const void* geom, int32_t P, int32_t V, gof_stream_t stream, int32_t* num_rendered);
 
 /* Backward: replays the blend back-to-front and produces the reference's 9 gradient tensors. */
 int gof_backward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
@@ -178,6 +197,10 @@ int gof_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
 int gof_render_epilogue(const float* out_color, const float* viewmatrix, int32_t W, int32_t H,
                         float fovx, float fovy, float* normal_world, float* depth_normal,
                         gof_stream_t stream);
+/* Same for V frames: out_color [V,9,H,W], viewmatrix [V,16], outputs [V,3,H,W] (either may be NULL). */
+int gof_render_epilogue_batch(const float* out_color, const float* viewmatrix, int32_t V, int32_t W, int32_t H,
+                              float fovx, float fovy, float* normal_world, float* depth_normal,
+                              gof_stream_t stream);
 
 /* Test accessor: copy one named array of the opaque state into dst (device pointer).
  * Names: depths[P] f32, means2D[P,2] f32, conic_opacity[P,4] f32, view2gaussian[P,10] f32,
@@ -187,6 +210,11 @@ int gof_render_epilogue(const float* out_color, const float* viewmatrix, int32_t
 int64_t gof_state_get(const char* name, int32_t P, int32_t W, int32_t H, int64_t num_rendered,
                       const void* geom, const void* binning, const void* img,
                       void* dst, int64_t dst_bytes, gof_stream_t stream);
+/* Same on the state of a V-view batch: per-Gaussian arrays are [V,P,...], per-pixel [V,...,H,W],
+ * ranges [V*T,2] (offsets into the batch's list), point_list / point_list_keys [R_total]. */
+int64_t gof_state_get_batch(const char* name, int32_t P, int32_t W, int32_t H, int32_t V, int64_t num_rendered,
+                            const void* geom, const void* binning, const void* img,
+                            void* dst, int64_t dst_bytes, gof_stream_t stream);
 
 #ifdef __cplusplus
 }

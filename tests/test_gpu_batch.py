@@ -1,0 +1,119 @@
+"""GPU tests of the batched entry point (gof_forward_batch / rasterize_views / render_views): frame v of a
+batch must be bit-identical to the single-frame call with camera v, in both hand-off modes."""
+import pytest
+import torch
+
+import cases
+import refgpu
+
+pytestmark = pytest.mark.gpu
+
+
+def _scene(S, res, device="cuda", seed=0):
+    from f3d_gaus_b200 import cameras, synthetic
+    pc = {k: v.to(device) for k, v in synthetic.f3d_like(seed, S).items()}
+    cams = cameras.orbit_cameras(8)
+    cfg = synthetic.cfg_for(res)
+    return pc, cams, cfg
+
+
+def _per_view(pc, cams, res, v, device="cuda"):
+    c = cases.make_case({k: t.cpu() for k, t in pc.items()}, cams.world_view[v], cams.full_proj[v], cams.centers[v],
+                        W=res, H=res, fov_deg=13.164, device=device)
+    o = refgpu.OursRun().forward(c)
+    return c, o
+
+
+def _batch(pc, cams, res, workspace=None, views=range(8)):
+    from f3d_gaus_b200.diff_gof_rasterization import rasterize_views
+    import math
+    idx = list(views)
+    dev = pc["xyz"].device
+    shs = torch.cat([pc["features_dc"][0], pc["features_rest"][0]], dim=1).contiguous()
+    tanfov = math.tan(13.164 * math.pi / 360)
+    return rasterize_views(torch.zeros(3, device=dev), pc["xyz"][0], None, pc["opacity"][0], pc["scaling"][0],
+                           pc["rotation"][0], 1.0, cams.world_view[idx].to(dev), cams.full_proj[idx].to(dev), tanfov,
+                           tanfov, 0.0, res, res, shs, 1, cams.centers[idx].to(dev), workspace=workspace)
+
+
+@pytest.mark.parametrize("S,res", [(64, 128), (256, 256), (96, 200)])
+def test_batch_equals_per_view(S, res):
+    from f3d_gaus_b200.diff_gof_rasterization import state_array_batch
+    pc, cams, cfg = _scene(S, res)
+    R, color, radii, geom, binning, img = _batch(pc, cams, res)
+    torch.cuda.synchronize()
+    P, V = S * S, 8
+    nc = state_array_batch("n_contrib", P, res, res, V, sum(R), geom, binning, img)
+    fT = state_array_batch("final_T", P, res, res, V, sum(R), geom, binning, img)
+    rng = state_array_batch("ranges", P, res, res, V, sum(R), geom, binning, img)
+    plist = state_array_batch("point_list", P, res, res, V, sum(R), geom, binning, img)
+    keys = state_array_batch("point_list_keys", P, res, res, V, sum(R), geom, binning, img)
+    T = ((res + 15) // 16) ** 2
+    start = 0
+    for v in range(V):
+        c, o = _per_view(pc, cams, res, v)
+        assert R[v] == o["num_rendered"]
+        assert torch.equal(radii[v], o["radii"])
+        assert torch.equal(color[v].view(torch.int32), o["out_color"].view(torch.int32)), f"view {v}"
+        assert torch.equal(nc[v].reshape(2, -1), o["n_contrib"])
+        assert torch.equal(fT[v].reshape(4, -1).view(torch.int32), o["final_T"].view(torch.int32))
+        # the batch's tile lists are the per-view lists, concatenated in view order
+        assert torch.equal(plist[start:start + R[v]], o["point_list"])
+        assert torch.equal(keys[start:start + R[v]], o["point_list_keys"])
+        rv = rng[v * T:(v + 1) * T]
+        touched = rv[:, 1] > rv[:, 0]
+        assert torch.equal((rv - start)[touched], o["ranges"][touched])
+        assert not rv[~touched].any()
+        start += R[v]
+
+
+def test_workspace_sync_free_and_overflow_retry():
+    from f3d_gaus_b200.diff_gof_rasterization import BatchWorkspace
+    pc, cams, cfg = _scene(128, 256)
+    R0, color0, radii0, *_ = _batch(pc, cams, 256)
+    ws = BatchWorkspace("cuda:0")
+    R, color, radii, *_ = _batch(pc, cams, 256, workspace=ws)
+    assert R is None
+    torch.cuda.synchronize()
+    assert ws.finish() == R0
+    assert torch.equal(color.view(torch.int32), color0.view(torch.int32)) and torch.equal(radii, radii0)
+    # a blob that is too small: overflow is reported, buffers grow, the re-run is correct
+    ws2 = BatchWorkspace("cuda:0")
+    ws2.capacity_hint = 1000
+    _batch(pc, cams, 256, workspace=ws2)
+    assert ws2.finish() is None
+    R, color, radii, *_ = _batch(pc, cams, 256, workspace=ws2)
+    assert ws2.finish() == R0
+    assert torch.equal(color.view(torch.int32), color0.view(torch.int32))
+
+
+def test_render_views_matches_render_predicted():
+    from f3d_gaus_b200.gaussian_renderer import render_predicted_more_v2_gof, render_views
+    pc, cams, cfg = _scene(128, 256)
+    dev = "cuda"
+    wv, fp, cc = cams.world_view.to(dev), cams.full_proj.to(dev), cams.centers.to(dev)
+    bg = torch.tensor([0.1, 0.2, 0.3], device=dev)
+    out = render_views(pc, 0, wv, fp, cc, bg, cfg)
+    with torch.no_grad():
+        for v in (0, 3, 7):
+            o = render_predicted_more_v2_gof(pc, 0, wv[v:v + 1], fp[v:v + 1], cc[v:v + 1], bg, cfg)
+            for k in ("render", "rendered_depth", "rendered_alpha", "distortion_map", "rendered_normal", "depth_normal"):
+                assert torch.equal(out[k][v], o[k]), (k, v)
+            assert torch.equal(out["radii"][v], o["radii"])
+
+
+def test_big_tile_global_sort_path():
+    """> 4096 Gaussians in one tile: the bucket is sorted in place in global memory."""
+    c = cases.unit_case(3, 6000, 32, 32, device="cuda")
+    c["means3D"] = c["means3D"].clone()
+    c["means3D"][:, :2] *= 0.05          # everything lands in the same few tiles
+    o = refgpu.OursRun().forward(c)
+    rng = o["ranges"].long()
+    assert int((rng[:, 1] - rng[:, 0]).max()) > 4096
+    keys = o["point_list_keys"]
+    assert bool((keys[1:] >= keys[:-1]).all())
+    if refgpu.ref_available():
+        r = refgpu.RefRun().forward(c)
+        assert torch.equal(o["point_list"], r["point_list"]) and torch.equal(keys, r["point_list_keys"])
+        assert torch.equal(o["out_color"].view(torch.int32), r["out_color"].view(torch.int32)) or \
+            (o["out_color"] - r["out_color"]).abs().max().item() <= 2e-5
