@@ -7,12 +7,14 @@ renderCUDA HBM GB/s vs roofline").
 
 Workload `nvs256` (BASELINE configs[1]): one seeded "f3d-like" scene of 65,536 Gaussians (SH degree 1)
 per GPU, rendered at 256x256 from the 8 orbit views of the cycle-aggregative loop.  One STEP = one
-pass of the hot path over that batch = 8 full forwards (preprocess -> binning -> blend).
-`value` = frames/s over all GPUs with the scene resident in HBM; `e2e` = the same frames through
-the reference-facing API (render_predicted_more_v2_gof) starting from pinned HOST buffers, with the
-H2D copy of the Gaussian set and the D2H copy of the rendered rgb/depth/alpha inside the timed
-region.  Timing: CUDA events per step on the launch stream, an L2 flush (256 MB write) between
-steps outside the events, max over ranks.
+pass of the hot path over that batch = 8 full forwards (preprocess -> binning -> blend), issued as
+ONE batched call (gof_forward_batch).  `value` = frames/s over all GPUs with the scene resident in
+HBM; `e2e` = the same frames through the loop's public API (gaussian_renderer.render_views) starting
+from pinned HOST buffers, with the H2D copy of the Gaussian set and the D2H copy of the rendered
+rgb/depth/alpha inside the timed region.  `per_view_api` repeats both measurements one frame per call
+through the reference-shaped functions (_C.rasterize_gaussians / render_predicted_more_v2_gof).
+Timing: CUDA events per step on the launch stream, an L2 flush (256 MB write) between steps outside
+the events, max over ranks.
 
 `--impl reference` times the UNMODIFIED reference rasterizer (oracle/_ref/libgof_ref.so: its CUDA
 sources compiled for sm_100a -- the reference has no CPU implementation of this path) on the same
@@ -159,14 +161,41 @@ def traffic_from_profiles():
 
 # ------------------------------------------------------------------------------ arms --------
 class OursArm:
+    """The product.  A step = the 8 views of the scene in ONE batched pass (gof_forward_batch, sync-free
+    workspace mode); `per_view_step` = the same 8 frames through the reference-shaped one-frame call."""
     name = "ours"
+    KERNELS_PER_STEP = 5        # preprocess, tile_scan, scatter, tile_sort_gather, render_fwd (one launch each per batch)
 
     def __init__(self, device):
         from f3d_gaus_b200 import _lib
-        from f3d_gaus_b200.diff_gof_rasterization import _C
+        from f3d_gaus_b200.diff_gof_rasterization import _C, BatchWorkspace, rasterize_views
         self._lib, self._C, self.device = _lib, _C, device
+        self.rasterize_views = rasterize_views
+        self.ws = BatchWorkspace(device)
+        self.ws_e2e = BatchWorkspace(device)
         self.empty = torch.Tensor([])
-        self.launches_per_frame = None
+        self.batch = None
+        self.out = None
+
+    def _prepare(self, flat):
+        c = flat[0]
+        self.batch = dict(vm=torch.stack([f["viewmatrix"] for f in flat]).contiguous(),
+                          pm=torch.stack([f["projmatrix"] for f in flat]).contiguous(),
+                          cam=torch.stack([f["campos"] for f in flat]).contiguous())
+        self.out = torch.empty((len(flat), 9, c["H"], c["W"]), dtype=torch.float32, device=self.device)
+
+    def step(self, flat):
+        if self.batch is None:
+            self._prepare(flat)
+        c, b = flat[0], self.batch
+        self.rasterize_views(c["bg"], c["means3D"], None, c["opacities"], c["scales"], c["rotations"],
+                             c["scale_modifier"], b["vm"], b["pm"], c["tanfovx"], c["tanfovy"], c["kernel_size"],
+                             c["H"], c["W"], c["shs"], c["D"], b["cam"], workspace=self.ws, out_color=self.out)
+        return None
+
+    def finish(self):
+        """Per-view num_rendered of the last step (one mailbox read; None => the blob overflowed)."""
+        return self.ws.finish()
 
     def frame(self, c):
         e = self.empty
@@ -175,11 +204,10 @@ class OursArm:
                                            c["tanfovy"], c["kernel_size"], e, c["H"], c["W"], c["shs"], c["D"],
                                            c["campos"], False, False)
 
-    def step(self, flat):
+    def per_view_step(self, flat):
         R = 0
         for c in flat:
-            out = self.frame(c)
-            R += int(out[0])
+            R += int(self.frame(c)[0])
         return R
 
     def profile(self, on):
@@ -189,6 +217,22 @@ class OursArm:
         return self._lib.profile_read(self.device.index)
 
     def e2e_step(self, host_pc, dev_pc, cams_dev, cfg, bg, out_dev, out_host):
+        """Public API of the loop (render_views) from pinned host buffers: H2D of the Gaussian set, one batched
+        render of the 8 views, D2H of rgb/depth/alpha."""
+        from f3d_gaus_b200.gaussian_renderer import render_views
+        for k in host_pc:
+            dev_pc[k].copy_(host_pc[k], non_blocking=True)
+        o = render_views(dev_pc, 0, cams_dev[0], cams_dev[1], cams_dev[2], bg, cfg, workspace=self.ws_e2e, epilogue=False)
+        out_dev[:, 0:3].copy_(o["render"])
+        out_dev[:, 3:4].copy_(o["rendered_depth"])
+        out_dev[:, 4:5].copy_(o["rendered_alpha"])
+        out_host.copy_(out_dev, non_blocking=True)
+
+    def e2e_finish(self):
+        return self.ws_e2e.finish()
+
+    def e2e_per_view_step(self, host_pc, dev_pc, cams_dev, cfg, bg, out_dev, out_host):
+        """The same through the reference's own one-frame function (render_predicted_more_v2_gof)."""
         from f3d_gaus_b200.gaussian_renderer import render_predicted_more_v2_gof
         for k in host_pc:
             dev_pc[k].copy_(host_pc[k], non_blocking=True)
@@ -237,6 +281,12 @@ class ReferenceArm:
         pass
 
     def profile_read(self):
+        return None
+
+    def finish(self):
+        return None
+
+    def e2e_finish(self):
         return None
 
     def e2e_step(self, host_pc, dev_pc, cams_dev, cfg, bg, out_dev, out_host):
@@ -318,30 +368,68 @@ def main():
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
     P, K, W_ = P_SIDE * P_SIDE, args.steps, args.warmup
 
+    def timed_device(step_fn):
+        """K steps, CUDA events around each on the launch stream, L2 flush outside the events; max over ranks."""
+        for _ in range(W_):
+            step_fn()
+        torch.cuda.synchronize()
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        barrier(world)
+        for i in range(K):
+            flush.zero_()                      # L2 flush between timed iterations, outside the events
+            starts[i].record()
+            step_fn()
+            ends[i].record()
+        barrier(world)
+        return max_over_ranks(sum(s.elapsed_time(e) for s, e in zip(starts, ends)), world)
+
+    def timed_e2e(step_fn):
+        """Host clock around each step (host buffers in, host buffers out, device idle on both sides)."""
+        for _ in range(W_):
+            step_fn()
+        torch.cuda.synchronize()
+        barrier(world)
+        ms = 0.0
+        for i in range(K):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            step_fn()
+            torch.cuda.synchronize()
+            ms += (time.perf_counter() - t0) * 1e3
+        barrier(world)
+        return max_over_ranks(ms, world)
+
     # ---------------- kernel-level throughput: inputs resident in HBM -------------------------
-    for _ in range(W_):
-        R_step = arm.step(flat)
-    torch.cuda.synchronize()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    R_views = None
+    if args.impl == "ours":
+        arm.step(flat)
+        torch.cuda.synchronize()
+        if arm.finish() is None:               # first call sized the binning blob; overflow => it has been grown
+            arm.step(flat)
+            torch.cuda.synchronize()
+            assert arm.finish() is not None
     arm.profile(True)
     if args.impl == "ours":
         arm.profile_read()
-    barrier(world)
     sampler = ClockSampler(local) if rank == 0 else None
-    for i in range(K):
-        flush.zero_()                      # L2 flush between timed iterations, outside the events
-        starts[i].record()
-        arm.step(flat)
-        ends[i].record()
-    barrier(world)
+    total_ms = timed_device(lambda: arm.step(flat))
     clocks = sampler.stop() if sampler else None
     prof = arm.profile_read()
     arm.profile(False)
-    total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
-    total_ms = max_over_ranks(total_ms, world)
+    if args.impl == "ours":
+        R_views = arm.finish()
+        assert R_views is not None, "binning blob overflowed inside the timed region"
+        R_step = sum(R_views)
+    else:
+        R_step = arm.step(flat)
     frames = VIEWS * K * world
     value = frames / (total_ms * 1e-3)
+    per_view_value = None
+    if args.impl == "ours":
+        pv_ms = timed_device(lambda: arm.per_view_step(flat))
+        per_view_value = frames / (pv_ms * 1e-3)
 
     # ---------------- end to end through the public API, host buffers -------------------------
     host_pc = {k: v.pin_memory() for k, v in pc_cpu.items()}
@@ -350,21 +438,20 @@ def main():
     bg = torch.zeros(3, device=device)
     out_dev = torch.empty((VIEWS, 5, RES, RES), dtype=torch.float32, device=device)
     out_host = torch.empty((VIEWS, 5, RES, RES), dtype=torch.float32).pin_memory()
-    for _ in range(W_):
-        arm.e2e_step(host_pc, dev_pc, cams_dev, cfg, bg, out_dev, out_host)
-    torch.cuda.synchronize()
-    barrier(world)
-    e2e_ms = 0.0
-    for i in range(K):
-        flush.zero_()
+    e2e_args = (host_pc, dev_pc, cams_dev, cfg, bg, out_dev, out_host)
+    if args.impl == "ours":
+        arm.e2e_step(*e2e_args)
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        arm.e2e_step(host_pc, dev_pc, cams_dev, cfg, bg, out_dev, out_host)
-        torch.cuda.synchronize()
-        e2e_ms += (time.perf_counter() - t0) * 1e3
-    barrier(world)
-    e2e_ms = max_over_ranks(e2e_ms, world)
+        if arm.e2e_finish() is None:
+            arm.e2e_step(*e2e_args)
+    e2e_ms = timed_e2e(lambda: arm.e2e_step(*e2e_args))
+    if args.impl == "ours":
+        assert arm.e2e_finish() is not None, "binning blob overflowed inside the e2e region"
     e2e_value = frames / (e2e_ms * 1e-3)
+    e2e_pv_value = None
+    if args.impl == "ours":
+        e2e_pv_ms = timed_e2e(lambda: arm.e2e_per_view_step(*e2e_args))
+        e2e_pv_value = frames / (e2e_pv_ms * 1e-3)
     h2d = sum(v.numel() * v.element_size() for v in pc_cpu.values())
     d2h = out_host.numel() * out_host.element_size()
 
@@ -373,19 +460,20 @@ def main():
     launches = None
     peak, peak_src = measured_peak_gbs()
     if args.impl == "ours" and prof and prof["fwd_calls"]:
-        n_calls = prof["fwd_calls"]
+        n_calls = prof["fwd_calls"]            # one call = one batch of VIEWS frames = one launch of every kernel
         blend_ms = prof["fwd_ms"]["blend"] / n_calls
-        R_frame = R_step / VIEWS
-        abytes = algorithmic_bytes_render_fwd(P, R_frame, RES, RES)
+        abytes = sum(algorithmic_bytes_render_fwd(P, r, RES, RES) for r in R_views)
         achieved = abytes / (blend_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "render_fwd_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic_from_profiles(), "peak_source": peak_src,
+        traffic = traffic_from_profiles()
+        roofline = {"bound": "hbm", "kernel": "render_fwd_kernel (one launch blends the 8 frames of a step)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": abytes, "avg_launch_ms": blend_ms,
-                    "num_rendered_per_frame": R_frame,
-                    "stage_ms_per_frame": {k: v / n_calls for k, v in prof["fwd_ms"].items()}}
-        # kernels of ours per frame: preprocess, scan(2: init+scan), duplicate, sort (histogram +
-        # exclusive-sum + 6 onesweep passes for 41 bits), ranges/gather, blend; + 1 memset
-        launches = K * VIEWS * (1 + 2 + 1 + 8 + 1 + 1)
+                    "num_rendered_per_view": R_views,
+                    "stage_ms_per_step": {k: v / n_calls for k, v in prof["fwd_ms"].items()},
+                    "note": "issue/latency-bound kernel (256*R pair evaluations per frame against 15 MB of algorithmic "
+                            "traffic); see DESIGN.md 4"}
+        launches = K * arm.KERNELS_PER_STEP
 
     if rank != 0:
         return
@@ -395,7 +483,9 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "nvs256: 65536 f3d-like Gaussians (SH deg 1) per GPU, 8 orbit views, 256x256, forward "
                                "(BASELINE configs[1])", "frames_per_step": VIEWS, "num_rendered_per_step": R_step,
-                   "l2": "flushed (256 MB write) between timed steps"},
+                   "l2": "flushed (256 MB write) between timed steps",
+                   "api": ("value: gof_forward_batch (8 views per call, sync-free); e2e: render_views from pinned host "
+                           "buffers" if args.impl == "ours" else "one Rasterizer::forward call per frame")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / K},
@@ -403,6 +493,10 @@ def main():
     }
     if args.impl == "ours":
         line["roofline"] = roofline
+        line["per_view_api"] = {"value": per_view_value, "e2e": e2e_pv_value, "unit": "frames/s",
+                                "what": "the same frames one call per frame: value through _C.rasterize_gaussians "
+                                        "(blocking num_rendered hand-off per frame, like the reference), e2e through "
+                                        "render_predicted_more_v2_gof"}
         if world == 1 and not args.no_cpu_baseline:
             import cases
             flat_cpu = [cases.case_to(c, "cpu") for c in flat]

@@ -245,7 +245,7 @@ int gof_forward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* in
 	if ((rc = launch_binning(f, g, im, b, capacity, s)) != GOF_OK) return rc;
 	GOF_STAGE_CHECK(prm, s);
 	GOF_PROF_MARK(ctx, marks, s);
-	if ((rc = launch_render_fwd(*prm, f, im, b, in->background, bg_stride, out_color, s)) != GOF_OK) return rc;
+	if ((rc = launch_render_fwd(*prm, f, g, im, b, in->background, bg_stride, out_color, s)) != GOF_OK) return rc;
 	GOF_STAGE_CHECK(prm, s);
 	GOF_PROF_MARK(ctx, marks, s);
 	if (ctx->profiling) ctx->calls[0].push_back(std::move(marks));

@@ -131,26 +131,46 @@ tile_scan_kernel(int VT, int T, int V, const uint32_t* __restrict__ counts, uint
 	}
 }
 
-// One thread per (view, Gaussian): claim a slot in every touched tile's bucket.
+// One thread per (view, Gaussian): claim a slot in every touched tile's bucket.  Slots are claimed
+// per BLOCK: duplicates are counted in a shared-memory histogram, one global atomic per touched tile
+// reserves the block's share of the bucket, and threads then take their slots from the shared
+// counters (grids above SCATTER_TILES tiles claim straight from the global cursors).
+constexpr int SCATTER_TILES = 4096;
 __global__ void __launch_bounds__(256)
 scatter_kernel(int P, int T, dim3 grid, const uint32_t* __restrict__ tiles_touched, const ushort4* __restrict__ rect,
                const float* __restrict__ depths, uint32_t* __restrict__ cursor, uint64_t* __restrict__ entries,
                const int32_t* __restrict__ mailbox)
 {
-	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= P) return;
+	__shared__ uint32_t s_cur[SCATTER_TILES];
 	if (mailbox[1]) return;   // binning capacity exceeded (sync-free mode): outputs are invalid, write nothing
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	const int view = blockIdx.y;
 	const size_t g = (size_t)view * P + idx;
-	if (tiles_touched[g] == 0) return;
-	const ushort4 r = rect[g];
-	const uint64_t e = ((uint64_t)__float_as_uint(depths[g]) << 32) | (uint32_t)idx;
+	const bool active = idx < P && tiles_touched[g] != 0;
+	ushort4 r = make_ushort4(0, 0, 0, 0);
+	uint64_t e = 0;
+	if (active) {
+		r = rect[g];
+		e = ((uint64_t)__float_as_uint(depths[g]) << 32) | (uint32_t)idx;
+	}
 	uint32_t* cur = cursor + (size_t)view * T;
-	for (uint32_t y = r.y; y < r.w; y++)
-		for (uint32_t x = r.x; x < r.z; x++) {
-			const uint32_t slot = atomicAdd(&cur[y * grid.x + x], 1u);
-			entries[slot] = e;
+	if (T <= SCATTER_TILES) {
+		for (int i = threadIdx.x; i < T; i += 256) s_cur[i] = 0;
+		__syncthreads();
+		for (uint32_t y = r.y; y < r.w; y++)
+			for (uint32_t x = r.x; x < r.z; x++) atomicAdd(&s_cur[y * grid.x + x], 1u);
+		__syncthreads();
+		for (int i = threadIdx.x; i < T; i += 256) {
+			const uint32_t c = s_cur[i];
+			if (c) s_cur[i] = atomicAdd(&cur[i], c);      // first slot of this block's share
 		}
+		__syncthreads();
+		for (uint32_t y = r.y; y < r.w; y++)
+			for (uint32_t x = r.x; x < r.z; x++) entries[atomicAdd(&s_cur[y * grid.x + x], 1u)] = e;
+	} else {
+		for (uint32_t y = r.y; y < r.w; y++)
+			for (uint32_t x = r.x; x < r.z; x++) entries[atomicAdd(&cur[y * grid.x + x], 1u)] = e;
+	}
 }
 
 constexpr int SORT_THREADS = 256;
@@ -178,7 +198,7 @@ __device__ __forceinline__ void bitonic_sort(uint64_t* a, int n, int npad)
 }
 
 // One CTA per tile of the batch: sort the bucket, write point_list and the slab.
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, 3)
 tile_sort_gather_kernel(int P, int T, dim3 grid, int W, int H, float focal_x, float focal_y,
                         const uint2* __restrict__ ranges, uint64_t* __restrict__ entries,
                         const float* __restrict__ rec_all, uint32_t* __restrict__ point_list,

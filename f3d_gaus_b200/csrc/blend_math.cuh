@@ -65,6 +65,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
 	while (!mbar_try_wait(bar, parity)) {}
 }
+// Producer-side wait: the elected lane polls rarely so that it does not take issue slots from the
+// consumer warps of its scheduler.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity)
+{
+	while (!mbar_try_wait(bar, parity)) __nanosleep(200);
+}
+// Shared-memory loads by 32-bit shared-window address (no generic-address arithmetic in the loops).
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+	float4 v;
+	asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t addr)
+{
+	float2 v;
+	asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr)
+{
+	float v;
+	asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+	return v;
+}
 // TMA bulk copy global -> shared, completion signalled on `bar` (bytes % 16 == 0, 16-B aligned).
 __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
 {

@@ -97,7 +97,7 @@ int launch_preprocess(const GofParams& prm, const GofInputs& in, const Frame& f,
 int launch_tile_scan(const Frame& f, const GeomState& g, const ImgState& im, int64_t capacity, cudaStream_t s);
 int launch_binning(const Frame& f, const GeomState& g, const ImgState& im, const BinState& b, int64_t capacity,
                    cudaStream_t s);
-int launch_render_fwd(const GofParams& prm, const Frame& f, const ImgState& im, const BinState& b,
+int launch_render_fwd(const GofParams& prm, const Frame& f, const GeomState& g, const ImgState& im, const BinState& b,
                       const float* background, int bg_stride, float* out_color, cudaStream_t s);
 int launch_render_bwd(const GofParams& prm, const Frame& f, const GeomState& g, const ImgState& im,
                       const BinState& b, const float* background, const float* dL_dpix, float* gacc, cudaStream_t s);

@@ -19,6 +19,7 @@ namespace gof {
 namespace {
 
 constexpr int PRE_THREADS = 256;
+constexpr int HIST_TILES = 4096;      // shared-memory tile histogram up to this many tiles per view (16 KB)
 
 __device__ const float kSH_C0 = 0.28209479177387814f;
 __device__ const float kSH_C1 = 0.4886025119029199f;
@@ -290,6 +291,16 @@ __device__ __forceinline__ void stage_floats(const float* __restrict__ src, floa
 	for (int i = head + 4 * nvec + threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
 
+__device__ __forceinline__ void preprocess_one(const int idx, int P, int D, int M, const float* s_xyz, const float* s_scl,
+	const float* s_vm, const float* s_pm, const float* s_cam, const bool has_scales, const float scale_modifier,
+	const float* __restrict__ rotations, const float* __restrict__ opacities, const float* __restrict__ shs,
+	const float* __restrict__ cov3D_precomp, const float* __restrict__ colors_precomp, const float* __restrict__ v2g_precomp,
+	const int W, const int H, const float tan_fovx, const float tan_fovy, const float focal_x, const float focal_y,
+	const float kernel_size, int* __restrict__ radii, float2* __restrict__ means2D, float* __restrict__ depths,
+	float* __restrict__ rec, float4* __restrict__ conic_opacity, uint8_t* __restrict__ clamped, const dim3 grid,
+	uint32_t* __restrict__ tiles_touched, ushort4* __restrict__ rects, uint32_t* s_hist, uint32_t* __restrict__ tile_counts,
+	bool prefiltered);
+
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_kernel(int P, int D, int M,
 	const float* __restrict__ means3D, const float* __restrict__ scales, const float scale_modifier,
@@ -307,6 +318,12 @@ preprocess_kernel(int P, int D, int M,
 	__shared__ float s_xyz[PRE_THREADS * 3];
 	__shared__ float s_scl[PRE_THREADS * 3];
 	__shared__ float s_vm[16], s_pm[16], s_cam[3];
+	// Tile histogram of this block's duplicates: counted in shared memory, flushed with one global
+	// atomic per touched tile (grids above HIST_TILES tiles count straight into global memory).
+	__shared__ uint32_t s_hist[HIST_TILES];
+	const int T = grid.x * grid.y;
+	const bool use_hist = T <= HIST_TILES;
+	if (use_hist) for (int i = threadIdx.x; i < T; i += PRE_THREADS) s_hist[i] = 0;
 
 	// blockIdx.y = view of the batch: per-view camera, per-view slice of every state array
 	const int view = blockIdx.y;
@@ -333,8 +350,30 @@ preprocess_kernel(int P, int D, int M,
 	__syncthreads();
 
 	const int idx = base + threadIdx.x;
-	if (idx >= P) return;
+	if (idx < P) preprocess_one(idx, P, D, M, s_xyz, s_scl, s_vm, s_pm, s_cam, scales != nullptr, scale_modifier, rotations, opacities, shs,
+	                            cov3D_precomp, colors_precomp, v2g_precomp, W, H, tan_fovx, tan_fovy, focal_x, focal_y, kernel_size,
+	                            radii, means2D, depths, rec, conic_opacity, clamped, grid, tiles_touched, rects,
+	                            use_hist ? s_hist : nullptr, tile_counts, prefiltered);
+	if (use_hist) {
+		__syncthreads();
+		for (int i = threadIdx.x; i < T; i += PRE_THREADS) {
+			const uint32_t c = s_hist[i];
+			if (c) atomicAdd(&tile_counts[i], c);
+		}
+	}
+}
 
+// One Gaussian of one view (the body of the reference's preprocessCUDA, forward.cu:283-404).
+__device__ __forceinline__ void preprocess_one(const int idx, int P, int D, int M, const float* s_xyz, const float* s_scl,
+	const float* s_vm, const float* s_pm, const float* s_cam, const bool has_scales, const float scale_modifier,
+	const float* __restrict__ rotations, const float* __restrict__ opacities, const float* __restrict__ shs,
+	const float* __restrict__ cov3D_precomp, const float* __restrict__ colors_precomp, const float* __restrict__ v2g_precomp,
+	const int W, const int H, const float tan_fovx, const float tan_fovy, const float focal_x, const float focal_y,
+	const float kernel_size, int* __restrict__ radii, float2* __restrict__ means2D, float* __restrict__ depths,
+	float* __restrict__ rec, float4* __restrict__ conic_opacity, uint8_t* __restrict__ clamped, const dim3 grid,
+	uint32_t* __restrict__ tiles_touched, ushort4* __restrict__ rects, uint32_t* s_hist, uint32_t* __restrict__ tile_counts,
+	bool prefiltered)
+{
 	// Not visible until proven otherwise (forward.cu:317-320).
 	radii[idx] = 0;
 	tiles_touched[idx] = 0;
@@ -363,7 +402,7 @@ preprocess_kernel(int P, int D, int M,
 
 	V3 scale = { 0.f, 0.f, 0.f };
 	float4 rot = { 0.f, 0.f, 0.f, 0.f };
-	if (scales) scale = { s_scl[3 * threadIdx.x], s_scl[3 * threadIdx.x + 1], s_scl[3 * threadIdx.x + 2] };
+	if (has_scales) scale = { s_scl[3 * threadIdx.x], s_scl[3 * threadIdx.x + 1], s_scl[3 * threadIdx.x + 2] };
 	if (rotations) {
 		if ((reinterpret_cast<uintptr_t>(rotations) & 15) == 0) rot = __ldg(reinterpret_cast<const float4*>(rotations) + idx);
 		else rot = { rotations[4 * idx], rotations[4 * idx + 1], rotations[4 * idx + 2], rotations[4 * idx + 3] };
@@ -438,8 +477,9 @@ preprocess_kernel(int P, int D, int M,
 	// Tile histogram for the bucketed binning (binning.cu): one count per (tile, Gaussian) duplicate.
 	rects[idx] = make_ushort4((unsigned short)rect_min.x, (unsigned short)rect_min.y, (unsigned short)rect_max.x,
 	                          (unsigned short)rect_max.y);
+	uint32_t* hist = s_hist ? s_hist : tile_counts;
 	for (uint32_t y = rect_min.y; y < rect_max.y; y++)
-		for (uint32_t x = rect_min.x; x < rect_max.x; x++) atomicAdd(&tile_counts[y * grid.x + x], 1u);
+		for (uint32_t x = rect_min.x; x < rect_max.x; x++) atomicAdd(&hist[y * grid.x + x], 1u);
 
 	float q[10];
 	if (v2g_precomp == nullptr) {

@@ -103,7 +103,8 @@ template <bool EXACT>
 __global__ void __launch_bounds__(FWD_THREADS)
 render_fwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ slab, int W, int H,
                   float focal_x, float focal_y, const float* __restrict__ bg_colors, int bg_stride,
-                  float* __restrict__ final_T_all, uint32_t* __restrict__ n_contrib_all, float* __restrict__ out_color_all)
+                  float* __restrict__ final_T_all, uint32_t* __restrict__ n_contrib_all, float* __restrict__ out_color_all,
+                  const int32_t* __restrict__ mailbox)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	float4 (*s_rec)[CHUNK * REC_F4] = reinterpret_cast<float4 (*)[CHUNK * REC_F4]>(smem_raw);
@@ -116,7 +117,9 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 	const size_t N = (size_t)W * H;
 
 	const uint2 range = ranges[((size_t)view * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x];
-	const int n = (int)(range.y - range.x);
+	// sync-free mode: if the binning blob was too small nothing was binned -- blend empty lists (the
+	// caller sees the overflow flag in the mailbox and re-runs the batch with a larger blob)
+	const int n = mailbox[1] ? 0 : (int)(range.y - range.x);
 	const int nchunks = (n + CHUNK - 1) / CHUNK;
 	const float* tile_slab = slab + (size_t)range.x * SLAB_FLOATS;
 
@@ -132,7 +135,7 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 		if (lane == 0) {
 			for (int c = 0; c < nchunks; c++) {
 				const int s = c % STAGES;
-				if (c >= STAGES) mbar_wait(&s_empty[s], (uint32_t)(((c / STAGES) - 1) & 1));
+				if (c >= STAGES) mbar_wait_backoff(&s_empty[s], (uint32_t)(((c / STAGES) - 1) & 1));
 				const int cnt = min(CHUNK, n - c * CHUNK);
 				const uint32_t bytes = (uint32_t)cnt * SLAB_BYTES;
 				mbar_arrive_expect_tx(&s_full[s], bytes);
@@ -162,45 +165,50 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 	bool done = !inside;
 	bool warp_done = __all_sync(0xffffffffu, done);
 
+	const uint32_t rec_base = smem_u32(smem_raw);
 	for (int c = 0; c < nchunks; c++) {
 		const int s = c % STAGES;
 		mbar_wait(&s_full[s], (uint32_t)((c / STAGES) & 1));
 		if (!warp_done) {
 			const int cnt = min(CHUNK, n - c * CHUNK);
-			const float4* rec = &s_rec[s][0];
+			const uint32_t rec = rec_base + (uint32_t)s * (CHUNK * SLAB_BYTES);   // shared-window address of the stage
 			const uint32_t base = (uint32_t)c * CHUNK;
 			// ---- pass 1: branch-free conic sweep over the chunk (broadcast reads, 5 FMAs per pair) ----
-			unsigned long long m_lo = 0, m_hi = 0;   // survivors among records [0,64) and [64,128)
+			uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;   // survivors among records [0,32) [32,64) [64,96) [96,128)
 #pragma unroll 1
 			for (int w = 0; w < CHUNK / 32; w++) {
 				const int valid = cnt - 32 * w;
 				if (valid <= 0) break;
 				uint32_t bits = 0;
-				const float4* rw = rec + REC_F4 * 32 * w;
+				const uint32_t rw = rec + (uint32_t)w * (32 * SLAB_BYTES);
 #pragma unroll
 				for (int jj = 0; jj < 32; jj++) {
-					const float4 k0 = rw[REC_F4 * jj];
-					const float2 k1 = *reinterpret_cast<const float2*>(&rw[REC_F4 * jj + 1]);
+					const float4 k0 = lds128(rw + jj * SLAB_BYTES);
+					const float2 k1 = lds64(rw + jj * SLAB_BYTES + 16);
 					if (!conic_reject(k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, fx, fy)) bits |= 1u << jj;
 				}
 				if (valid < 32) bits &= (1u << valid) - 1u;   // stale records beyond the list end
-				if (w < 2) m_lo |= (unsigned long long)bits << (32 * w);
-				else m_hi |= (unsigned long long)bits << (32 * (w - 2));
+				if (w == 0) m0 = bits; else if (w == 1) m1 = bits; else if (w == 2) m2 = bits; else m3 = bits;
 			}
-			if (done) { m_lo = 0; m_hi = 0; }
-			// ---- pass 2: each pixel blends its own survivors, in list order -------------------------
-			while ((m_lo | m_hi) != 0) {
-				int j;
-				if (m_lo != 0) { j = __ffsll((long long)m_lo) - 1; m_lo &= m_lo - 1; }
-				else { j = 64 + __ffsll((long long)m_hi) - 1; m_hi &= m_hi - 1; }
-				const float4* r = rec + REC_F4 * j;
-				const float4 k1 = r[1], a = r[2], b = r[3], cc = r[4];
-				const PairGeom g = pair_geom(a, b, cc, rx, ry);
-				if (pair_pretest_reject(g, cc.y, k1.z)) continue;
-				float t, alpha, G;
-				if (!pair_alpha_exact(g, cc.y, k1.w, t, alpha, G)) continue;
-				const float4 d = make_float4(cc.z, cc.w, r[5].x, 0.0f);
-				if (blend_pair<EXACT>(st, g, t, alpha, d, base + j + 1)) { done = true; m_lo = 0; m_hi = 0; }
+			if (done) { m0 = 0; m1 = 0; m2 = 0; m3 = 0; }
+			// ---- pass 2: each pixel blends its own survivors, in list order.  ONE loop over the whole
+			// chunk: the warp iterates max-over-lanes(survivors in 128 records) times, m0 is the word being
+			// consumed, m1..m3 shift down when it runs empty.
+			uint32_t jbase = 0;
+			while ((m0 | m1 | m2 | m3) != 0) {
+				if (m0 == 0) { m0 = m1; m1 = m2; m2 = m3; m3 = 0; jbase += 32; }
+				if (m0 != 0) {
+					const uint32_t j = jbase + (uint32_t)__ffs((int)m0) - 1u;
+					m0 &= m0 - 1u;
+					const uint32_t r = rec + j * SLAB_BYTES;
+					const float4 a = lds128(r + 32), b = lds128(r + 48), cc = lds128(r + 64);
+					const PairGeom g = pair_geom(a, b, cc, rx, ry);
+					float t, alpha, G;
+					if (pair_alpha_exact(g, cc.y, lds32(r + 28), t, alpha, G)) {
+						const float4 d = make_float4(cc.z, cc.w, lds32(r + 80), 0.0f);
+						if (blend_pair<EXACT>(st, g, t, alpha, d, base + j + 1)) { done = true; m0 = 0; m1 = 0; m2 = 0; m3 = 0; }
+					}
+				}
 			}
 			warp_done = __all_sync(0xffffffffu, done);
 		}
@@ -232,7 +240,7 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 
 }  // namespace
 
-int launch_render_fwd(const GofParams& prm, const Frame& f, const ImgState& im, const BinState& b,
+int launch_render_fwd(const GofParams& prm, const Frame& f, const GeomState& g, const ImgState& im, const BinState& b,
                       const float* background, int bg_stride, float* out_color, cudaStream_t s)
 {
 	const dim3 grid(f.grid.x, f.grid.y, f.V);
@@ -245,10 +253,10 @@ int launch_render_fwd(const GofParams& prm, const Frame& f, const ImgState& im, 
 	}
 	if (prm.flags & GOF_FLAG_EXACT_BLEND)
 		render_fwd_kernel<true><<<grid, FWD_THREADS, smem, s>>>(im.ranges, b.slab, prm.W, prm.H, f.focal_x, f.focal_y,
-		                                                     background, bg_stride, im.final_T, im.n_contrib, out_color);
+		                                                     background, bg_stride, im.final_T, im.n_contrib, out_color, g.mailbox);
 	else
 		render_fwd_kernel<false><<<grid, FWD_THREADS, smem, s>>>(im.ranges, b.slab, prm.W, prm.H, f.focal_x, f.focal_y,
-		                                                      background, bg_stride, im.final_T, im.n_contrib, out_color);
+		                                                      background, bg_stride, im.final_T, im.n_contrib, out_color, g.mailbox);
 	GOF_CUDA_CHECK(cudaGetLastError());
 	return GOF_OK;
 }

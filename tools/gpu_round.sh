@@ -13,6 +13,8 @@ cat $OUT/bench_reference.json $OUT/bench_ours.json
 timeout 300 python tools/quick_bench.py 256 256 50 > $OUT/quick_bench.log 2>&1; cat $OUT/quick_bench.log
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/launches_bench.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'render_fwd_kernel|render_bwd_kernel' -s 16 -c 4 \
-    -o $OUT/prof_blend python tools/quick_bench.py 256 256 3 > $OUT/ncu_full.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'render_fwd_kernel|tile_sort_gather|preprocess_kernel|scatter_kernel' -s 12 -c 5 \
+    -o $OUT/prof_blend python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'render_bwd_kernel' -s 6 -c 1 \
+    -o $OUT/prof_bwd python tools/quick_bench.py 256 256 3 > $OUT/ncu_full_bwd.log 2>&1
 ls -la $OUT

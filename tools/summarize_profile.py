@@ -41,6 +41,7 @@ def launches(src, out_md, title):
             continue
         k = re.sub(r"\(.*", "", r[ki])
         k = re.sub(r"<unnamed>::", "", k)[:100]
+        k = (k, r[gi], r[bi])                      # same kernel at different grids = different work
         a = agg.setdefault(k, [0, 0.0, r[gi], r[bi]])
         a[0] += 1
         a[1] += v
@@ -51,7 +52,7 @@ def launches(src, out_md, title):
         f.write("| launches | total us | share | avg us | grid | block | kernel |\n|---:|---:|---:|---:|---|---|---|\n")
         for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
             f.write(f"| {a[0]} | {a[1] / 1e3:.1f} | {100 * a[1] / tot:.1f}% | {a[1] / a[0] / 1e3:.2f} | {a[2]} | {a[3]} "
-                    f"| `{k}` |\n")
+                    f"| `{k[0]}` |\n")
         f.write(f"\nTotal device time in the list: {tot / 1e6:.3f} ms over {sum(a[0] for a in agg.values())} launches.\n")
     return agg
 
