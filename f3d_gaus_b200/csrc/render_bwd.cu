@@ -7,16 +7,20 @@
 // the distortion gradient flows only through the mapped depth (dL_dweight is detached), the
 // power/alpha clamps are not gated.
 //
-// B200 design:
-//   * same TMA-streamed slab as the forward, walked from the tile's deepest contributor
-//     (block-max of last_contributor) towards the front; chunks behind it are never loaded;
-//   * same float32 pre-test + exact alpha as the forward (blend_math.cuh), so the set of
-//     contributing pairs is identical to the forward's by construction;
-//   * the reference issues 17 scalar global atomics per contributing (pixel, Gaussian) pair.
-//     Here all lanes of a warp visit the same Gaussian in lock-step, the 17 partial gradients
-//     are summed across the warp with shuffles, and one lane issues five 128-bit vector
-//     reductions (red.global.add.v4.f32) into a packed 80-byte per-Gaussian accumulator.
-//     Warps with <= 2 contributing lanes skip the shuffle tree and reduce directly.
+// B200 design (same skeleton as the forward blend, render_fwd.cu):
+//   * one CTA per tile: 8 consumer warps (8x4 pixels each) + one producer warp; the tile's
+//     slab is streamed by TMA bulk copies into a shared-memory ring, walked from the tile's deepest
+//     contributor (block-max of last_contributor) towards the front -- chunks behind it are never
+//     loaded; full/empty mbarriers per stage, no CTA-wide barrier in the loop;
+//   * per 128-record chunk, pass 1 is the branch-free conic sweep (conic.cuh) that leaves each
+//     pixel a 128-bit survivor mask, pass 2 is lane-private: each pixel walks ITS survivors from
+//     the back, re-evaluates the exact alpha (blend_math.cuh -- the contributing set therefore
+//     equals the forward's by construction) and forms the 17 partial gradients of the pair;
+//   * the reference issues 17 scalar global atomics per contributing (pixel, Gaussian) pair; here a
+//     pair issues four 128-bit vector reductions (red.global.add.v4.f32) + one scalar into a packed
+//     80-byte per-Gaussian accumulator that the backward preprocess unpacks.  (Shared-memory
+//     accumulation was measured and rejected: float atomic-add has no native shared-memory form on
+//     sm_100a -- it compiles to a compare-and-swap spin loop, ATOMS.CAST.SPIN -- and was slower.)
 #include "blend_math.cuh"
 #include "conic.cuh"
 
@@ -26,46 +30,40 @@ namespace {
 
 constexpr int CHUNK = 128;
 constexpr int STAGES = 3;
-constexpr int REC_F4 = SLAB_FLOATS / 4;
+constexpr int CONSUMER_WARPS = TILE_PIX / 32;
+constexpr int BWD_THREADS = TILE_PIX + 32;
+constexpr int STAGE_REC_BYTES = CHUNK * SLAB_BYTES;      // 12 KB
+constexpr size_t BWD_SMEM = (size_t)STAGES * STAGE_REC_BYTES + 2 * STAGES * sizeof(uint64_t) + 64;
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d)
+__device__ __forceinline__ void red_global_v4(float* addr, float4 v)
 {
-	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-__device__ __forceinline__ float warp_sum(float v)
-{
-	v += __shfl_xor_sync(0xffffffffu, v, 16);
-	v += __shfl_xor_sync(0xffffffffu, v, 8);
-	v += __shfl_xor_sync(0xffffffffu, v, 4);
-	v += __shfl_xor_sync(0xffffffffu, v, 2);
-	v += __shfl_xor_sync(0xffffffffu, v, 1);
-	return v;
-}
-
-__global__ void __launch_bounds__(TILE_PIX)
+__global__ void __launch_bounds__(BWD_THREADS)
 render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ slab, int P, int W, int H,
                   float focal_x, float focal_y, const float* __restrict__ bg_colors, int bg_stride,
                   const float2* __restrict__ means2D_all, const float4* __restrict__ conic_opacity_all,
                   const float* __restrict__ final_Ts_all, const uint32_t* __restrict__ n_contrib_all,
                   const float* __restrict__ dL_dpixels_all, float* __restrict__ gacc_all)
 {
-	__shared__ __align__(128) float4 s_rec[STAGES][CHUNK * REC_F4];
-	__shared__ __align__(8) uint64_t s_full[STAGES];
-	__shared__ uint32_t s_max[TILE_PIX / 32];
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	// layout: [STAGES] record stages | full[STAGES] | empty[STAGES] | s_max[8]
+	const uint32_t rec_base = smem_u32(smem_raw);
+	uint64_t* s_full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * STAGE_REC_BYTES);
+	uint64_t* s_empty = s_full + STAGES;
+	uint32_t* s_max = reinterpret_cast<uint32_t*>(s_empty + STAGES);
 
 	const int tid = threadIdx.x;
 	const int warp = tid >> 5, lane = tid & 31;
 	const int view = blockIdx.z;
-	const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
+	const bool consumer = warp < CONSUMER_WARPS;
+	const int lx = (warp & 1) * 8 + (lane & 7), ly = ((warp >> 1) & 3) * 4 + (lane >> 3);
 	const uint32_t px = blockIdx.x * TILE_X + lx;
 	const uint32_t py = blockIdx.y * TILE_Y + ly;
-	const bool inside = px < (uint32_t)W && py < (uint32_t)H;
+	const bool inside = consumer && px < (uint32_t)W && py < (uint32_t)H;
 	const uint32_t pix_id = W * py + px;
 	const size_t N = (size_t)W * H;
-	const float rx = pixel_ray(px, W, focal_x);
-	const float ry = pixel_ray(py, H, focal_y);
-	const float fx = (float)lx, fy = (float)ly;
 
 	const float* bg_color = bg_colors + (size_t)view * bg_stride;
 	const float2* means2D = means2D_all + (size_t)view * P;
@@ -82,34 +80,42 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 	const uint32_t last_contributor = inside ? n_contrib[pix_id] : 0;
 	const uint32_t max_contributor = inside ? n_contrib[pix_id + N] : 0;
 
-	// Deepest record any pixel of this tile blended.
-	uint32_t wmax = __reduce_max_sync(0xffffffffu, last_contributor);
-	if (lane == 0) s_max[warp] = wmax;
+	// Deepest record any pixel of this tile blended; init barriers.
+	const uint32_t wmax = __reduce_max_sync(0xffffffffu, last_contributor);
+	if (consumer && lane == 0) s_max[warp] = wmax;
 	if (tid == 0) {
 #pragma unroll
-		for (int s = 0; s < STAGES; s++) mbar_init(&s_full[s], 1);
+		for (int s = 0; s < STAGES; s++) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], CONSUMER_WARPS); }
 		mbar_fence_init();
 	}
 	__syncthreads();
 	uint32_t tile_last = 0;
 #pragma unroll
-	for (int k = 0; k < TILE_PIX / 32; k++) tile_last = max(tile_last, s_max[k]);
-	const int m = min((int)tile_last, n);          // records [0, m) may contribute
-	const int nchunks = (m + CHUNK - 1) / CHUNK;    // walked from chunk nchunks-1 down to 0
+	for (int k = 0; k < CONSUMER_WARPS; k++) tile_last = max(tile_last, s_max[k]);
+	const int m = min((int)tile_last, n);           // records [0, m) may contribute
+	const int nchunks = (m + CHUNK - 1) / CHUNK;     // walked from chunk nchunks-1 down to 0
+	// the i-th chunk in walk order is chunk (nchunks-1-i); it lives in stage i % STAGES
 
-	// i-th chunk in walk order is chunk (nchunks-1-i); it lives in stage i % STAGES.
-	auto issue = [&](int i) {
-		const int c = nchunks - 1 - i;
-		const int s = i % STAGES;
-		const int cnt = min(CHUNK, m - c * CHUNK);
-		const uint32_t bytes = (uint32_t)cnt * SLAB_BYTES;
-		mbar_arrive_expect_tx(&s_full[s], bytes);
-		tma_bulk_g2s(&s_rec[s][0], tile_slab + (size_t)c * CHUNK * SLAB_FLOATS, bytes, &s_full[s]);
-	};
-	if (tid == 0) {
-		const int pre = min(STAGES, nchunks);
-		for (int i = 0; i < pre; i++) issue(i);
+	if (!consumer) {
+		// ------------- producer warp: one elected lane streams the slab, deepest chunk first ---------
+		if (lane == 0) {
+			for (int i = 0; i < nchunks; i++) {
+				const int s = i % STAGES;
+				if (i >= STAGES) mbar_wait_backoff(&s_empty[s], (uint32_t)(((i / STAGES) - 1) & 1));
+				const int c = nchunks - 1 - i;
+				const int cnt = min(CHUNK, m - c * CHUNK);
+				const uint32_t bytes = (uint32_t)cnt * SLAB_BYTES;
+				mbar_arrive_expect_tx(&s_full[s], bytes);
+				tma_bulk_g2s(smem_raw + (size_t)s * STAGE_REC_BYTES, tile_slab + (size_t)c * CHUNK * SLAB_FLOATS, bytes, &s_full[s]);
+			}
+		}
+		return;
 	}
+
+	// ------------- consumer warps -----------------------------------------------------------------
+	const float rx = pixel_ray(px, W, focal_x);
+	const float ry = pixel_ray(py, H, focal_y);
+	const float fx = (float)lx, fy = (float)ly;
 
 	// Per-pixel state (backward.cu:690-735).
 	const float T_final = inside ? final_Ts[pix_id] : 0;
@@ -139,41 +145,44 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 		const int s = i % STAGES;
 		mbar_wait(&s_full[s], (uint32_t)((i / STAGES) & 1));
 		const int cnt = min(CHUNK, m - c * CHUNK);
-		const float4* rec = &s_rec[s][0];
+		const uint32_t rec = rec_base + s * STAGE_REC_BYTES;
 		const uint32_t base = (uint32_t)c * CHUNK;
 
-		// walk the chunk back to front, 4 records per pre-test group
-		for (int j1 = cnt; j1 > 0; j1 -= 4) {
-			uint32_t mask = 0;
+		// ---- pass 1: conic sweep; only records this pixel blended (index < last_contributor) ----
+		uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+		if (base < last_contributor) {
+#pragma unroll 1
+			for (int w = 0; w < CHUNK / 32; w++) {
+				const int valid = min(cnt, (int)(last_contributor - base)) - 32 * w;
+				if (valid <= 0) break;
+				uint32_t bits = 0;
+				const uint32_t rw = rec + (uint32_t)w * (32 * SLAB_BYTES);
 #pragma unroll
-			for (int k = 0; k < 4; k++) {
-				const int j = j1 - 1 - k;
-				if (j >= 0 && base + j < last_contributor) {
-					const float4 k0 = rec[REC_F4 * j];
-					const float2 k1 = *reinterpret_cast<const float2*>(&rec[REC_F4 * j + 1]);
-					if (!conic_reject(k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, fx, fy)) mask |= 1u << k;
+				for (int jj = 0; jj < 32; jj++) {
+					const float4 k0 = lds128(rw + jj * SLAB_BYTES);
+					const float2 k1 = lds64(rw + jj * SLAB_BYTES + 16);
+					if (!conic_reject(k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, fx, fy)) bits |= 1u << jj;
 				}
+				if (valid < 32) bits &= (1u << valid) - 1u;
+				if (w == 0) m0 = bits; else if (w == 1) m1 = bits; else if (w == 2) m2 = bits; else m3 = bits;
 			}
-			uint32_t wmask = __reduce_or_sync(0xffffffffu, mask);
-			while (wmask) {   // warp-uniform loop over records some lane must evaluate exactly
-				const int k = __ffs(wmask) - 1;
-				wmask &= wmask - 1;
-				const int j = j1 - 1 - k;
-				const float4 k1 = rec[REC_F4 * j + 1], a = rec[REC_F4 * j + 2], b = rec[REC_F4 * j + 3], cc = rec[REC_F4 * j + 4];
-				const float4 k5 = rec[REC_F4 * j + 5];
-				const float4 d = make_float4(cc.z, cc.w, k5.x, k5.y);   // rgb, id
+		}
+		// ---- pass 2: this pixel's survivors, back to front; m3 is the word being consumed ----------
+		uint32_t jbase = 96;
+		while ((m0 | m1 | m2 | m3) != 0) {
+			if (m3 == 0) { m3 = m2; m2 = m1; m1 = m0; m0 = 0; jbase -= 32; }
+			if (m3 != 0) {
+				const uint32_t bit = 31u - (uint32_t)__clz((int)m3);
+				m3 &= ~(1u << bit);
+				const uint32_t j = jbase + bit;
+				const uint32_t r = rec + j * SLAB_BYTES;
+				const float4 a = lds128(r + 32), b = lds128(r + 48), cc = lds128(r + 64);
 				const PairGeom g = pair_geom(a, b, cc, rx, ry);
-				float t = 0, alpha = 0, G = 0;
-				bool contrib = false;
-				if ((mask & (1u << k)) && !pair_pretest_reject(g, cc.y, k1.z)) contrib = pair_alpha_exact(g, cc.y, k1.w, t, alpha, G);
-				const uint32_t cmask = __ballot_sync(0xffffffffu, contrib);
-				if (cmask == 0) continue;
-
-				float gv[17];
-#pragma unroll
-				for (int q = 0; q < 17; q++) gv[q] = 0.0f;
-				const int gid = __float_as_int(d.w);
-				if (contrib) {
+				const float w = lds32(r + 28);
+				float t, alpha, G;
+				if (pair_alpha_exact(g, cc.y, w, t, alpha, G)) {
+					const float2 k5 = lds64(r + 80);       // b, id
+					const int gid = __float_as_int(k5.y);
 					const uint32_t contributor = base + j;   // 0-based position in the tile list
 					const double td = t;
 					const float mapped = (float)(fma(td, 100.0, -(100.0 * 0.2)) / ((100.0 - 0.2) * td));
@@ -181,17 +190,19 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 					const float length = (float)sqrt((double)(g.n0 * g.n0 + g.n1 * g.n1 + g.n2 * g.n2) + 1e-7);
 					const float nn[3] = { -g.n0 / length, -g.n1 / length, -g.n2 / length };
 					const float nraw[3] = { g.n0, g.n1, g.n2 };
+					float* dst = gacc + (size_t)gid * GACC_FLOATS;
+					float gcol[3];
 
 					T = T / (1.f - alpha);
 					const float weight = alpha * T;
 					float dL_dalpha = 0.0f;
-					const float col[3] = { d.x, d.y, d.z };
+					const float col[3] = { cc.z, cc.w, k5.x };
 #pragma unroll
 					for (int ch = 0; ch < 3; ch++) {
 						accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
 						last_color[ch] = col[ch];
 						dL_dalpha += (col[ch] - accum_rec[ch]) * dL_dpixel[ch];
-						gv[10 + ch] = weight * dL_dpixel[ch];
+						gcol[ch] = weight * dL_dpixel[ch];
 					}
 					// distortion: only through the mapped depth (weights detached)
 					const float dL_dmax_t = 2.0f * weight * (mapped * final_A - final_D) * dL_dreg * dmax_t_dd;
@@ -217,20 +228,15 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 					last_alpha = alpha;
 					dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
 
-					const float w = k1.w;
 					const float dL_dG = w * dL_dalpha;
-					const float2 xy = means2D[gid];
-					const float4 con = conic_opacity[gid];
+					const float2 xy = __ldg(&means2D[gid]);
+					const float4 con = __ldg(&conic_opacity[gid]);
 					const float dx = xy.x - (float)px, dy = xy.y - (float)py;
 					const float gdx = G * dx, gdy = G * dy;
 					const float dG_ddelx = -gdx * con.x - gdy * con.y;
 					const float dG_ddely = -gdy * con.z - gdx * con.y;
 					const float gmx = dL_dG * dG_ddelx * ddelx_dx;
 					const float gmy = dL_dG * dG_ddely * ddely_dy;
-					gv[14] = gmx;
-					gv[15] = gmy;
-					gv[16] = fabsf(gmx) + fabsf(gmy);
-					gv[13] = G * dL_dalpha;
 
 					const float dL_dmin_value = dL_dG * G * -0.5f;
 					const double AA = g.AA, BB = g.BB;
@@ -243,42 +249,16 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 					dL_dn[1] += dL_dA * ry;
 					dL_dn[2] += dL_dA;
 
-					gv[0] = dL_dn[0] * rx;
-					gv[1] = dL_dn[0] * ry + dL_dn[1] * rx;
-					gv[2] = dL_dn[0] + dL_dn[2] * rx;
-					gv[3] = dL_dn[1] * ry;
-					gv[4] = dL_dn[1] + dL_dn[2] * ry;
-					gv[5] = dL_dn[2];
-					gv[6] = dL_dB * 2 * rx;
-					gv[7] = dL_dB * 2 * ry;
-					gv[8] = dL_dB * 2;
-					gv[9] = dL_dC;
-				}
-
-				float* dst = gacc + (size_t)gid * GACC_FLOATS;
-				if (__popc(cmask) <= 2) {
-					if (contrib) {
-						red_add_v4(dst + 0, gv[0], gv[1], gv[2], gv[3]);
-						red_add_v4(dst + 4, gv[4], gv[5], gv[6], gv[7]);
-						red_add_v4(dst + 8, gv[8], gv[9], gv[10], gv[11]);
-						red_add_v4(dst + 12, gv[12], gv[13], gv[14], gv[15]);
-						atomicAdd(dst + 16, gv[16]);
-					}
-				} else {
-#pragma unroll
-					for (int q = 0; q < 17; q++) gv[q] = warp_sum(gv[q]);
-					if (lane == 0) {
-						red_add_v4(dst + 0, gv[0], gv[1], gv[2], gv[3]);
-						red_add_v4(dst + 4, gv[4], gv[5], gv[6], gv[7]);
-						red_add_v4(dst + 8, gv[8], gv[9], gv[10], gv[11]);
-						red_add_v4(dst + 12, gv[12], gv[13], gv[14], gv[15]);
-						atomicAdd(dst + 16, gv[16]);
-					}
+					red_global_v4(dst + 0, make_float4(dL_dn[0] * rx, dL_dn[0] * ry + dL_dn[1] * rx, dL_dn[0] + dL_dn[2] * rx, dL_dn[1] * ry));
+					red_global_v4(dst + 4, make_float4(dL_dn[1] + dL_dn[2] * ry, dL_dn[2], (float)(dL_dB * 2 * rx), (float)(dL_dB * 2 * ry)));
+					red_global_v4(dst + 8, make_float4((float)(dL_dB * 2), (float)dL_dC, gcol[0], gcol[1]));
+					red_global_v4(dst + 12, make_float4(gcol[2], G * dL_dalpha, gmx, gmy));
+					atomicAdd(dst + 16, fabsf(gmx) + fabsf(gmy));
 				}
 			}
 		}
-		__syncthreads();   // everyone is done with stage s
-		if (tid == 0 && i + STAGES < nchunks) issue(i + STAGES);
+		__syncwarp();
+		if (lane == 0) mbar_arrive(&s_empty[s]);   // this warp is finished with stage s
 	}
 }
 
@@ -288,8 +268,9 @@ int launch_render_bwd(const GofParams& prm, const Frame& f, const GeomState& g, 
                       const BinState& b, const float* background, const float* dL_dpix, float* gacc, cudaStream_t s)
 {
 	const dim3 grid(f.grid.x, f.grid.y, f.V);
-	render_bwd_kernel<<<grid, TILE_PIX, 0, s>>>(im.ranges, b.slab, f.P, prm.W, prm.H, f.focal_x, f.focal_y, background, 0,
-	                                           g.means2D, g.conic_opacity, im.final_T, im.n_contrib, dL_dpix, gacc);
+	GOF_CUDA_CHECK(cudaFuncSetAttribute(render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
+	render_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, s>>>(im.ranges, b.slab, f.P, prm.W, prm.H, f.focal_x, f.focal_y, background, 0,
+	                                                     g.means2D, g.conic_opacity, im.final_T, im.n_contrib, dL_dpix, gacc);
 	GOF_CUDA_CHECK(cudaGetLastError());
 	return GOF_OK;
 }
