@@ -176,6 +176,8 @@ class OursArm:
         self.empty = torch.Tensor([])
         self.batch = None
         self.out = None
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.gathered = None
 
     def _prepare(self, flat):
         c = flat[0]
@@ -226,6 +228,10 @@ class OursArm:
         out_dev[:, 0:3].copy_(o["render"])
         out_dev[:, 3:4].copy_(o["rendered_depth"])
         out_dev[:, 4:5].copy_(o["rendered_alpha"])
+        if self.world > 1:
+            # the path's one exchange step: every rank receives all scenes' frames
+            from f3d_gaus_b200 import sharding
+            self.gathered = sharding.gather_frames(out_dev.unsqueeze(0), self.world)
         out_host.copy_(out_dev, non_blocking=True)
 
     def e2e_finish(self):
@@ -488,7 +494,9 @@ def main():
                            "buffers" if args.impl == "ours" else "one Rasterizer::forward call per frame")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / K},
+                "ms_per_step": e2e_ms / K,
+                "exchange": (f"all_gather_into_tensor of [1,{VIEWS},5,{RES},{RES}] f32 per rank (NCCL)"
+                             if (world > 1 and args.impl == "ours") else None)},
         "gpu_launches": launches,
     }
     if args.impl == "ours":

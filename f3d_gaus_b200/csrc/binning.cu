@@ -17,9 +17,9 @@
 //      A bucket is ~700 entries at F3D-Gaus sizes: one CTA sorts it in shared memory with a
 //      bitonic network (buckets above the shared-memory capacity are sorted in place in global
 //      memory by the same network).  The same CTA then writes point_list and the tile-ordered
-//      96-byte slab records, including the tile-local conic pre-test coefficients (conic.cuh).
+//      80-byte slab records, including the tile-local conic pre-test coefficients (conic.cuh).
 // HBM/L2 traffic per duplicate: 8 B written + 8 B read for the bucket entry, 64 B gathered,
-// 100 B written -- versus ~13 passes over 12-byte pairs for the 6-pass LSD sort it replaces, and
+// 84 B written -- versus ~13 passes over 12-byte pairs for the 6-pass LSD sort it replaces, and
 // three launches instead of twelve.
 #include "gof_common.cuh"
 #include "conic.cuh"
@@ -239,11 +239,10 @@ tile_sort_gather_kernel(int P, int T, dim3 grid, int W, int H, float focal_x, fl
 		conic_coefficients(q0, q1, q2, tr, c);
 		float4* dst = reinterpret_cast<float4*>(slab + (size_t)(range.x + i) * SLAB_FLOATS);
 		dst[0] = make_float4(c[0], c[1], c[2], c[3]);
-		dst[1] = make_float4(c[4], c[5], q2.z, q2.w);          // tau, w
-		dst[2] = q0;                                           // Sxx Sxy Sxz Syy
-		dst[3] = q1;                                           // Syz Szz Bx By
-		dst[4] = make_float4(q2.x, q2.y, q3.x, q3.y);          // Bz C r g
-		dst[5] = make_float4(q3.z, q3.w, 0.0f, 0.0f);          // b id
+		dst[1] = make_float4(c[4], c[5], q2.w, q0.x);          // c4 c5 w Sxx
+		dst[2] = make_float4(q0.y, q0.z, q0.w, q1.x);          // Sxy Sxz Syy Syz
+		dst[3] = make_float4(q1.y, q1.z, q1.w, q2.x);          // Szz Bx By Bz
+		dst[4] = make_float4(q2.y, q3.x, q3.y, q3.z);          // C r g b
 	}
 }
 

@@ -112,15 +112,16 @@ struct PairGeom {
 	float AA, BB;       // float32 quadratic coefficients
 };
 
-__device__ __forceinline__ PairGeom pair_geom(const float4& a, const float4& b, const float4& c, float rx, float ry)
+// k1 = (c4, c5, w, Sxx)  k2 = (Sxy, Sxz, Syy, Syz)  k3 = (Szz, Bx, By, Bz)   (slab record, gof_common.cuh)
+__device__ __forceinline__ PairGeom pair_geom(const float4& k1, const float4& k2, const float4& k3, float rx, float ry)
 {
-	// a = (Sxx, Sxy, Sxz, Syy)  b = (Syz, Szz, Bx, By)  c = (Bz, C, tau, w)
+	const float Sxx = k1.w, Sxy = k2.x, Sxz = k2.y, Syy = k2.z, Syz = k2.w, Szz = k3.x, Bx = k3.y, By = k3.z, Bz = k3.w;
 	PairGeom g;
-	g.n0 = __fadd_rn(a.z, __fmaf_rn(a.x, rx, __fmul_rn(a.y, ry)));
-	g.n1 = __fadd_rn(b.x, __fmaf_rn(a.y, rx, __fmul_rn(a.w, ry)));
-	g.n2 = __fadd_rn(b.y, __fmaf_rn(b.x, ry, __fmul_rn(a.z, rx)));
+	g.n0 = __fadd_rn(Sxz, __fmaf_rn(Sxx, rx, __fmul_rn(Sxy, ry)));
+	g.n1 = __fadd_rn(Syz, __fmaf_rn(Sxy, rx, __fmul_rn(Syy, ry)));
+	g.n2 = __fadd_rn(Szz, __fmaf_rn(Syz, ry, __fmul_rn(Sxz, rx)));
 	g.AA = __fadd_rn(__fmaf_rn(g.n0, rx, __fmul_rn(g.n1, ry)), g.n2);
-	const float bb = __fadd_rn(c.x, __fmaf_rn(b.z, rx, __fmul_rn(b.w, ry)));
+	const float bb = __fadd_rn(Bz, __fmaf_rn(Bx, rx, __fmul_rn(By, ry)));
 	g.BB = __fadd_rn(bb, bb);
 	return g;
 }

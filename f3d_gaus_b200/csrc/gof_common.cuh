@@ -25,16 +25,18 @@ constexpr int CH_DEPTH = 6, CH_ALPHA = 7, CH_DIST = 8;
 constexpr int REC_FLOATS = 16;
 constexpr int REC_TAU = 10, REC_W = 11, REC_RGB = 12, REC_ID = 15;
 
-// Per-duplicate "slab record", 96 B, written in tile order by the tile sort so that a tile's
-// sorted Gaussians are one contiguous run that TMA bulk copies can stream:
-//  float4 #0  c0 c1 c2 c3     tile-local conic pre-test  g(x,y) = c0 + x(c1 + c3 x + c4 y) + y(c2 + c5 y)
-//  float4 #1  c4 c5 tau w
-//  float4 #2  Sxx Sxy Sxz Syy
-//  float4 #3  Syz Szz Bx  By
-//  float4 #4  Bz  C   r   g
-//  float4 #5  b   id  -   -
-constexpr int SLAB_FLOATS = 24;
-constexpr int SLAB_BYTES = 96;
+// Per-duplicate "slab record", 80 B (five float4), written in tile order by the tile sort so that a
+// tile's sorted Gaussians are one contiguous run that TMA bulk copies can stream.  80 B = 5 x 16 B
+// also makes the lane-private record reads of the blend's pass 2 spread over all eight 16-byte
+// bank groups of shared memory (5 j mod 8 is a permutation).
+//  float4 #0  c0  c1  c2  c3    tile-local conic pre-test  g(x,y) = c0 + x(c1 + c3 x + c4 y) + y(c2 + c5 y)
+//  float4 #1  c4  c5  w   Sxx
+//  float4 #2  Sxy Sxz Syy Syz
+//  float4 #3  Szz Bx  By  Bz
+//  float4 #4  C   r   g   b
+// (the Gaussian index of a slab entry is point_list[entry]; only the backward needs it)
+constexpr int SLAB_FLOATS = 20;
+constexpr int SLAB_BYTES = 80;
 
 constexpr size_t ALIGN = 256;
 __host__ __device__ inline size_t align_up(size_t x, size_t a = ALIGN) { return (x + a - 1) / a * a; }

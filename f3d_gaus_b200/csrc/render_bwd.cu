@@ -28,11 +28,14 @@ namespace gof {
 
 namespace {
 
+#ifndef GOF_BWD_MIN_CTAS
+#define GOF_BWD_MIN_CTAS 2
+#endif
 constexpr int CHUNK = 128;
 constexpr int STAGES = 3;
 constexpr int CONSUMER_WARPS = TILE_PIX / 32;
 constexpr int BWD_THREADS = TILE_PIX + 32;
-constexpr int STAGE_REC_BYTES = CHUNK * SLAB_BYTES;      // 12 KB
+constexpr int STAGE_REC_BYTES = CHUNK * SLAB_BYTES;      // 10 KB
 constexpr size_t BWD_SMEM = (size_t)STAGES * STAGE_REC_BYTES + 2 * STAGES * sizeof(uint64_t) + 64;
 
 __device__ __forceinline__ void red_global_v4(float* addr, float4 v)
@@ -40,8 +43,9 @@ __device__ __forceinline__ void red_global_v4(float* addr, float4 v)
 	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-__global__ void __launch_bounds__(BWD_THREADS)
-render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ slab, int P, int W, int H,
+__global__ void __launch_bounds__(BWD_THREADS, GOF_BWD_MIN_CTAS)
+render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ slab, const uint32_t* __restrict__ point_list,
+                  int P, int W, int H,
                   float focal_x, float focal_y, const float* __restrict__ bg_colors, int bg_stride,
                   const float2* __restrict__ means2D_all, const float4* __restrict__ conic_opacity_all,
                   const float* __restrict__ final_Ts_all, const uint32_t* __restrict__ n_contrib_all,
@@ -76,6 +80,7 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 	const uint2 range = ranges[((size_t)view * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x];
 	const int n = (int)(range.y - range.x);
 	const float* tile_slab = slab + (size_t)range.x * SLAB_FLOATS;
+	const uint32_t* tile_ids = point_list + range.x;
 
 	const uint32_t last_contributor = inside ? n_contrib[pix_id] : 0;
 	const uint32_t max_contributor = inside ? n_contrib[pix_id + N] : 0;
@@ -176,14 +181,13 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 				m3 &= ~(1u << bit);
 				const uint32_t j = jbase + bit;
 				const uint32_t r = rec + j * SLAB_BYTES;
-				const float4 a = lds128(r + 32), b = lds128(r + 48), cc = lds128(r + 64);
-				const PairGeom g = pair_geom(a, b, cc, rx, ry);
-				const float w = lds32(r + 28);
+				const float4 k1 = lds128(r + 16), k2 = lds128(r + 32), k3 = lds128(r + 48), k4 = lds128(r + 64);
+				const PairGeom g = pair_geom(k1, k2, k3, rx, ry);
+				const float w = k1.z;
 				float t, alpha, G;
-				if (pair_alpha_exact(g, cc.y, w, t, alpha, G)) {
-					const float2 k5 = lds64(r + 80);       // b, id
-					const int gid = __float_as_int(k5.y);
+				if (pair_alpha_exact(g, k4.x, w, t, alpha, G)) {
 					const uint32_t contributor = base + j;   // 0-based position in the tile list
+					const int gid = (int)__ldg(&tile_ids[contributor]);
 					const double td = t;
 					const float mapped = (float)(fma(td, 100.0, -(100.0 * 0.2)) / ((100.0 - 0.2) * td));
 					const float dmax_t_dd = (float)((100.0 * 0.2) / ((100.0 - 0.2) * td * td));
@@ -196,7 +200,7 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 					T = T / (1.f - alpha);
 					const float weight = alpha * T;
 					float dL_dalpha = 0.0f;
-					const float col[3] = { cc.z, cc.w, k5.x };
+					const float col[3] = { k4.y, k4.z, k4.w };
 #pragma unroll
 					for (int ch = 0; ch < 3; ch++) {
 						accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
@@ -269,7 +273,7 @@ int launch_render_bwd(const GofParams& prm, const Frame& f, const GeomState& g, 
 {
 	const dim3 grid(f.grid.x, f.grid.y, f.V);
 	GOF_CUDA_CHECK(cudaFuncSetAttribute(render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
-	render_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, s>>>(im.ranges, b.slab, f.P, prm.W, prm.H, f.focal_x, f.focal_y, background, 0,
+	render_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, s>>>(im.ranges, b.slab, b.point_list, f.P, prm.W, prm.H, f.focal_x, f.focal_y, background, 0,
 	                                                     g.means2D, g.conic_opacity, im.final_T, im.n_contrib, dL_dpix, gacc);
 	GOF_CUDA_CHECK(cudaGetLastError());
 	return GOF_OK;

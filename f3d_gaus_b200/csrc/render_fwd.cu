@@ -7,7 +7,7 @@
 // B200 design:
 //   * One CTA per 16x16 tile (the tile size is part of the binning contract): 8 consumer warps,
 //     each owning an 8x4 pixel block, plus one producer warp.
-//   * The tile's sorted Gaussians arrive as a contiguous slab of 96-byte records (binning.cu).
+//   * The tile's sorted Gaussians arrive as a contiguous slab of 80-byte records (binning.cu).
 //     The producer streams it into a 4-stage shared-memory ring with TMA bulk copies
 //     (cp.async.bulk, completion on a "full" mbarrier per stage); each consumer warp releases a
 //     stage by arriving on its "empty" mbarrier.  There is no CTA-wide barrier in the loop: warps
@@ -32,8 +32,14 @@ namespace gof {
 
 namespace {
 
-constexpr int CHUNK = 128;                 // records per pipeline stage (12 KB)
-constexpr int STAGES = 4;
+#ifndef GOF_FWD_STAGES
+#define GOF_FWD_STAGES 4
+#endif
+#ifndef GOF_FWD_MIN_CTAS
+#define GOF_FWD_MIN_CTAS 3
+#endif
+constexpr int CHUNK = 128;                 // records per pipeline stage (10 KB)
+constexpr int STAGES = GOF_FWD_STAGES;
 
 struct PixState {
 	float T;
@@ -100,7 +106,7 @@ constexpr int FWD_THREADS = TILE_PIX + 32;             // + 1 producer warp
 constexpr int REC_F4 = SLAB_FLOATS / 4;                // float4 per slab record (6)
 
 template <bool EXACT>
-__global__ void __launch_bounds__(FWD_THREADS)
+__global__ void __launch_bounds__(FWD_THREADS, GOF_FWD_MIN_CTAS)
 render_fwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ slab, int W, int H,
                   float focal_x, float focal_y, const float* __restrict__ bg_colors, int bg_stride,
                   float* __restrict__ final_T_all, uint32_t* __restrict__ n_contrib_all, float* __restrict__ out_color_all,
@@ -201,11 +207,11 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 					const uint32_t j = jbase + (uint32_t)__ffs((int)m0) - 1u;
 					m0 &= m0 - 1u;
 					const uint32_t r = rec + j * SLAB_BYTES;
-					const float4 a = lds128(r + 32), b = lds128(r + 48), cc = lds128(r + 64);
-					const PairGeom g = pair_geom(a, b, cc, rx, ry);
+					const float4 k1 = lds128(r + 16), k2 = lds128(r + 32), k3 = lds128(r + 48), k4 = lds128(r + 64);
+					const PairGeom g = pair_geom(k1, k2, k3, rx, ry);
 					float t, alpha, G;
-					if (pair_alpha_exact(g, cc.y, lds32(r + 28), t, alpha, G)) {
-						const float4 d = make_float4(cc.z, cc.w, lds32(r + 80), 0.0f);
+					if (pair_alpha_exact(g, k4.x, k1.z, t, alpha, G)) {
+						const float4 d = make_float4(k4.y, k4.z, k4.w, 0.0f);
 						if (blend_pair<EXACT>(st, g, t, alpha, d, base + j + 1)) { done = true; m0 = 0; m1 = 0; m2 = 0; m3 = 0; }
 					}
 				}
