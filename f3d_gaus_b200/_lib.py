@@ -65,6 +65,9 @@ SIGNATURES = {
                                     POINTER(c_int32), POINTER(c_void_p), c_void_p]),
     "gof_state_get_batch": (c_int64, [c_char_p, c_int32, c_int32, c_int32, c_int32, c_int64, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_int64, c_void_p]),
+    "gof_integrate": (c_int32, [c_void_p, POINTER(GofParams), POINTER(GofInputs), c_int32, c_void_p, c_void_p, c_size_t,
+                                c_void_p, c_size_t, ALLOC_FN, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                POINTER(c_int32), c_void_p]),
     "gof_num_rendered": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, POINTER(c_int32)]),
     "gof_backward": (c_int32, [c_void_p, POINTER(GofParams), POINTER(GofInputs), c_int32, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, POINTER(GofGrads), c_void_p]),

@@ -262,6 +262,57 @@ int gof_forward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
 	                         out_color, radii, num_rendered, binning_out, stream);
 }
 
+int gof_integrate(GofContext* ctx, const GofParams* prm, const GofInputs* in, int32_t PN, const float* points3D,
+                  void* geom, size_t geom_bytes, void* img, size_t img_bytes, GofAllocFn alloc, void* alloc_user,
+                  float* out_color, int32_t* radii, float* out_alpha_integrated, float* out_color_integrated,
+                  int32_t* num_rendered, gof_stream_t stream)
+{
+	if (!ctx || !prm || !in || !alloc) { set_error("gof_integrate: NULL argument"); return GOF_EINVAL; }
+	cudaStream_t s = (cudaStream_t)stream;
+	const int P = prm->P, W = prm->W, H = prm->H;
+	if (W <= 0 || H <= 0 || P <= 0 || PN < 0) { set_error("gof_integrate: bad sizes P=%d PN=%d W=%d H=%d", P, PN, W, H); return GOF_EINVAL; }
+	if (!out_color || !radii || (PN > 0 && (!points3D || !out_alpha_integrated || !out_color_integrated))) {
+		set_error("gof_integrate: NULL output / points pointer");
+		return GOF_EINVAL;
+	}
+	if (!in->means3D || !in->opacities || !in->viewmatrix || !in->projmatrix || !in->campos || !in->background) {
+		set_error("gof_integrate: a required input pointer is NULL");
+		return GOF_EINVAL;
+	}
+	if ((in->shs == nullptr) == (in->colors_precomp == nullptr)) { set_error("gof_integrate: provide exactly one of shs / colors_precomp"); return GOF_EINVAL; }
+	if (((in->scales == nullptr) || (in->rotations == nullptr)) == (in->cov3D_precomp == nullptr)) {
+		set_error("gof_integrate: provide exactly one of (scales, rotations) / cov3D_precomp");
+		return GOF_EINVAL;
+	}
+	if (in->cov3D_precomp && !in->view2gaussian_precomp) { set_error("gof_integrate: cov3D_precomp needs view2gaussian_precomp"); return GOF_EINVAL; }
+	const Frame f = make_frame(prm, 1);
+	const size_t N = (size_t)W * H;
+	GeomState g = GeomState::carve(align_base(geom), (size_t)P, 1);
+	ImgState im = ImgState::carve(align_base(img), N, (size_t)f.T, 1);
+	if (!geom || g.total > geom_bytes) { set_error("gof_integrate: geom blob too small"); return GOF_ENOMEM; }
+	if (!img || im.total > img_bytes) { set_error("gof_integrate: img blob too small"); return GOF_ENOMEM; }
+	int rc;
+	if ((rc = launch_preprocess(*prm, *in, f, g, im, radii, s)) != GOF_OK) return rc;
+	GOF_STAGE_CHECK(prm, s);
+	if ((rc = launch_tile_scan(f, g, im, (int64_t)1 << 40, s)) != GOF_OK) return rc;
+	GOF_CUDA_CHECK(cudaMemcpyAsync(ctx->pinned, g.mailbox, (MAILBOX_HEAD + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+	GOF_CUDA_CHECK(cudaStreamSynchronize(s));
+	const int64_t R = ctx->pinned[0];
+	const size_t max_count = (size_t)ctx->pinned[2];
+	if (num_rendered) *num_rendered = (int32_t)R;
+	const size_t bin_bytes = BinState::carve(nullptr, (size_t)R).total;
+	const size_t scr_bytes = IntegrateScratch::carve(nullptr, (size_t)PN, (size_t)f.T, max_count).total;
+	char* blob = (char*)alloc(alloc_user, bin_bytes + scr_bytes + 2 * ALIGN);
+	if (!blob) { set_error("gof_integrate: allocation callback returned NULL for %zu bytes", bin_bytes + scr_bytes); return GOF_ENOMEM; }
+	BinState b = BinState::carve(align_base(blob), (size_t)R);
+	IntegrateScratch sc = IntegrateScratch::carve(align_base(align_base(blob) + bin_bytes), (size_t)PN, (size_t)f.T, max_count);
+	if ((rc = launch_binning(f, g, im, b, R, s, 0.5f)) != GOF_OK) return rc;
+	GOF_STAGE_CHECK(prm, s);
+	if ((rc = launch_integrate(*prm, *in, f, g, im, b, sc, PN, points3D, out_color, out_alpha_integrated, out_color_integrated, s)) != GOF_OK) return rc;
+	GOF_STAGE_CHECK(prm, s);
+	return GOF_OK;
+}
+
 int gof_num_rendered(GofContext* ctx, const void* geom, int32_t P, int32_t V, gof_stream_t stream, int32_t* num_rendered)
 {
 	if (!ctx || !geom || !num_rendered || P <= 0 || V <= 0 || V > GOF_MAX_VIEWS) { set_error("gof_num_rendered: bad argument"); return GOF_EINVAL; }

@@ -199,7 +199,7 @@ __device__ __forceinline__ void bitonic_sort(uint64_t* a, int n, int npad)
 
 // One CTA per tile of the batch: sort the bucket, write point_list and the slab.
 __global__ void __launch_bounds__(SORT_THREADS, 3)
-tile_sort_gather_kernel(int P, int T, dim3 grid, int W, int H, float focal_x, float focal_y,
+tile_sort_gather_kernel(int P, int T, dim3 grid, int W, int H, float focal_x, float focal_y, float ray_pad,
                         const uint2* __restrict__ ranges, uint64_t* __restrict__ entries,
                         const float* __restrict__ rec_all, uint32_t* __restrict__ point_list,
                         float* __restrict__ slab, const int32_t* __restrict__ mailbox)
@@ -226,7 +226,7 @@ tile_sort_gather_kernel(int P, int T, dim3 grid, int W, int H, float focal_x, fl
 	__syncthreads();
 	if (n > 1) bitonic_sort(a, n, npad);
 
-	const TileRays tr = tile_rays(tx, ty, W, H, focal_x, focal_y);
+	const TileRays tr = tile_rays(tx, ty, W, H, focal_x, focal_y, (double)ray_pad);
 	const float* rec = rec_all + (size_t)view * P * REC_FLOATS;
 	for (int i = threadIdx.x; i < n; i += SORT_THREADS) {
 		const uint64_t e = a[i];
@@ -299,15 +299,22 @@ int launch_tile_scan(const Frame& f, const GeomState& g, const ImgState& im, int
 	return GOF_OK;
 }
 
+int launch_tile_scan_raw(int T, const uint32_t* counts, uint2* ranges, uint32_t* cursor, int32_t* mailbox, cudaStream_t s)
+{
+	tile_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(T, T, 1, counts, ranges, cursor, mailbox, (long long)1 << 40);
+	GOF_CUDA_CHECK(cudaGetLastError());
+	return GOF_OK;
+}
+
 int launch_binning(const Frame& f, const GeomState& g, const ImgState& im, const BinState& b, int64_t capacity,
-                   cudaStream_t s)
+                   cudaStream_t s, float ray_pad)
 {
 	if (capacity <= 0) return GOF_OK;
 	dim3 blocks((f.P + 255) / 256, f.V);
 	scatter_kernel<<<blocks, 256, 0, s>>>(f.P, f.T, f.grid, g.tiles_touched, g.rect, g.depths, im.tile_cursor, b.entries,
 	                                      g.mailbox);
 	GOF_CUDA_CHECK(cudaGetLastError());
-	tile_sort_gather_kernel<<<f.V * f.T, SORT_THREADS, 0, s>>>(f.P, f.T, f.grid, f.W, f.H, f.focal_x, f.focal_y, im.ranges,
+	tile_sort_gather_kernel<<<f.V * f.T, SORT_THREADS, 0, s>>>(f.P, f.T, f.grid, f.W, f.H, f.focal_x, f.focal_y, ray_pad, im.ranges,
 	                                                           b.entries, g.rec, b.point_list, b.slab, g.mailbox);
 	GOF_CUDA_CHECK(cudaGetLastError());
 	return GOF_OK;

@@ -35,22 +35,30 @@ struct TileRays {
 	double ax, bx, ay, by;     // rx = ax * x + bx, ry = ay * y + by for tile-local pixel x, y in [0, 15]
 	double rcx, rcy, hx, hy;   // centre and half-widths of the tile's ray box
 	double rhox, rhoy;         // max |rx|, max |ry| over the tile
+	double m;                  // max |x|, |y| the polynomial is evaluated at (15, or 15.5 with sub-pixel rays)
+	double rel_extra;          // extra relative error of q in the consumer's arithmetic (0 for the blend)
 };
 
-__device__ __forceinline__ TileRays tile_rays(int tx, int ty, int W, int H, float focal_x, float focal_y)
+// pad = 0: rays through pixel centres only (the blend).  pad = 0.5: any ray through the tile's pixels
+// (point integration: corner rays and query points at sub-pixel positions; x, y in [-0.5, 15.5]); that
+// consumer also forms BB/AA with a float32 division, one more rounding of q (rel_extra).
+__device__ __forceinline__ TileRays tile_rays(int tx, int ty, int W, int H, float focal_x, float focal_y, double pad = 0.0)
 {
 	TileRays t;
 	t.ax = 1.0 / (double)focal_x;
 	t.ay = 1.0 / (double)focal_y;
 	t.bx = ((double)(tx * TILE_X) + 0.5 - W / 2.) / (double)focal_x;
 	t.by = ((double)(ty * TILE_Y) + 0.5 - H / 2.) / (double)focal_y;
-	const double rxh = t.bx + (TILE_X - 1) * t.ax, ryh = t.by + (TILE_Y - 1) * t.ay;
-	t.rcx = 0.5 * (t.bx + rxh);
-	t.rcy = 0.5 * (t.by + ryh);
-	t.hx = 0.5 * (rxh - t.bx);
-	t.hy = 0.5 * (ryh - t.by);
-	t.rhox = fmax(fabs(t.bx), fabs(rxh));
-	t.rhoy = fmax(fabs(t.by), fabs(ryh));
+	const double rxl = t.bx - pad * t.ax, ryl = t.by - pad * t.ay;
+	const double rxh = t.bx + (TILE_X - 1 + pad) * t.ax, ryh = t.by + (TILE_Y - 1 + pad) * t.ay;
+	t.rcx = 0.5 * (rxl + rxh);
+	t.rcy = 0.5 * (ryl + ryh);
+	t.hx = 0.5 * (rxh - rxl);
+	t.hy = 0.5 * (ryh - ryl);
+	t.rhox = fmax(fabs(rxl), fabs(rxh));
+	t.rhoy = fmax(fabs(ryl), fabs(ryh));
+	t.m = 15.0 + pad;
+	t.rel_extra = pad > 0.0 ? 24.0 * 5.9604644775390625e-08 : 0.0;   // float32 BB/AA division; float32 AA t^2 + BB t + C (4 q-sized terms)
 	return t;
 }
 
@@ -85,7 +93,7 @@ __device__ __forceinline__ void conic_coefficients(const float4& q0, const float
 	const double E_bb = (bmax * dBB + 0.25 * dBB * dBB) / AAl;
 	const double Qp = (bmax + 0.5 * dBB) * (bmax + 0.5 * dBB) / AAl;
 	const double E_aa = Qp * dAA / (AAl - (ok ? dAA : 0.0));
-	const double E = 1.25 * (E_bb + E_aa);
+	const double E = 1.25 * (E_bb + E_aa) + t.rel_extra * Qp;
 	const double K = C - (tau + E);
 
 	// polynomial expansion in tile-local pixel coordinates
@@ -101,7 +109,7 @@ __device__ __forceinline__ void conic_coefficients(const float4& q0, const float
 	const double c3 = (p * p - K * a_xx) * inv;
 	const double c4 = (2.0 * p * q - K * a_xy) * inv;
 	const double c5 = (q * q - K * a_yy) * inv;
-	const double m = 15.0;
+	const double m = t.m;
 	// float32 evaluation error of g (+ the double rounding of the expansion itself, which works on
 	// terms of magnitude (r0^2 + |K| a_0)/AAc and their x, y analogues)
 	const double eta = 8.0 * u * (fabs(c0) + m * (fabs(c1) + fabs(c2)) + m * m * (fabs(c3) + fabs(c4) + fabs(c5)))

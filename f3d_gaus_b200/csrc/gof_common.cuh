@@ -97,8 +97,28 @@ struct Frame {
 int launch_preprocess(const GofParams& prm, const GofInputs& in, const Frame& f, const GeomState& g,
                       const ImgState& im, int32_t* radii, cudaStream_t s);
 int launch_tile_scan(const Frame& f, const GeomState& g, const ImgState& im, int64_t capacity, cudaStream_t s);
+// ray_pad: 0 for the blend (rays through pixel centres), 0.5 for point integration (conic.cuh)
 int launch_binning(const Frame& f, const GeomState& g, const ImgState& im, const BinState& b, int64_t capacity,
-                   cudaStream_t s);
+                   cudaStream_t s, float ray_pad = 0.0f);
+// point integration (integrate.cu)
+struct IntegrateScratch {
+	uint32_t* used_mask;      // [T][words][256]  per-pixel contributed bits over the tile's list
+	int words;                // 32-bit words per pixel = 4 * ceil(max tile count / 128)
+	float2* points2D;         // [PN]
+	float* point_depths;      // [PN]
+	uint32_t* point_tile;     // [PN]  tile of the point, 0xffffffff if culled
+	uint32_t* point_counts;   // [T]
+	uint32_t* point_cursor;   // [T]
+	uint2* point_ranges;      // [T]
+	uint32_t* point_list;     // [PN]  bucketed by tile
+	int32_t* point_mailbox;   // [MAILBOX_HEAD + 1]
+	size_t total;
+	static IntegrateScratch carve(char* base, size_t PN, size_t T, size_t max_count);
+};
+int launch_integrate(const GofParams& prm, const GofInputs& in, const Frame& f, const GeomState& g, const ImgState& im,
+                     const BinState& b, const IntegrateScratch& sc, int PN, const float* points3D, float* out_color,
+                     float* out_alpha_integrated, float* out_color_integrated, cudaStream_t s);
+int launch_tile_scan_raw(int T, const uint32_t* counts, uint2* ranges, uint32_t* cursor, int32_t* mailbox, cudaStream_t s);
 int launch_render_fwd(const GofParams& prm, const Frame& f, const GeomState& g, const ImgState& im, const BinState& b,
                       const float* background, int bg_stride, float* out_color, cudaStream_t s);
 int launch_render_bwd(const GofParams& prm, const Frame& f, const GeomState& g, const ImgState& im,

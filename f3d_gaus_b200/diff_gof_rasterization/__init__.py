@@ -162,11 +162,60 @@ class _CModule:
             _lib.check(rc, "mark_visible")
         return present
 
+    # -- integrate ----------------------------------------------------------------------------
     @staticmethod
-    def integrate_gaussians_to_points(*args, **kwargs):
-        raise NotImplementedError(
-            "integrate_gaussians_to_points (GOF mesh extraction, forward.cu:803-1218) is outside the hot path "
-            "built so far; see DESIGN.md, 'next'")
+    def integrate_gaussians_to_points(background, points3D, means3D, colors, opacity, scales, rotations, scale_modifier,
+                                      cov3D_precomp, view2gaussian_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
+                                      kernel_size, subpixel_offset, image_height, image_width, sh, degree, campos,
+                                      prefiltered, debug):
+        """IntegrateGaussiansToPointsCUDA (rasterize_points.cu:234-343): returns (num_rendered, out_color[9,H,W],
+        out_alpha_integrated[PN], out_color_integrated[PN,3], radii[P], geomBuffer, binningBuffer, imgBuffer)."""
+        if means3D.dim() != 2 or means3D.size(1) != 3:
+            raise RuntimeError("means3D must have dimensions (num_points, 3)")
+        if points3D.dim() != 2 or points3D.size(1) != 3:
+            raise RuntimeError("points3D must have dimensions (num_points, 3)")
+        if not means3D.is_cuda:
+            raise RuntimeError("diff_gof_rasterization (B200): tensors must be on a CUDA device; there is no CPU path")
+        device = means3D.device
+        P, PN, H, W = int(means3D.size(0)), int(points3D.size(0)), int(image_height), int(image_width)
+        M = int(sh.size(1)) if (sh is not None and sh.numel() != 0 and sh.size(0) != 0) else 0
+        f32 = dict(dtype=torch.float32, device=device)
+        byte_opts = dict(dtype=torch.uint8, device=device)
+        out_color = torch.zeros((_lib.OUTPUT_CHANNELS, H, W), **f32)
+        radii = torch.zeros((P,), dtype=torch.int32, device=device)
+        out_alpha = torch.ones((PN,), **f32)
+        out_rgb = torch.zeros((PN, 3), **f32)
+        empty = torch.empty(0, **byte_opts)
+        if P == 0 or PN == 0:      # rasterize_points.cu:291: nothing is launched
+            return NumRendered(0), out_color, out_alpha, out_rgb, radii, empty, empty.clone(), empty.clone()
+        keep: list = []
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            gsz, isz, bsz = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+            _lib.check(_lib.lib.gof_state_sizes(P, W, H, 0, ctypes.byref(gsz), ctypes.byref(isz), ctypes.byref(bsz)),
+                       "gof_state_sizes")
+            geom, img = torch.empty(gsz.value, **byte_opts), torch.empty(isz.value, **byte_opts)
+            holder = {}
+
+            def _alloc(_user, nbytes):
+                holder["binning"] = torch.empty(int(nbytes), **byte_opts)
+                return holder["binning"].data_ptr()
+
+            prm = _lib.GofParams(P, int(degree), M, W, H, float(tan_fovx), float(tan_fovy), float(kernel_size),
+                                 float(scale_modifier), int(bool(prefiltered)), int(bool(debug)), _lib.default_flags())
+            inp = _lib.GofInputs(
+                _dev_ptr(background, device, keep), _dev_ptr(means3D, device, keep), _dev_ptr(sh, device, keep),
+                _dev_ptr(colors, device, keep), _dev_ptr(opacity, device, keep), _dev_ptr(scales, device, keep),
+                _dev_ptr(rotations, device, keep), _dev_ptr(cov3D_precomp, device, keep),
+                _dev_ptr(view2gaussian_precomp, device, keep), _dev_ptr(viewmatrix, device, keep),
+                _dev_ptr(projmatrix, device, keep), _dev_ptr(campos, device, keep))
+            R = ctypes.c_int32(0)
+            rc = _lib.lib.gof_integrate(_lib.context(device.index), ctypes.byref(prm), ctypes.byref(inp), PN,
+                                        _dev_ptr(points3D, device, keep), geom.data_ptr(), geom.numel(), img.data_ptr(),
+                                        img.numel(), _lib.ALLOC_FN(_alloc), None, out_color.data_ptr(), radii.data_ptr(),
+                                        out_alpha.data_ptr(), out_rgb.data_ptr(), ctypes.byref(R), stream)
+            _lib.check(rc, "integrate_gaussians_to_points")
+        return (NumRendered(R.value), out_color, out_alpha, out_rgb, radii, geom, holder.get("binning", empty), img)
 
 
 _C = _CModule()
@@ -471,8 +520,26 @@ class GaussianRasterizer_GOF(nn.Module):
 
     def integrate(self, points3D, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None,
                   rotations=None, cov3D_precomp=None, view2gaussian_precomp=None):
+        """GaussianRasterizer_GOF.integrate (reference :241-307): (color, alpha_integrated, color_integrated, radii)."""
         self._validate(shs, colors_precomp, scales, rotations, cov3D_precomp)
-        return _C.integrate_gaussians_to_points()
+        rs = self.raster_settings
+        fill = lambda t: _absent() if t is None else t
+        args = (rs.bg, points3D, means3D, fill(colors_precomp), opacities, fill(scales), fill(rotations),
+                rs.scale_modifier, fill(cov3D_precomp), fill(view2gaussian_precomp), rs.viewmatrix, rs.projmatrix,
+                rs.tanfovx, rs.tanfovy, rs.kernel_size, rs.subpixel_offset, rs.image_height, rs.image_width, fill(shs),
+                rs.sh_degree, rs.campos, rs.prefiltered, rs.debug)
+        if rs.debug:
+            snapshot = _cpu_copy(args)
+            try:
+                out = _C.integrate_gaussians_to_points(*args)
+            except Exception:
+                torch.save(snapshot, "snapshot_fw.dump")
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                raise
+        else:
+            out = _C.integrate_gaussians_to_points(*args)
+        _num_rendered, color, alpha_integrated, color_integrated, radii, _g, _b, _i = out
+        return color, alpha_integrated, color_integrated, radii
 
 
 # Un-suffixed names (commented out in the reference at :167,:184; used by vanilla render()).

@@ -2,6 +2,7 @@
 
   render_predicted_more_v2_gof   (:915-1067)  dict-of-tensors -> rasterizer -> output dict
   depths_to_points / depth_to_normal (:881-909)
+  render_predicted_more_v2_gof_in (:1070-1228) point integration for mesh extraction (rasterizer.integrate)
   render_views                    all V views of a scene in one batched pass (what the reference's render loops do frame by frame)
   render                          the vanilla signature (src/gaussian-splatting/gaussian_renderer/__init__.py:18-100)
 
@@ -145,6 +146,39 @@ def render_predicted_more_v2_gof(pc: dict, bs, world_view_transform, full_proj_t
             "viewspace_points": screenspace_points,
             "visibility_filter": radii > 0,
             "radii": radii}
+
+
+def render_predicted_more_v2_gof_in(points3D, pc: dict, bs, world_view_transform, full_proj_transform, camera_center,
+                                    bg_color: torch.Tensor, cfg, kernel_size=0.0, scaling_modifier=1.0,
+                                    override_color=None, subpixel_offset=None):
+    """Point integration for mesh extraction (reference :1070-1228): the dict of
+    `render_predicted_more_v2_gof` plus `alpha_integrated[PN]` and `color_integrated[PN,3]`."""
+    xyz = pc["xyz"][bs]
+    device = xyz.device
+    screenspace_points = torch.zeros_like(xyz, dtype=pc["xyz"].dtype, requires_grad=True, device=device) + 0
+    fov = cfg['model']['fov']
+    tanfov = math.tan(fov * np.pi / 360)
+    Fov = fov * np.pi / 180
+    H = W = int(cfg['model']['training_resolution'])
+    raster_settings = GaussianRasterizationSettings_GOF(
+        image_height=H, image_width=W, tanfovx=tanfov, tanfovy=tanfov, kernel_size=kernel_size,
+        subpixel_offset=_subpixel_offset(H, W, device), bg=bg_color, scale_modifier=scaling_modifier,
+        viewmatrix=world_view_transform, projmatrix=full_proj_transform, sh_degree=cfg['model']['max_sh_degree'],
+        campos=camera_center, prefiltered=False, debug=False)
+    rasterizer = GaussianRasterizer_GOF(raster_settings=raster_settings)
+    if override_color is None:
+        shs, colors_precomp = torch.cat([pc["features_dc"][bs], pc["features_rest"][bs]], dim=1).contiguous(), None
+    else:
+        shs, colors_precomp = None, pc["rgbs"][bs]
+    rendered_image, alpha_integrated, color_integrated, radii = rasterizer.integrate(
+        points3D=points3D, means3D=xyz, means2D=screenspace_points, shs=shs, colors_precomp=colors_precomp,
+        opacities=pc["opacity"][bs], scales=pc["scaling"][bs], rotations=pc["rotation"][bs], cov3D_precomp=None,
+        view2gaussian_precomp=None)
+    normal_world, depth_normal = fused_epilogue(rendered_image, world_view_transform, W, H, Fov, Fov)
+    return {"render": rendered_image[:3], "rendered_normal": normal_world, "rendered_depth": rendered_image[6:7],
+            "depth_normal": depth_normal, "rendered_alpha": rendered_image[7:8], "distortion_map": rendered_image[8:9],
+            "viewspace_points": screenspace_points, "visibility_filter": radii > 0,
+            "alpha_integrated": alpha_integrated, "color_integrated": color_integrated, "radii": radii}
 
 
 def render_views(pc: dict, bs, world_view_transforms, full_proj_transforms, camera_centers, bg_color: torch.Tensor, cfg,

@@ -7,6 +7,7 @@
  *   gof_forward          <- CudaRasterizer::Rasterizer::forward   RAST/cuda_rasterizer/rasterizer.h:30-59
  *   gof_forward_batch    <- the per-frame render loops around it  visualize.py:293-306,387-402
  *                           (bound by RasterizeGaussiansCUDA,      RAST/rasterize_points.cu:36-122)
+ *   gof_integrate        <- CudaRasterizer::Rasterizer::integrate RAST/cuda_rasterizer/rasterizer.h:93-123
  *   gof_backward         <- CudaRasterizer::Rasterizer::backward  RAST/cuda_rasterizer/rasterizer.h:61-91
  *                           (bound by RasterizeGaussiansBackwardCUDA, RAST/rasterize_points.cu:124-211)
  *   gof_preprocess_backward <- BACKWARD::preprocess             RAST/cuda_rasterizer/backward.cu:957-1033
@@ -163,6 +164,18 @@ int gof_forward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* in
                       void* binning, size_t binning_bytes, GofAllocFn alloc, void* alloc_user,
                       float* out_color, int32_t* radii,
                       int32_t* num_rendered, void** binning_out, gof_stream_t stream);
+
+/* Point integration for GOF mesh extraction (Rasterizer::integrate, rasterizer_impl.cu:530-792, bound by
+ * IntegrateGaussiansToPointsCUDA, rasterize_points.cu:234-343): renders the Gaussians with five rays per
+ * pixel and, for each of the PN query points (points3D [PN,3]) that projects into the image, accumulates
+ * alpha along the ray through the point up to the point's depth.
+ *   out_color [9,H,W]: rgb, 0,0,0, max depth, alpha, number of query points in the pixel;
+ *   out_alpha_integrated [PN] (1 for points outside the view), out_color_integrated [PN,3].
+ * The binning blob and the scratch are obtained through `alloc` (one call, after one stream sync). */
+int gof_integrate(GofContext* ctx, const GofParams* prm, const GofInputs* in, int32_t PN, const float* points3D,
+                  void* geom, size_t geom_bytes, void* img, size_t img_bytes, GofAllocFn alloc, void* alloc_user,
+                  float* out_color, int32_t* radii, float* out_alpha_integrated, float* out_color_integrated,
+                  int32_t* num_rendered, gof_stream_t stream);
 
 /* Sync-free mode: blocks on `stream` and returns the per-view R ([V]) of the last forward that used
  * `geom` (or GOF_EOVERFLOW if the binning blob was too small for it). */

@@ -1,8 +1,8 @@
 // oracle/ref_harness.cu -- TEST INFRASTRUCTURE, not product code.
 //
 // A thin extern "C" driver around the UNMODIFIED reference rasterizer
-// (CudaRasterizer::Rasterizer::{forward,backward,markVisible},
-// RAST/cuda_rasterizer/rasterizer.h:20-91), compiled for sm_100a from the
+// (CudaRasterizer::Rasterizer::{forward,backward,integrate,markVisible},
+// RAST/cuda_rasterizer/rasterizer.h:20-123), compiled for sm_100a from the
 // sources where they lie under /root/reference by oracle/Makefile into
 // oracle/_ref/libgof_ref.so.  It replaces the reference's torch glue
 // (RAST/rasterize_points.cu:36-211) with plain cudaMalloc-backed state blobs so
@@ -47,7 +47,7 @@ thread_local std::string g_err;
 }  // namespace
 
 struct RefState {
-	Blob geom, binning, img;
+	Blob geom, binning, img, point, point_binning;
 	int P = 0, R = 0, W = 0, H = 0;
 };
 
@@ -105,6 +105,35 @@ int ref_backward(RefState* s, int P, int D, int M, int R,
 			dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh,
 			dL_dscale, dL_drot, dL_dview2gaussian, debug != 0);
 		return 0;
+	} catch (const std::exception& e) {
+		g_err = e.what();
+		return -1;
+	}
+}
+
+// Rasterizer::integrate (rasterizer.h:93-123).  Returns num_rendered or -1.
+int ref_integrate(RefState* s, int PN, int P, int D, int M,
+	const float* background, int W, int H, const float* points3D,
+	const float* means3D, const float* shs, const float* colors_precomp,
+	const float* opacities, const float* scales, float scale_modifier,
+	const float* rotations, const float* cov3D_precomp, const float* view2gaussian_precomp,
+	const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+	float tan_fovx, float tan_fovy, float kernel_size, const float* subpixel_offset,
+	int prefiltered, float* out_color, int* radii, float* out_alpha_integrated, float* out_color_integrated, int debug)
+{
+	try {
+		std::function<char*(size_t)> g = [s](size_t n) { return s->geom.resize(n); };
+		std::function<char*(size_t)> b = [s](size_t n) { return s->binning.resize(n); };
+		std::function<char*(size_t)> i = [s](size_t n) { return s->img.resize(n); };
+		std::function<char*(size_t)> pt = [s](size_t n) { return s->point.resize(n); };
+		std::function<char*(size_t)> pb = [s](size_t n) { return s->point_binning.resize(n); };
+		int R = CudaRasterizer::Rasterizer::integrate(g, b, i, pt, pb, PN, P, D, M, background, W, H, points3D,
+			means3D, shs, colors_precomp, opacities, scales, scale_modifier, rotations,
+			cov3D_precomp, view2gaussian_precomp, viewmatrix, projmatrix, cam_pos,
+			tan_fovx, tan_fovy, kernel_size, subpixel_offset, prefiltered != 0,
+			out_color, radii, out_alpha_integrated, out_color_integrated, debug != 0);
+		s->P = P; s->R = R; s->W = W; s->H = H;
+		return R;
 	} catch (const std::exception& e) {
 		g_err = e.what();
 		return -1;

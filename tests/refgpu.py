@@ -55,6 +55,9 @@ def ref_lib():
             [c_float] + [c_void_p] * 5 + [c_float, c_float, c_float, c_void_p, c_void_p, c_void_p] + [c_void_p] * 10 + [c_int]
         lib.ref_state_get.restype = c_longlong
         lib.ref_state_get.argtypes = [c_void_p, c_char_p, c_void_p, c_longlong]
+        lib.ref_integrate.restype = c_int
+        lib.ref_integrate.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int] + [c_void_p] * 6 + \
+            [c_float] + [c_void_p] * 6 + [c_float, c_float, c_float, c_void_p, c_int] + [c_void_p] * 4 + [c_int]
         lib.ref_mark_visible.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p]
         _ref = lib
     return _ref
@@ -132,6 +135,45 @@ class RefRun:
             raise RuntimeError(self.lib.ref_last_error().decode())
         torch.cuda.synchronize()
         return g
+
+
+def ref_integrate(c: dict, points3D: torch.Tensor) -> dict:
+    """The reference's Rasterizer::integrate on case `c` and query points [PN,3]."""
+    lib = ref_lib()
+    st = lib.ref_state_create()
+    dev = c["means3D"].device
+    P, W, H, PN = c["means3D"].shape[0], c["W"], c["H"], points3D.shape[0]
+    M = c["shs"].shape[1] if c.get("shs") is not None else 0
+    out_color = torch.zeros((9, H, W), dtype=torch.float32, device=dev)
+    radii = torch.zeros((P,), dtype=torch.int32, device=dev)
+    alpha = torch.ones((PN,), dtype=torch.float32, device=dev)
+    rgb = torch.zeros((PN, 3), dtype=torch.float32, device=dev)
+    sub = torch.zeros((H, W, 2), dtype=torch.float32, device=dev)
+    pts = points3D.contiguous()
+    torch.cuda.synchronize()
+    R = lib.ref_integrate(st, PN, P, c["D"], M, _p(c["bg"]), W, H, _p(pts), _p(c["means3D"]), _p(c.get("shs")),
+                          _p(c.get("colors_precomp")), _p(c["opacities"]), _p(c.get("scales")), c["scale_modifier"],
+                          _p(c.get("rotations")), _p(c.get("cov3D_precomp")), _p(c.get("view2gaussian_precomp")),
+                          _p(c["viewmatrix"]), _p(c["projmatrix"]), _p(c["campos"]), c["tanfovx"], c["tanfovy"],
+                          c["kernel_size"], sub.data_ptr(), 0, out_color.data_ptr(), radii.data_ptr(), alpha.data_ptr(),
+                          rgb.data_ptr(), 0)
+    torch.cuda.synchronize()
+    if R < 0:
+        raise RuntimeError(lib.ref_last_error().decode())
+    lib.ref_state_destroy(st)
+    return {"num_rendered": R, "out_color": out_color, "radii": radii, "alpha_integrated": alpha, "color_integrated": rgb}
+
+
+def ours_integrate(c: dict, points3D: torch.Tensor) -> dict:
+    from f3d_gaus_b200.diff_gof_rasterization import _C
+    e = torch.Tensor([])
+    g = lambda k: c[k] if c.get(k) is not None else e
+    R, color, alpha, rgb, radii, *_ = _C.integrate_gaussians_to_points(
+        c["bg"], points3D, c["means3D"], g("colors_precomp"), c["opacities"], g("scales"), g("rotations"),
+        c["scale_modifier"], g("cov3D_precomp"), g("view2gaussian_precomp"), c["viewmatrix"], c["projmatrix"],
+        c["tanfovx"], c["tanfovy"], c["kernel_size"], e, c["H"], c["W"], g("shs"), c["D"], c["campos"], False, False)
+    torch.cuda.synchronize()
+    return {"num_rendered": int(R), "out_color": color, "radii": radii, "alpha_integrated": alpha, "color_integrated": rgb}
 
 
 class OursRun:

@@ -67,7 +67,7 @@ def test_rasterizer_argument_validation():
         r(x, x, torch.zeros(4, 1), shs=None, colors_precomp=None, scales=x, rotations=torch.zeros(4, 4))
     with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
         r(x, x, torch.zeros(4, 1), shs=torch.zeros(4, 4, 3), scales=x, rotations=None)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="CUDA device"):     # integrate exists; like every entry point it has no CPU path
         r.integrate(x, x, x, torch.zeros(4, 1), shs=torch.zeros(4, 4, 3), scales=x, rotations=torch.zeros(4, 4))
 
 
