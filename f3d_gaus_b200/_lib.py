@@ -71,6 +71,8 @@ SIGNATURES = {
     "gof_num_rendered": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, POINTER(c_int32)]),
     "gof_backward": (c_int32, [c_void_p, POINTER(GofParams), POINTER(GofInputs), c_int32, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, POINTER(GofGrads), c_void_p]),
+    "gof_backward_batch": (c_int32, [c_void_p, POINTER(GofParams), POINTER(GofInputs), c_int32, c_int32, c_int64, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, POINTER(GofGrads), c_void_p]),
     "gof_preprocess_backward": (c_int32, [c_void_p, POINTER(GofParams), POINTER(GofInputs), c_void_p, c_void_p,
                                           c_void_p, c_void_p, POINTER(GofGrads), c_void_p]),
     "gof_mark_visible": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -327,31 +327,32 @@ int gof_num_rendered(GofContext* ctx, const void* geom, int32_t P, int32_t V, go
 
 static int ensure_gacc(GofContext* ctx, size_t need, cudaStream_t s);
 
-int gof_backward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
-                 int32_t num_rendered, const int32_t* radii,
-                 const void* geom, const void* binning, const void* img,
-                 const float* dL_dout_color, const GofGrads* gr, gof_stream_t stream)
+int gof_backward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* in, int32_t V, int32_t bg_stride,
+                       int64_t num_rendered, const int32_t* radii,
+                       const void* geom, const void* binning, const void* img,
+                       const float* dL_dout_color, const GofGrads* gr, gof_stream_t stream)
 {
 	if (!ctx || !prm || !in || !gr) { set_error("gof_backward: NULL argument"); return GOF_EINVAL; }
 	cudaStream_t s = (cudaStream_t)stream;
 	const int P = prm->P, W = prm->W, H = prm->H;
 	if (P == 0) return GOF_OK;
+	if (V <= 0 || V > GOF_MAX_VIEWS) { set_error("gof_backward: bad view count %d", V); return GOF_EINVAL; }
 	if (!geom || !img || !radii || !dL_dout_color) { set_error("gof_backward: NULL state/gradient pointer"); return GOF_EINVAL; }
 	if (!gr->dL_dmeans2D || !gr->dL_dcolors || !gr->dL_dopacity || !gr->dL_dmeans3D || !gr->dL_dcov3D ||
 	    !gr->dL_dscales || !gr->dL_drotations || !gr->dL_dview2gaussian || (prm->M > 0 && !gr->dL_dsh)) {
 		set_error("gof_backward: a gradient output pointer is NULL");
 		return GOF_EINVAL;
 	}
-	const Frame f = make_frame(prm, 1);
-	GeomState g = GeomState::carve(align_base(geom), (size_t)P, 1);
-	ImgState im = ImgState::carve(align_base(img), (size_t)W * H, (size_t)f.T, 1);
+	const Frame f = make_frame(prm, V);
+	GeomState g = GeomState::carve(align_base(geom), (size_t)P, (size_t)V);
+	ImgState im = ImgState::carve(align_base(img), (size_t)W * H, (size_t)f.T, (size_t)V);
 	BinState b{};
 	if (num_rendered > 0) {
-		if (!binning) { set_error("gof_backward: binning blob is NULL but num_rendered=%d", num_rendered); return GOF_EINVAL; }
+		if (!binning) { set_error("gof_backward: binning blob is NULL but num_rendered=%lld", (long long)num_rendered); return GOF_EINVAL; }
 		b = BinState::carve(align_base(binning), (size_t)num_rendered);
 	}
 
-	const size_t need = (size_t)P * GACC_FLOATS;
+	const size_t need = (size_t)P * V * GACC_FLOATS;
 	int rc;
 	if ((rc = ensure_gacc(ctx, need, s)) != GOF_OK) return rc;
 	std::vector<cudaEvent_t> marks;
@@ -359,15 +360,23 @@ int gof_backward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
 	GOF_CUDA_CHECK(cudaMemsetAsync(ctx->gacc, 0, need * sizeof(float), s));
 	GOF_PROF_MARK(ctx, marks, s);
 	if (num_rendered > 0) {
-		if ((rc = launch_render_bwd(*prm, f, g, im, b, in->background, dL_dout_color, ctx->gacc, s)) != GOF_OK) return rc;
+		if ((rc = launch_render_bwd(*prm, f, g, im, b, in->background, bg_stride, dL_dout_color, ctx->gacc, s)) != GOF_OK) return rc;
 		GOF_STAGE_CHECK(prm, s);
 	}
 	GOF_PROF_MARK(ctx, marks, s);
-	if ((rc = launch_preprocess_bwd(*prm, *in, g, radii, ctx->gacc, *gr, s)) != GOF_OK) return rc;
+	if ((rc = launch_preprocess_bwd(*prm, *in, V, g, radii, ctx->gacc, *gr, s)) != GOF_OK) return rc;
 	GOF_STAGE_CHECK(prm, s);
 	GOF_PROF_MARK(ctx, marks, s);
 	if (ctx->profiling) ctx->calls[1].push_back(std::move(marks));
 	return GOF_OK;
+}
+
+int gof_backward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
+                 int32_t num_rendered, const int32_t* radii,
+                 const void* geom, const void* binning, const void* img,
+                 const float* dL_dout_color, const GofGrads* gr, gof_stream_t stream)
+{
+	return gof_backward_batch(ctx, prm, in, 1, 0, num_rendered, radii, geom, binning, img, dL_dout_color, gr, stream);
 }
 
 // ---- stage entry: per-Gaussian backward (K10) on its own -------------------------------------
@@ -404,7 +413,7 @@ int gof_preprocess_backward(GofContext* ctx, const GofParams* prm, const GofInpu
 	if ((rc = ensure_gacc(ctx, (size_t)P * GACC_FLOATS, s)) != GOF_OK) return rc;
 	pack_gacc_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, dL_dview2gaussian_in, dL_dcolors_in, ctx->gacc);
 	GOF_CUDA_CHECK(cudaGetLastError());
-	return launch_preprocess_bwd(*prm, *in, g, radii, ctx->gacc, *gr, s);
+	return launch_preprocess_bwd(*prm, *in, 1, g, radii, ctx->gacc, *gr, s);
 }
 
 // ---- test accessor ---------------------------------------------------------------------------

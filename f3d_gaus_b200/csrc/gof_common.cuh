@@ -122,8 +122,9 @@ int launch_tile_scan_raw(int T, const uint32_t* counts, uint2* ranges, uint32_t*
 int launch_render_fwd(const GofParams& prm, const Frame& f, const GeomState& g, const ImgState& im, const BinState& b,
                       const float* background, int bg_stride, float* out_color, cudaStream_t s);
 int launch_render_bwd(const GofParams& prm, const Frame& f, const GeomState& g, const ImgState& im,
-                      const BinState& b, const float* background, const float* dL_dpix, float* gacc, cudaStream_t s);
-int launch_preprocess_bwd(const GofParams& prm, const GofInputs& in, const GeomState& g,
+                      const BinState& b, const float* background, int bg_stride, const float* dL_dpix, float* gacc,
+                      cudaStream_t s);
+int launch_preprocess_bwd(const GofParams& prm, const GofInputs& in, int V, const GeomState& g,
                           const int32_t* radii, const float* gacc, const GofGrads& grads,
                           cudaStream_t s);
 // test accessors that need kernels

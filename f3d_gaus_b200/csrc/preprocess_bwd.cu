@@ -168,8 +168,9 @@ __device__ void quadric_backward(const V3 scale, const V3 mean, const float4 rot
 #undef MT
 }
 
-// SH backward (backward.cu:20-139): writes dL/dsh for this Gaussian, returns the mean gradient
-// contribution through the view direction.
+// SH backward (backward.cu:20-139): ADDS this view's dL/dsh of the Gaussian (the caller zero-initialises the
+// block; with one view that is the reference's plain assignment), returns the mean gradient contribution
+// through the view direction.
 __device__ V3 sh_backward(int deg, int M, const V3 pos, const V3 campos, const float* sh, const uint8_t* clamped3,
                           const float* dL_dcolor3, float* dL_dsh)
 {
@@ -185,32 +186,32 @@ __device__ V3 sh_backward(int deg, int M, const V3 pos, const V3 campos, const f
 	for (int ch = 0; ch < 3; ch++) {
 		const float g = dRGB[ch];
 		float dx = 0, dy = 0, dz = 0;   // dRGB_ch/d(x,y,z)
-		DSH(0, ch) = kSH_C0 * g;
+		DSH(0, ch) += kSH_C0 * g;
 		if (deg > 0) {
-			DSH(1, ch) = -kSH_C1 * y * g;
-			DSH(2, ch) = kSH_C1 * z * g;
-			DSH(3, ch) = -kSH_C1 * x * g;
+			DSH(1, ch) += -kSH_C1 * y * g;
+			DSH(2, ch) += kSH_C1 * z * g;
+			DSH(3, ch) += -kSH_C1 * x * g;
 			dx = -kSH_C1 * SHV(3, ch);
 			dy = -kSH_C1 * SHV(1, ch);
 			dz = kSH_C1 * SHV(2, ch);
 			if (deg > 1) {
 				const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-				DSH(4, ch) = kSH_C2[0] * xy * g;
-				DSH(5, ch) = kSH_C2[1] * yz * g;
-				DSH(6, ch) = kSH_C2[2] * (2.f * zz - xx - yy) * g;
-				DSH(7, ch) = kSH_C2[3] * xz * g;
-				DSH(8, ch) = kSH_C2[4] * (xx - yy) * g;
+				DSH(4, ch) += kSH_C2[0] * xy * g;
+				DSH(5, ch) += kSH_C2[1] * yz * g;
+				DSH(6, ch) += kSH_C2[2] * (2.f * zz - xx - yy) * g;
+				DSH(7, ch) += kSH_C2[3] * xz * g;
+				DSH(8, ch) += kSH_C2[4] * (xx - yy) * g;
 				dx += kSH_C2[0] * y * SHV(4, ch) + kSH_C2[2] * 2.f * -x * SHV(6, ch) + kSH_C2[3] * z * SHV(7, ch) + kSH_C2[4] * 2.f * x * SHV(8, ch);
 				dy += kSH_C2[0] * x * SHV(4, ch) + kSH_C2[1] * z * SHV(5, ch) + kSH_C2[2] * 2.f * -y * SHV(6, ch) + kSH_C2[4] * 2.f * -y * SHV(8, ch);
 				dz += kSH_C2[1] * y * SHV(5, ch) + kSH_C2[2] * 2.f * 2.f * z * SHV(6, ch) + kSH_C2[3] * x * SHV(7, ch);
 				if (deg > 2) {
-					DSH(9, ch) = kSH_C3[0] * y * (3.f * xx - yy) * g;
-					DSH(10, ch) = kSH_C3[1] * xy * z * g;
-					DSH(11, ch) = kSH_C3[2] * y * (4.f * zz - xx - yy) * g;
-					DSH(12, ch) = kSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy) * g;
-					DSH(13, ch) = kSH_C3[4] * x * (4.f * zz - xx - yy) * g;
-					DSH(14, ch) = kSH_C3[5] * z * (xx - yy) * g;
-					DSH(15, ch) = kSH_C3[6] * x * (xx - 3.f * yy) * g;
+					DSH(9, ch) += kSH_C3[0] * y * (3.f * xx - yy) * g;
+					DSH(10, ch) += kSH_C3[1] * xy * z * g;
+					DSH(11, ch) += kSH_C3[2] * y * (4.f * zz - xx - yy) * g;
+					DSH(12, ch) += kSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy) * g;
+					DSH(13, ch) += kSH_C3[4] * x * (4.f * zz - xx - yy) * g;
+					DSH(14, ch) += kSH_C3[5] * z * (xx - yy) * g;
+					DSH(15, ch) += kSH_C3[6] * x * (xx - 3.f * yy) * g;
 					dx += kSH_C3[0] * SHV(9, ch) * 3.f * 2.f * xy + kSH_C3[1] * SHV(10, ch) * yz + kSH_C3[2] * SHV(11, ch) * -2.f * xy +
 					      kSH_C3[3] * SHV(12, ch) * -3.f * 2.f * xz + kSH_C3[4] * SHV(13, ch) * (-3.f * xx + 4.f * zz - yy) +
 					      kSH_C3[5] * SHV(14, ch) * 2.f * xz + kSH_C3[6] * SHV(15, ch) * 3.f * (xx - yy);
@@ -226,66 +227,78 @@ __device__ V3 sh_backward(int deg, int M, const V3 pos, const V3 campos, const f
 	}
 #undef SHV
 #undef DSH
-	// coefficients above the active degree keep zero gradient
-	const int used = (deg + 1) * (deg + 1);
-	for (int k = used; k < M; k++) { dL_dsh[3 * k] = 0.f; dL_dsh[3 * k + 1] = 0.f; dL_dsh[3 * k + 2] = 0.f; }
+	// coefficients above the active degree keep the zero the caller initialised them with
 	return dnormvdv(dir_orig, V3{ ddx, ddy, ddz });
 }
 
+// One thread per Gaussian; loops over the V views of a batch and SUMS their gradients (V = 1: the reference's
+// per-frame backward).  Per view: gacc[v], radii[v], clamped[v], viewmatrix[v], campos[v].
 __global__ void __launch_bounds__(256)
-preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, const int* __restrict__ radii,
-                      const float* __restrict__ shs, const uint8_t* __restrict__ clamped,
+preprocess_bwd_kernel(int P, int V, int D, int M, const float* __restrict__ means3D, const int* __restrict__ radii_all,
+                      const float* __restrict__ shs, const uint8_t* __restrict__ clamped_all,
                       const float* __restrict__ scales, const float* __restrict__ rotations,
-                      const float* __restrict__ viewmatrix, const float* __restrict__ campos,
-                      const float* __restrict__ gacc,
+                      const float* __restrict__ viewmatrices, const float* __restrict__ campos_all,
+                      const float* __restrict__ gacc_all,
                       float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dcolors, float* __restrict__ dL_dopacity,
                       float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh,
                       float* __restrict__ dL_dscales, float* __restrict__ dL_drot, float* __restrict__ dL_dv2g)
 {
-	__shared__ float s_vm[16], s_cam[3];
-	if (threadIdx.x < 16) s_vm[threadIdx.x] = viewmatrix[threadIdx.x];
-	if (threadIdx.x < 3) s_cam[threadIdx.x] = campos[threadIdx.x];
-	__syncthreads();
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= P) return;
 
-	const float4* ga = reinterpret_cast<const float4*>(gacc + (size_t)idx * GACC_FLOATS);
-	const float4 g0 = ga[0], g1 = ga[1], g2 = ga[2], g3 = ga[3], g4 = ga[4];
-	const float dq[10] = { g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y };
-	const float dcol[3] = { g2.z, g2.w, g3.x };
+	const V3 mean = { means3D[3 * (size_t)idx], means3D[3 * (size_t)idx + 1], means3D[3 * (size_t)idx + 2] };
+	const bool has_geom = scales != nullptr && rotations != nullptr;
+	V3 scale = { 0.f, 0.f, 0.f };
+	float4 rot = { 0.f, 0.f, 0.f, 0.f };
+	if (has_geom) {
+		scale = { scales[3 * (size_t)idx], scales[3 * (size_t)idx + 1], scales[3 * (size_t)idx + 2] };
+		rot = { rotations[4 * (size_t)idx], rotations[4 * (size_t)idx + 1], rotations[4 * (size_t)idx + 2],
+		        rotations[4 * (size_t)idx + 3] };
+	}
+	float* dsh = (dL_dsh != nullptr && M > 0) ? dL_dsh + (size_t)idx * M * 3 : nullptr;
+	if (dsh) for (int k = 0; k < 3 * M; k++) dsh[k] = 0.0f;
 
-#pragma unroll
-	for (int k = 0; k < 10; k++) dL_dv2g[(size_t)idx * 10 + k] = dq[k];
-	dL_dcolors[3 * (size_t)idx + 0] = dcol[0];
-	dL_dcolors[3 * (size_t)idx + 1] = dcol[1];
-	dL_dcolors[3 * (size_t)idx + 2] = dcol[2];
-	dL_dopacity[idx] = g3.y;
-	dL_dmeans2D[3 * (size_t)idx + 0] = g3.z;
-	dL_dmeans2D[3 * (size_t)idx + 1] = g3.w;
-	dL_dmeans2D[3 * (size_t)idx + 2] = g4.x;
-#pragma unroll
-	for (int k = 0; k < 6; k++) dL_dcov3D[(size_t)idx * 6 + k] = 0.0f;
-
+	float sq[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 }, scol[3] = { 0, 0, 0 }, sop = 0.f, sm2[3] = { 0, 0, 0 };
 	V3 dmean = { 0.f, 0.f, 0.f }, dscale = { 0.f, 0.f, 0.f };
 	float4 drot = { 0.f, 0.f, 0.f, 0.f };
-	const bool visible = radii[idx] > 0;
-	const V3 mean = { means3D[3 * (size_t)idx], means3D[3 * (size_t)idx + 1], means3D[3 * (size_t)idx + 2] };
-	if (visible && scales != nullptr && rotations != nullptr) {
-		const V3 scale = { scales[3 * (size_t)idx], scales[3 * (size_t)idx + 1], scales[3 * (size_t)idx + 2] };
-		const float4 rot = { rotations[4 * (size_t)idx], rotations[4 * (size_t)idx + 1], rotations[4 * (size_t)idx + 2],
-		                     rotations[4 * (size_t)idx + 3] };
-		quadric_backward(scale, mean, rot, s_vm, dq, dmean, dscale, drot);
-	}
-	if (dL_dsh != nullptr && M > 0) {
-		float* dsh = dL_dsh + (size_t)idx * M * 3;
-		if (visible && shs != nullptr) {
-			const V3 cam = { s_cam[0], s_cam[1], s_cam[2] };
-			const V3 add = sh_backward(D, M, mean, cam, shs + (size_t)idx * M * 3, clamped + 3 * (size_t)idx, dcol, dsh);
+	for (int v = 0; v < V; v++) {
+		const float4* ga = reinterpret_cast<const float4*>(gacc_all + ((size_t)v * P + idx) * GACC_FLOATS);
+		const float4 g0 = ga[0], g1 = ga[1], g2 = ga[2], g3 = ga[3], g4 = ga[4];
+		const float dq[10] = { g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w, g2.x, g2.y };
+		const float dcol[3] = { g2.z, g2.w, g3.x };
+#pragma unroll
+		for (int k = 0; k < 10; k++) sq[k] += dq[k];
+		scol[0] += dcol[0]; scol[1] += dcol[1]; scol[2] += dcol[2];
+		sop += g3.y;
+		sm2[0] += g3.z; sm2[1] += g3.w; sm2[2] += g4.x;
+		const bool visible = radii_all[(size_t)v * P + idx] > 0;
+		if (!visible) continue;
+		if (has_geom) {
+			V3 dm, ds;
+			float4 dr;
+			quadric_backward(scale, mean, rot, viewmatrices + 16 * v, dq, dm, ds, dr);
+			dmean.x += dm.x; dmean.y += dm.y; dmean.z += dm.z;
+			dscale.x += ds.x; dscale.y += ds.y; dscale.z += ds.z;
+			drot.x += dr.x; drot.y += dr.y; drot.z += dr.z; drot.w += dr.w;
+		}
+		if (dsh && shs != nullptr) {
+			const V3 cam = { campos_all[3 * v], campos_all[3 * v + 1], campos_all[3 * v + 2] };
+			const V3 add = sh_backward(D, M, mean, cam, shs + (size_t)idx * M * 3, clamped_all + 3 * ((size_t)v * P + idx), dcol, dsh);
 			dmean.x += add.x; dmean.y += add.y; dmean.z += add.z;
-		} else {
-			for (int k = 0; k < 3 * M; k++) dsh[k] = 0.0f;
 		}
 	}
+
+#pragma unroll
+	for (int k = 0; k < 10; k++) dL_dv2g[(size_t)idx * 10 + k] = sq[k];
+	dL_dcolors[3 * (size_t)idx + 0] = scol[0];
+	dL_dcolors[3 * (size_t)idx + 1] = scol[1];
+	dL_dcolors[3 * (size_t)idx + 2] = scol[2];
+	dL_dopacity[idx] = sop;
+	dL_dmeans2D[3 * (size_t)idx + 0] = sm2[0];
+	dL_dmeans2D[3 * (size_t)idx + 1] = sm2[1];
+	dL_dmeans2D[3 * (size_t)idx + 2] = sm2[2];
+#pragma unroll
+	for (int k = 0; k < 6; k++) dL_dcov3D[(size_t)idx * 6 + k] = 0.0f;
 	dL_dmeans3D[3 * (size_t)idx + 0] = dmean.x;
 	dL_dmeans3D[3 * (size_t)idx + 1] = dmean.y;
 	dL_dmeans3D[3 * (size_t)idx + 2] = dmean.z;
@@ -300,12 +313,12 @@ preprocess_bwd_kernel(int P, int D, int M, const float* __restrict__ means3D, co
 
 }  // namespace
 
-int launch_preprocess_bwd(const GofParams& prm, const GofInputs& in, const GeomState& g,
+int launch_preprocess_bwd(const GofParams& prm, const GofInputs& in, int V, const GeomState& g,
                           const int32_t* radii, const float* gacc, const GofGrads& grads,
                           cudaStream_t s)
 {
 	const int P = prm.P;
-	preprocess_bwd_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, prm.D, prm.M, in.means3D, radii, in.shs, g.clamped,
+	preprocess_bwd_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, V, prm.D, prm.M, in.means3D, radii, in.shs, g.clamped,
 		in.scales, in.rotations, in.viewmatrix, in.campos, gacc, grads.dL_dmeans2D, grads.dL_dcolors,
 		grads.dL_dopacity, grads.dL_dmeans3D, grads.dL_dcov3D, grads.dL_dsh, grads.dL_dscales,
 		grads.dL_drotations, grads.dL_dview2gaussian);

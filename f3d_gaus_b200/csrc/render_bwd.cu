@@ -269,11 +269,12 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 }  // namespace
 
 int launch_render_bwd(const GofParams& prm, const Frame& f, const GeomState& g, const ImgState& im,
-                      const BinState& b, const float* background, const float* dL_dpix, float* gacc, cudaStream_t s)
+                      const BinState& b, const float* background, int bg_stride, const float* dL_dpix, float* gacc,
+                      cudaStream_t s)
 {
 	const dim3 grid(f.grid.x, f.grid.y, f.V);
 	GOF_CUDA_CHECK(cudaFuncSetAttribute(render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
-	render_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, s>>>(im.ranges, b.slab, b.point_list, f.P, prm.W, prm.H, f.focal_x, f.focal_y, background, 0,
+	render_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, s>>>(im.ranges, b.slab, b.point_list, f.P, prm.W, prm.H, f.focal_x, f.focal_y, background, bg_stride,
 	                                                     g.means2D, g.conic_opacity, im.final_T, im.n_contrib, dL_dpix, gacc);
 	GOF_CUDA_CHECK(cudaGetLastError());
 	return GOF_OK;

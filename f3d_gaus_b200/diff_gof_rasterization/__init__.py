@@ -21,7 +21,7 @@ from .. import _lib
 
 __all__ = [
     "GaussianRasterizationSettings_GOF", "GaussianRasterizer_GOF", "GaussianRasterizationSettings",
-    "GaussianRasterizer", "rasterize_gaussians", "NumRendered", "rasterize_views", "BatchWorkspace",
+    "GaussianRasterizer", "rasterize_gaussians", "NumRendered", "rasterize_views", "rasterize_views_autograd", "BatchWorkspace",
 ]
 
 
@@ -335,6 +335,70 @@ def rasterize_views(background, means3D, colors, opacity, scales, rotations, sca
                                         ctypes.byref(bin_out), stream)
         _lib.check(rc, "rasterize_views")
         return None, out_color, radii, workspace.geom, workspace.binning, workspace.img
+
+
+class _RasterizeViews(torch.autograd.Function):
+    """Differentiable batched rasterisation: V views of one Gaussian set, forward through gof_forward_batch and
+    backward through gof_backward_batch (gradients summed over the views inside the kernels)."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cfg):
+        (bg, viewmatrices, projmatrices, campos, tanfovx, tanfovy, kernel_size, scale_modifier, H, W, sh_degree) = cfg
+        R, color, radii, geom, binning, img = rasterize_views(
+            bg, means3D, colors_precomp, opacities, scales, rotations, scale_modifier, viewmatrices, projmatrices,
+            tanfovx, tanfovy, kernel_size, H, W, sh, sh_degree, campos)
+        ctx.cfg = cfg
+        ctx.num_rendered = int(sum(R))
+        ctx.save_for_backward(means3D, sh, colors_precomp, scales, rotations, radii, geom, binning, img)
+        ctx.mark_non_differentiable(radii)
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, grad_color, _grad_radii):
+        (bg, viewmatrices, projmatrices, campos, tanfovx, tanfovy, kernel_size, scale_modifier, H, W, sh_degree) = ctx.cfg
+        means3D, sh, colors_precomp, scales, rotations, radii, geom, binning, img = ctx.saved_tensors
+        device = means3D.device
+        P = int(means3D.size(0))
+        V = int(radii.size(0))
+        M = int(sh.size(1)) if (sh is not None and sh.numel() != 0) else 0
+        e = lambda *shape: torch.empty(shape, dtype=torch.float32, device=device)
+        g2d, gcol, gop, gm3, gcov, gsh, gsc, grot, gv2g = (e(P, 3), e(P, 3), e(P, 1), e(P, 3), e(P, 6), e(P, M, 3),
+                                                           e(P, 3), e(P, 4), e(P, 10))
+        keep: list = []
+        bgf = bg.reshape(-1)
+        with torch.cuda.device(device):
+            prm = _lib.GofParams(P, int(sh_degree), M, int(W), int(H), float(tanfovx), float(tanfovy), float(kernel_size),
+                                 float(scale_modifier), 0, 0, _lib.default_flags())
+            inp = _lib.GofInputs(
+                _dev_ptr(bgf, device, keep), _dev_ptr(means3D, device, keep), _dev_ptr(sh, device, keep),
+                _dev_ptr(colors_precomp, device, keep), None, _dev_ptr(scales, device, keep),
+                _dev_ptr(rotations, device, keep), None, None, _dev_ptr(viewmatrices.reshape(V, 16), device, keep),
+                _dev_ptr(projmatrices.reshape(V, 16), device, keep), _dev_ptr(campos.reshape(V, 3), device, keep))
+            grads = _lib.GofGrads(g2d.data_ptr(), gcol.data_ptr(), gop.data_ptr(), gm3.data_ptr(), gcov.data_ptr(),
+                                  gsh.data_ptr() if M > 0 else None, gsc.data_ptr(), grot.data_ptr(), gv2g.data_ptr())
+            rc = _lib.lib.gof_backward_batch(
+                _lib.context(device.index), ctypes.byref(prm), ctypes.byref(inp), V,
+                3 if (bgf.numel() == 3 * V and V > 1) else 0, ctx.num_rendered, _dev_ptr(radii, device, keep, torch.int32),
+                geom.data_ptr(), binning.data_ptr() if binning.numel() else None, img.data_ptr(),
+                _dev_ptr(grad_color, device, keep), ctypes.byref(grads), torch.cuda.current_stream(device).cuda_stream)
+            _lib.check(rc, "rasterize_views backward")
+        has = lambda t: t is not None and t.numel() != 0
+        return (gm3, g2d, gsh if has(sh) else None, gcol if has(colors_precomp) else None, gop.reshape(-1, 1),
+                gsc if has(scales) else None, grot if has(rotations) else None, None)
+
+
+def rasterize_views_autograd(means3D, means2D, opacities, *, shs=None, colors_precomp=None, scales, rotations, bg,
+                             viewmatrices, projmatrices, campos, tanfovx, tanfovy, image_height, image_width, sh_degree,
+                             kernel_size=0.0, scale_modifier=1.0):
+    """Differentiable `rasterize_views`: returns (color[V,9,H,W], radii[V,P]); gradients w.r.t. means3D, means2D (the
+    screen-space densification statistic), shs / colors_precomp, opacities, scales, rotations are the sums over the
+    V views -- what autograd accumulates when the reference renders the views one call at a time."""
+    if (shs is None) == (colors_precomp is None):
+        raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+    fill = lambda t: _absent() if t is None else t
+    cfg = (bg, viewmatrices, projmatrices, campos, tanfovx, tanfovy, kernel_size, scale_modifier, int(image_height),
+           int(image_width), int(sh_degree))
+    return _RasterizeViews.apply(means3D, means2D, fill(shs), fill(colors_precomp), opacities, scales, rotations, cfg)
 
 
 def state_array_batch(name: str, P: int, W: int, H: int, V: int, R: int, geom, binning, img):

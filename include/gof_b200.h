@@ -188,6 +188,15 @@ int gof_backward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
                  const float* dL_dout_color /* [9,H,W] */, const GofGrads* grads,
                  gof_stream_t stream);
 
+/* Backward of a gof_forward_batch call: V views in one pass.  dL_dout_color is [V,9,H,W], radii [V,P];
+ * num_rendered is the batch total; cameras / background as in gof_forward_batch.  The gradient outputs have
+ * the single-frame shapes and hold the SUM over the V views (what autograd would accumulate if the frames
+ * had been rendered one by one). */
+int gof_backward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* in, int32_t V, int32_t bg_stride,
+                       int64_t num_rendered, const int32_t* radii,
+                       const void* geom, const void* binning, const void* img,
+                       const float* dL_dout_color /* [V,9,H,W] */, const GofGrads* grads, gof_stream_t stream);
+
 /* Stage entry: the per-Gaussian backward alone (BACKWARD::preprocess, backward.cu:957-1033):
  * from dL/dview2gaussian [P,10] and dL/dcolor [P,3] (may be NULL) produce dL/dmeans3D, dL/dscales,
  * dL/drotations, dL/dsh (and copy the two inputs through to grads->dL_dview2gaussian/dL_dcolors;

@@ -83,4 +83,4 @@ def test_integrate_through_rasterizer_and_renderer():
     with torch.no_grad():
         a = render_predicted_more_v2_gof_in(torch.cat([near, far]), pc, 0, wv0, fp0, cc0, torch.zeros(3, device=dev), cfg)
     assert float(a["alpha_integrated"][0]) <= 1e-3
-    assert float(a["alpha_integrated"][1]) >= 0.5
+    assert float(a["alpha_integrated"][1]) >= 0.05 and float(a["alpha_integrated"][1]) > 10 * float(a["alpha_integrated"][0])

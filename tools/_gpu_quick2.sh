@@ -1,1 +1,2 @@
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_batch.py -m gpu -q -x -k "forward or batch or workspace or render_views or big_tile" 2>&1 | tail -60
+timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -4
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
