@@ -133,6 +133,13 @@ __device__ __forceinline__ float rcp_approx(float x)
 	return r;
 }
 
+__device__ __forceinline__ float rsqrt_approx(float x)
+{
+	float r;
+	asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // one MUFU.RSQ, no denormal fix-up (x >= 1e-7 here)
+	return r;
+}
+
 // true  => the reference skips this pair (no side effects); false => run the exact path.
 // q32 = BB^2/(4 AA) from 3 roundings + a 1-ulp reciprocal: within 3e-7 relative of the exact
 // quotient of the float32 AA, BB the reference widens to double (1e-6 is the bound used).
@@ -153,7 +160,10 @@ __device__ __forceinline__ bool pair_alpha_exact(const PairGeom& g, float C, flo
 	// both t and the BB/AA factor of the ray minimum.
 	const double u = (-BB) / AA;
 	t = (float)(u * 0.5);
-	if (t <= 0.2) return false;   // compared in double, like NEAR_PLANE (auxiliary.h:26)
+	// The reference compares the float t with the DOUBLE constant 0.2 (NEAR_PLANE, auxiliary.h:26).  0.2 is not a
+	// float: the floats around it are 0.19999998807907104 (0x3E4CCCCC) and 0.20000000298023224 (0x3E4CCCCD), so
+	// for a float t:  t <= 0.2 (double)  <=>  t <= 0x3E4CCCCC.  NaN fails both forms alike.
+	if (t <= __uint_as_float(0x3E4CCCCCu)) return false;
 	const double mv = fma(u, BB * 0.25, (double)C);
 	float power = (float)(mv * -0.5);
 	if (power > 0.0f) power = 0.0f;

@@ -200,20 +200,24 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 			// ---- pass 2: each pixel blends its own survivors, in list order.  ONE loop over the whole
 			// chunk: the warp iterates max-over-lanes(survivors in 128 records) times, m0 is the word being
 			// consumed, m1..m3 shift down when it runs empty.
-			uint32_t jbase = 0;
-			while ((m0 | m1 | m2 | m3) != 0) {
-				if (m0 == 0) { m0 = m1; m1 = m2; m2 = m3; m3 = 0; jbase += 32; }
-				if (m0 != 0) {
-					const uint32_t j = jbase + (uint32_t)__ffs((int)m0) - 1u;
-					m0 &= m0 - 1u;
-					const uint32_t r = rec + j * SLAB_BYTES;
-					const float4 k1 = lds128(r + 16), k2 = lds128(r + 32), k3 = lds128(r + 48), k4 = lds128(r + 64);
-					const PairGeom g = pair_geom(k1, k2, k3, rx, ry);
-					float t, alpha, G;
-					if (pair_alpha_exact(g, k4.x, k1.z, t, alpha, G)) {
-						const float4 d = make_float4(k4.y, k4.z, k4.w, 0.0f);
-						if (blend_pair<EXACT>(st, g, t, alpha, d, base + j + 1)) { done = true; m0 = 0; m1 = 0; m2 = 0; m3 = 0; }
-					}
+			// `cur` = the word being consumed, `wsel` its index; m1..m3 stay loop-invariant.
+			uint32_t cur = m0, wsel = 0;
+			for (;;) {
+				if (cur == 0) {   // next non-empty word of this lane, or leave the loop
+					if (wsel < 1 && m1 != 0) { cur = m1; wsel = 1; }
+					else if (wsel < 2 && m2 != 0) { cur = m2; wsel = 2; }
+					else if (wsel < 3 && m3 != 0) { cur = m3; wsel = 3; }
+					else break;
+				}
+				const uint32_t j = 32u * wsel + (uint32_t)__ffs((int)cur) - 1u;
+				cur &= cur - 1u;
+				const uint32_t r = rec + j * SLAB_BYTES;
+				const float4 k1 = lds128(r + 16), k2 = lds128(r + 32), k3 = lds128(r + 48), k4 = lds128(r + 64);
+				const PairGeom g = pair_geom(k1, k2, k3, rx, ry);
+				float t, alpha, G;
+				if (pair_alpha_exact(g, k4.x, k1.z, t, alpha, G)) {
+					const float4 d = make_float4(k4.y, k4.z, k4.w, 0.0f);
+					if (blend_pair<EXACT>(st, g, t, alpha, d, base + j + 1)) { done = true; break; }
 				}
 			}
 			warp_done = __all_sync(0xffffffffu, done);
