@@ -178,6 +178,7 @@ class OursArm:
         self.out = None
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.gathered = None
+        self.sink = None
 
     def _prepare(self, flat):
         c = flat[0]
@@ -219,23 +220,21 @@ class OursArm:
         return self._lib.profile_read(self.device.index)
 
     def e2e_step(self, host_pc, dev_pc, cams_dev, cfg, bg, out_dev, out_host):
-        """Public API of the loop (render_views) from pinned host buffers: H2D of the Gaussian set, one batched
-        render of the 8 views, D2H of rgb/depth/alpha."""
-        from f3d_gaus_b200.gaussian_renderer import render_views
+        """Public API of the loop from pinned host buffers: H2D of the Gaussian set, batched render of the 8 views
+        (gaussian_renderer.HostFrameSink), D2H of rgb/depth/alpha into pinned host memory."""
+        from f3d_gaus_b200.gaussian_renderer import HostFrameSink
+        if self.sink is None:
+            self.sink = HostFrameSink(VIEWS, RES, RES, self.device, chunks=1)   # measured: 2 x 4-view passes are slower (tools/e2e_breakdown.py)
         for k in host_pc:
             dev_pc[k].copy_(host_pc[k], non_blocking=True)
-        o = render_views(dev_pc, 0, cams_dev[0], cams_dev[1], cams_dev[2], bg, cfg, workspace=self.ws_e2e, epilogue=False)
-        out_dev[:, 0:3].copy_(o["render"])
-        out_dev[:, 3:4].copy_(o["rendered_depth"])
-        out_dev[:, 4:5].copy_(o["rendered_alpha"])
+        self.sink.render(dev_pc, 0, cams_dev[0], cams_dev[1], cams_dev[2], bg, cfg)
         if self.world > 1:
             # the path's one exchange step (SURVEY.md 8e): every rank receives all scenes' frames
             from f3d_gaus_b200 import sharding
-            self.gathered = sharding.gather_frames(out_dev.unsqueeze(0), self.world)
-        out_host.copy_(out_dev, non_blocking=True)
+            self.gathered = sharding.gather_frames(self.sink.staging.unsqueeze(0), self.world)
 
     def e2e_finish(self):
-        return self.ws_e2e.finish()
+        return self.sink.finish()
 
     def e2e_per_view_step(self, host_pc, dev_pc, cams_dev, cfg, bg, out_dev, out_host):
         """The same through the reference's own one-frame function (render_predicted_more_v2_gof)."""
@@ -490,8 +489,9 @@ def main():
         "config": {"workload": "nvs256: 65536 f3d-like Gaussians (SH deg 1) per GPU, 8 orbit views, 256x256, forward "
                                "(BASELINE configs[1])", "frames_per_step": VIEWS, "num_rendered_per_step": R_step,
                    "l2": "flushed (256 MB write) between timed steps",
-                   "api": ("value: gof_forward_batch (8 views per call, sync-free); e2e: render_views from pinned host "
-                           "buffers" if args.impl == "ours" else "one Rasterizer::forward call per frame")},
+                   "api": ("value: gof_forward_batch (8 views per call, sync-free); e2e: HostFrameSink.render (render_views + D2H of "
+                           "rgb/depth/alpha) from pinned host buffers" if args.impl == "ours"
+                           else "one Rasterizer::forward call per frame")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / K,

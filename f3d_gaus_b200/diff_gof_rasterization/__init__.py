@@ -232,6 +232,8 @@ class BatchWorkspace:
 
     def __init__(self, device):
         self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.geom = self.img = self.binning = None
         self.key = None
         self.capacity_hint = 0

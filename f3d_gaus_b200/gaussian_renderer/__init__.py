@@ -3,6 +3,7 @@
   render_predicted_more_v2_gof   (:915-1067)  dict-of-tensors -> rasterizer -> output dict
   depths_to_points / depth_to_normal (:881-909)
   render_predicted_more_v2_gof_in (:1070-1228) point integration for mesh extraction (rasterizer.integrate)
+  HostFrameSink                   render_views + pipelined D2H of rgb/depth/alpha (the loops' `.cpu()` return path)
   render_views                    all V views of a scene in one batched pass (what the reference's render loops do frame by frame)
   render                          the vanilla signature (src/gaussian-splatting/gaussian_renderer/__init__.py:18-100)
 
@@ -226,6 +227,63 @@ def render_views(pc: dict, bs, world_view_transforms, full_proj_transforms, came
             _lib.check(rc, "gof_render_epilogue_batch")
             out["rendered_normal"], out["depth_normal"] = normal_world, depth_normal
     return out
+
+
+class HostFrameSink:
+    """Return path of the render loops to HOST memory (the reference does `.cpu()` on rgb, depth and alpha of every
+    frame, visualize.py:304-306): the V views are rendered in `chunks` batched passes and each pass's
+    [v,5,H,W] (rgb, median depth, alpha) block is copied to pinned host memory on a side stream while the next
+    pass renders (at 8 views of 256x256 one pass is fastest -- tools/e2e_breakdown.py -- so chunks defaults to 1; long
+    orbits such as the reference's 128-view loop are the use case for more).  `finish()` waits for the copies and returns the per-view num_rendered (None => a binning blob
+    overflowed and was grown: call `render` again)."""
+
+    def __init__(self, V: int, H: int, W: int, device, chunks: int = 1):
+        self.V, self.H, self.W, self.device = V, H, W, torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.chunks = max(1, min(chunks, V))
+        self.per = -(-V // self.chunks)
+        self.staging = torch.empty((V, 5, H, W), dtype=torch.float32, device=self.device)
+        self.host = torch.empty((V, 5, H, W), dtype=torch.float32).pin_memory()
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.workspaces = [BatchWorkspace(self.device) for _ in range(self.chunks)]
+        self.done = torch.cuda.Event()
+
+    def render(self, pc, bs, world_view_transforms, full_proj_transforms, camera_centers, bg_color, cfg, **kw):
+        main = torch.cuda.current_stream(self.device)
+        wv = world_view_transforms.reshape(self.V, 4, 4)
+        fp = full_proj_transforms.reshape(self.V, 4, 4)
+        cc = camera_centers.reshape(self.V, 3)
+        for ci in range(self.chunks):
+            lo, hi = ci * self.per, min(self.V, (ci + 1) * self.per)
+            if lo >= hi:
+                break
+            o = render_views(pc, bs, wv[lo:hi], fp[lo:hi], cc[lo:hi], bg_color, cfg, workspace=self.workspaces[ci],
+                             epilogue=False, **kw)
+            st = self.staging[lo:hi]
+            st[:, 0:3].copy_(o["render"])
+            st[:, 3:4].copy_(o["rendered_depth"])
+            st[:, 4:5].copy_(o["rendered_alpha"])
+            ready = torch.cuda.Event()
+            ready.record(main)
+            self.copy_stream.wait_event(ready)
+            with torch.cuda.stream(self.copy_stream):
+                self.host[lo:hi].copy_(st, non_blocking=True)
+        self.done.record(self.copy_stream)
+        main.wait_event(self.done)          # a later synchronisation of the main stream covers the copies
+        return self.host
+
+    def finish(self):
+        self.done.synchronize()
+        out = []
+        for ws in self.workspaces[:self.chunks]:
+            if ws.key is None:
+                continue
+            r = ws.finish()
+            if r is None:
+                return None
+            out += r
+        return out
 
 
 def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None,

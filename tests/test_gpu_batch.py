@@ -225,3 +225,22 @@ def test_batched_backward_equals_sum_of_per_view_backwards(kind):
     tol = 2e-2 if kind == "unit" else 0.5
     for k in ("xyz", "scaling", "rotation"):
         assert rel(g2[k], g1[k]) <= tol, (k, rel(g2[k], g1[k]))
+
+
+def test_host_frame_sink_pipelined_copy():
+    from f3d_gaus_b200.gaussian_renderer import HostFrameSink, render_views
+    pc, cams, cfg = _scene(128, 256)
+    dev = "cuda"
+    wv, fp, cc = cams.world_view.to(dev), cams.full_proj.to(dev), cams.centers.to(dev)
+    bg = torch.tensor([0.1, 0.2, 0.3], device=dev)
+    want = render_views(pc, 0, wv, fp, cc, bg, cfg, epilogue=False)
+    sink = HostFrameSink(8, 256, 256, dev, chunks=3)
+    for _ in range(2):                      # first call sizes the binning blobs (may overflow and grow)
+        host = sink.render(pc, 0, wv, fp, cc, bg, cfg)
+        R = sink.finish()
+        if R is not None:
+            break
+    assert R == want["num_rendered"]
+    assert torch.equal(host[:, 0:3], want["render"].cpu())
+    assert torch.equal(host[:, 3:4], want["rendered_depth"].cpu())
+    assert torch.equal(host[:, 4:5], want["rendered_alpha"].cpu())
