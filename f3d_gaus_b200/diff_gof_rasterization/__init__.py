@@ -39,6 +39,46 @@ def _dev_ptr(t: torch.Tensor | None, device: torch.device, keep: list, dtype=tor
     return t.data_ptr()
 
 
+_SIZES: dict = {}
+
+
+def _state_sizes(P: int, W: int, H: int, V: int = 1):
+    """(geom_bytes, img_bytes) of the opaque state blobs -- pure host arithmetic in the library, cached."""
+    key = (P, W, H, V)
+    got = _SIZES.get(key)
+    if got is None:
+        gsz, isz, bsz = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+        _lib.check(_lib.lib.gof_state_sizes_batch(P, W, H, V, 0, ctypes.byref(gsz), ctypes.byref(isz), ctypes.byref(bsz)),
+                   "gof_state_sizes")
+        got = _SIZES[key] = (gsz.value, isz.value)
+    return got
+
+
+class _BinningAllocator:
+    """The binning-blob allocation callback (the reference's resizeFunctional, rasterize_points.cu:28-34): one
+    persistent ctypes callback; `device` is set before each call, `blob` holds the tensor it allocated."""
+
+    def __init__(self):
+        self.device = None
+        self.blob = None
+        self.callback = _lib.ALLOC_FN(self._alloc)
+
+    def _alloc(self, _user, nbytes):
+        self.blob = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self.blob.data_ptr()
+
+    def arm(self, device):
+        self.device, self.blob = device, None
+        return self.callback
+
+    def take(self, device):
+        blob, self.blob = self.blob, None
+        return blob if blob is not None else torch.empty(0, dtype=torch.uint8, device=device)
+
+
+_ALLOC = _BinningAllocator()
+
+
 class NumRendered(int):
     """`num_rendered` as the reference returns it (a Python int)."""
 
@@ -71,18 +111,9 @@ class _CModule:
 
             out_color = torch.empty((_lib.OUTPUT_CHANNELS, H, W), dtype=torch.float32, device=device)
             radii = torch.empty((P,), dtype=torch.int32, device=device)
-            gsz, isz, bsz = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
-            _lib.check(_lib.lib.gof_state_sizes(P, W, H, 0, ctypes.byref(gsz), ctypes.byref(isz), ctypes.byref(bsz)),
-                       "gof_state_sizes")
-            geom = torch.empty(gsz.value, **byte_opts)
-            img = torch.empty(isz.value, **byte_opts)
-            holder = {}
-
-            def _alloc(_user, nbytes):
-                holder["binning"] = torch.empty(int(nbytes), **byte_opts)
-                return holder["binning"].data_ptr()
-
-            alloc_cb = _lib.ALLOC_FN(_alloc)
+            gbytes, ibytes = _state_sizes(P, W, H)
+            geom = torch.empty(gbytes, **byte_opts)
+            img = torch.empty(ibytes, **byte_opts)
             prm = _lib.GofParams(P, int(degree), M, W, H, float(tan_fovx), float(tan_fovy), float(kernel_size),
                                  float(scale_modifier), int(bool(prefiltered)), int(bool(debug)), _lib.default_flags())
             inp = _lib.GofInputs(
@@ -94,13 +125,11 @@ class _CModule:
             R = ctypes.c_int32(0)
             bin_out = ctypes.c_void_p()
             rc = _lib.lib.gof_forward(_lib.context(device.index), ctypes.byref(prm), ctypes.byref(inp),
-                                      geom.data_ptr(), geom.numel(), img.data_ptr(), img.numel(),
-                                      None, 0, alloc_cb, None, out_color.data_ptr(), radii.data_ptr(),
+                                      geom.data_ptr(), gbytes, img.data_ptr(), ibytes,
+                                      None, 0, _ALLOC.arm(device), None, out_color.data_ptr(), radii.data_ptr(),
                                       ctypes.byref(R), ctypes.byref(bin_out), stream)
             _lib.check(rc, "rasterize_gaussians")
-            binning = holder.get("binning")
-            if binning is None:
-                binning = torch.empty(0, **byte_opts)
+            binning = _ALLOC.take(device)
         return NumRendered(R.value), out_color, radii, geom, binning, img
 
     # -- backward -----------------------------------------------------------------------------
