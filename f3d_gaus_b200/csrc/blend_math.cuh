@@ -1,7 +1,7 @@
 // blend_math.cuh -- device helpers shared by the forward and backward tile blends:
 //   * mbarrier + TMA bulk-copy (cp.async.bulk, SASS UBLKCP) primitives for the slab pipeline;
-//   * the GOF ray-minimum evaluation of one (pixel, Gaussian) pair, split into a cheap
-//     conservative float32 pre-test and the exact path.
+//   * the exact GOF ray-minimum evaluation of one (pixel, Gaussian) pair (the cheap conservative
+//     pre-test that precedes it is the tile-local conic of conic.cuh).
 //
 // Arithmetic contract.  The reference evaluates, per pair (forward.cu:502-535):
 //     n  = Sigma_v * (rx, ry, 1)            float32
@@ -16,15 +16,12 @@
 // (n_k = S_kz + fma(S_kx, rx, S_ky*ry) etc.; established from its sm_100a SASS), so the
 // result does not depend on this compiler's contraction choices.
 //
-// The pre-test.  alpha >= 1/255 needs  w*exp(-mv/2) >= 1/255, i.e. mv <= 2 ln(255 w) =: tau0.
-// q32 = BB^2/(4 AA) evaluated in float32 is within 1e-6 relative of the exact q (3 roundings
-// + a 2-ulp approximate divide < 4e-7), so  mv >= C - q32 (1 + 1e-6)  whenever AA > 0.  If
-// that lower bound already exceeds tau = tau0 * 1.00001 + 2e-3 (stored per record by the
-// preprocess; -FLT_MAX when w < 1/255 since power <= 0 caps alpha at w) the pair is skipped
-// by the reference too -- either by its alpha test or by its t test, both of which have no
-// side effect other than `continue`.  NaNs fail every comparison and fall through to the
-// exact path.  Roughly 9 in 10 pairs of a tile list end here after ~20 float32 operations
-// and never touch the FP64 pipe.
+// The contribution threshold.  alpha >= 1/255 needs  w*exp(-mv/2) >= 1/255, i.e.
+// mv <= 2 ln(255 w) =: tau0.  The preprocess stores tau = tau0 * 1.00001 + 2e-3 per Gaussian
+// (-FLT_MAX when w < 1/255, since power <= 0 caps alpha at w; +FLT_MAX for a NaN opacity): a pair
+// whose ray minimum exceeds tau is skipped by the reference too -- by its alpha test or by its t
+// test, neither of which has a side effect other than `continue`.  The conic pre-test is built
+// from this tau plus a bound of the reference's own float32 evaluation error.
 #pragma once
 #include "gof_common.cuh"
 
@@ -138,16 +135,6 @@ __device__ __forceinline__ float rsqrt_approx(float x)
 	float r;
 	asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // one MUFU.RSQ, no denormal fix-up (x >= 1e-7 here)
 	return r;
-}
-
-// true  => the reference skips this pair (no side effects); false => run the exact path.
-// q32 = BB^2/(4 AA) from 3 roundings + a 1-ulp reciprocal: within 3e-7 relative of the exact
-// quotient of the float32 AA, BB the reference widens to double (1e-6 is the bound used).
-__device__ __forceinline__ bool pair_pretest_reject(const PairGeom& g, float C, float tau)
-{
-	const float q32 = __fmul_rn(__fmul_rn(__fmul_rn(g.BB, g.BB), 0.25f), rcp_approx(g.AA));
-	const float lower = __fmaf_rn(-1.000001f, q32, C);
-	return (g.AA > 1e-30f) && (lower > tau);
 }
 
 // Exact alpha of the pair.  Returns false if the reference `continue`s (t <= near plane or

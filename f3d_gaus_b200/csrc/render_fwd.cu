@@ -71,7 +71,7 @@ __device__ __forceinline__ bool blend_pair(PixState& s, const PairGeom& g, float
 	} else {
 		// same quantities with float32 reciprocals: far/(far-near) - (far*near/(far-near)) / t
 		m = __fmaf_rn(-(float)((100.0 * 0.2) / (100.0 - 0.2)), rcp_approx(t), (float)(100.0 / (100.0 - 0.2)));
-		const float inv_len = rsqrtf(len2 + 1e-7f);
+		const float inv_len = rsqrt_approx(len2 + 1e-7f);
 		nn0 = g.n0 * inv_len;
 		nn1 = g.n1 * inv_len;
 		nn2 = g.n2 * inv_len;
