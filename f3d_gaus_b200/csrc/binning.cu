@@ -71,6 +71,7 @@ BinState BinState::carve(char* base, size_t R)
 	take(p, b.entries, R);
 	take(p, b.point_list, R);
 	take(p, b.slab, R * SLAB_FLOATS);
+	take(p, b.block_mask, R);
 	b.total = align_up((size_t)(p - base)) + ALIGN;
 	return b;
 }
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 3)
 tile_sort_gather_kernel(int P, int T, dim3 grid, int W, int H, float focal_x, float focal_y, float ray_pad,
                         const uint2* __restrict__ ranges, uint64_t* __restrict__ entries,
                         const float* __restrict__ rec_all, uint32_t* __restrict__ point_list,
-                        float* __restrict__ slab, const int32_t* __restrict__ mailbox)
+                        float* __restrict__ slab, uint8_t* __restrict__ block_mask, const int32_t* __restrict__ mailbox)
 {
 	__shared__ uint64_t s_e[SORT_CAP];
 	if (mailbox[1]) return;
@@ -334,6 +335,7 @@ tile_sort_gather_kernel(int P, int T, dim3 grid, int W, int H, float focal_x, fl
 		const float4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2), q3 = __ldg(src + 3);
 		float c[6];
 		conic_coefficients(q0, q1, q2, tr, c);
+		block_mask[range.x + i] = (uint8_t)conic_block_mask(c, (double)ray_pad);
 		float4* dst = reinterpret_cast<float4*>(slab + (size_t)(range.x + i) * SLAB_FLOATS);
 		dst[0] = make_float4(c[0], c[1], c[2], c[3]);
 		dst[1] = make_float4(c[4], c[5], q2.w, q0.x);          // c4 c5 w Sxx
@@ -412,7 +414,7 @@ int launch_binning(const Frame& f, const GeomState& g, const ImgState& im, const
 	                                      g.mailbox);
 	GOF_CUDA_CHECK(cudaGetLastError());
 	tile_sort_gather_kernel<<<f.V * f.T, SORT_THREADS, 0, s>>>(f.P, f.T, f.grid, f.W, f.H, f.focal_x, f.focal_y, ray_pad, im.ranges,
-	                                                           b.entries, g.rec, b.point_list, b.slab, g.mailbox);
+	                                                           b.entries, g.rec, b.point_list, b.slab, b.block_mask, g.mailbox);
 	GOF_CUDA_CHECK(cudaGetLastError());
 	return GOF_OK;
 }

@@ -66,7 +66,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 // consumer warps of its scheduler.
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity)
 {
-	while (!mbar_try_wait(bar, parity)) __nanosleep(200);
+	while (!mbar_try_wait(bar, parity)) __nanosleep(1000);
 }
 // Shared-memory loads by 32-bit shared-window address (no generic-address arithmetic in the loops).
 __device__ __forceinline__ float4 lds128(uint32_t addr)
@@ -135,6 +135,21 @@ __device__ __forceinline__ float rsqrt_approx(float x)
 	float r;
 	asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // one MUFU.RSQ, no denormal fix-up (x >= 1e-7 here)
 	return r;
+}
+
+// Branch-free form of pair_alpha_exact for callers that evaluate two independent pairs per iteration (the
+// two dependency chains -- double division, exp -- then interleave): same results, validity returned.
+__device__ __forceinline__ bool pair_alpha_eval(const PairGeom& g, float C, float w, float& t, float& alpha)
+{
+	const double AA = g.AA;
+	const double BB = g.BB;
+	const double u = (-BB) / AA;
+	t = (float)(u * 0.5);
+	const double mv = fma(u, BB * 0.25, (double)C);
+	float power = (float)(mv * -0.5);
+	power = (power > 0.0f) ? 0.0f : power;
+	alpha = min(0.99f, __fmul_rn(w, expf(power)));
+	return !(t <= __uint_as_float(0x3E4CCCCCu)) && !(alpha < 1.0f / 255.0f);
 }
 
 // Exact alpha of the pair.  Returns false if the reference `continue`s (t <= near plane or

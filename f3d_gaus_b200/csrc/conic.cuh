@@ -132,6 +132,33 @@ __device__ __forceinline__ void conic_coefficients(const float4& q0, const float
 	}
 }
 
+// Which of the tile's eight 8x4 pixel blocks (block b: x in [8(b&1), 8(b&1)+7], y in [4(b>>1), 4(b>>1)+3], the
+// pixels of consumer warp b of the blend kernels) can contain a pixel that passes the conic test.  For a block
+// with centre (cx, cy) and half-widths (hx, hy), any quadratic obeys
+//     g(x, y) <= g(c) + |g_x(c)| hx + |g_y(c)| hy + max(c3,0) hx^2 + |c4| hx hy + max(c5,0) hy^2 =: U,
+// and the blend's float32 evaluation exceeds the exact polynomial by at most eta (see conic_coefficients), so
+// U + eta < 0 proves that the whole block rejects the record.  `pad` widens the block for sub-pixel rays.
+__device__ __forceinline__ uint32_t conic_block_mask(const float* c, double pad)
+{
+	const double c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4], c5 = c[5];
+	if (!(c0 < 1.0e30)) return 0xffu;                  // "never skip" records (and NaNs) stay relevant everywhere
+	const double m = 15.0 + pad;
+	const double eta = 16.0 * 5.9604644775390625e-08 *
+	                   (fabs(c0) + m * (fabs(c1) + fabs(c2)) + m * m * (fabs(c3) + fabs(c4) + fabs(c5)));
+	const double hx = 3.5 + pad, hy = 1.5 + pad;
+	const double quad = fmax(c3, 0.0) * hx * hx + fabs(c4) * hx * hy + fmax(c5, 0.0) * hy * hy + eta;
+	uint32_t mask = 0;
+#pragma unroll
+	for (int b = 0; b < 8; b++) {
+		const double cx = 8.0 * (b & 1) + 3.5, cy = 4.0 * (b >> 1) + 1.5;
+		const double gc = c0 + cx * (c1 + c3 * cx + c4 * cy) + cy * (c2 + c5 * cy);
+		const double gx = c1 + 2.0 * c3 * cx + c4 * cy, gy = c2 + c4 * cx + 2.0 * c5 * cy;
+		const double U = gc + fabs(gx) * hx + fabs(gy) * hy + quad;
+		if (!(U < 0.0)) mask |= 1u << b;
+	}
+	return mask;
+}
+
 // g(x, y) < 0  =>  the reference skips the pair.
 __device__ __forceinline__ bool conic_reject(float c0, float c1, float c2, float c3, float c4, float c5, float x, float y)
 {

@@ -69,7 +69,8 @@ struct ImgState {
 struct BinState {
 	uint64_t* entries;         // [R]  (depth bits << 32) | Gaussian index, bucketed by tile, then sorted in place
 	uint32_t* point_list;      // [R]  sorted Gaussian indices (the reference's point_list)
-	float* slab;               // [R,24] tile-ordered slab records
+	float* slab;               // [R,20] tile-ordered slab records
+	uint8_t* block_mask;       // [R]  bit b: the record can pass the conic test in 8x4 pixel block b of its tile
 	size_t total;
 	static BinState carve(char* base, size_t R);
 };

@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(FWD_THREADS, GOF_FWD_MIN_CTAS)
 render_fwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ slab, int W, int H,
                   float focal_x, float focal_y, const float* __restrict__ bg_colors, int bg_stride,
                   float* __restrict__ final_T_all, uint32_t* __restrict__ n_contrib_all, float* __restrict__ out_color_all,
-                  const int32_t* __restrict__ mailbox)
+                  const int32_t* __restrict__ mailbox, const uint8_t* __restrict__ block_mask)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	float4 (*s_rec)[CHUNK * REC_F4] = reinterpret_cast<float4 (*)[CHUNK * REC_F4]>(smem_raw);
@@ -172,53 +172,79 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 	bool warp_done = __all_sync(0xffffffffu, done);
 
 	const uint32_t rec_base = smem_u32(smem_raw);
+	const uint8_t* tile_bm = block_mask + range.x;
 	for (int c = 0; c < nchunks; c++) {
 		const int s = c % STAGES;
+		const int cnt = min(CHUNK, n - c * CHUNK);
+		// this lane's share of the chunk's block masks (records lane, 32+lane, 64+lane, 96+lane): read from
+		// L2 before waiting for the TMA stage so that the latency overlaps it
+		uint32_t bm0 = 0, bm1 = 0, bm2 = 0, bm3 = 0;
+		if (!warp_done) {
+			const uint8_t* q = tile_bm + c * CHUNK + lane;
+			if (lane < cnt) bm0 = __ldg(q);
+			if (32 + lane < cnt) bm1 = __ldg(q + 32);
+			if (64 + lane < cnt) bm2 = __ldg(q + 64);
+			if (96 + lane < cnt) bm3 = __ldg(q + 96);
+		}
 		mbar_wait(&s_full[s], (uint32_t)((c / STAGES) & 1));
 		if (!warp_done) {
-			const int cnt = min(CHUNK, n - c * CHUNK);
 			const uint32_t rec = rec_base + (uint32_t)s * (CHUNK * SLAB_BYTES);   // shared-window address of the stage
 			const uint32_t base = (uint32_t)c * CHUNK;
-			// ---- pass 1: branch-free conic sweep over the chunk (broadcast reads, 5 FMAs per pair) ----
+			// ---- pass 1: conic sweep over the chunk's records that can touch this warp's 8x4 block (bit `warp`
+			// of the record's block mask, ~1/3 of them); coefficients are warp-broadcast shared-memory reads.
 			uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;   // survivors among records [0,32) [32,64) [64,96) [96,128)
 #pragma unroll 1
 			for (int w = 0; w < CHUNK / 32; w++) {
 				const int valid = cnt - 32 * w;
 				if (valid <= 0) break;
+				const uint32_t bm = (w == 0) ? bm0 : (w == 1) ? bm1 : (w == 2) ? bm2 : bm3;
+				uint32_t rel = __ballot_sync(0xffffffffu, (bm >> warp) & 1u);
 				uint32_t bits = 0;
 				const uint32_t rw = rec + (uint32_t)w * (32 * SLAB_BYTES);
-#pragma unroll
-				for (int jj = 0; jj < 32; jj++) {
-					const float4 k0 = lds128(rw + jj * SLAB_BYTES);
-					const float2 k1 = lds64(rw + jj * SLAB_BYTES + 16);
-					if (!conic_reject(k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, fx, fy)) bits |= 1u << jj;
+				while (rel != 0) {                       // warp-uniform; two records per trip for ILP
+					const int j0 = __ffs((int)rel) - 1;
+					rel &= rel - 1;
+					const int j1 = rel ? __ffs((int)rel) - 1 : j0;
+					rel &= rel - 1;                      // (0 & -1 == 0 when the second record does not exist)
+					const float4 a0 = lds128(rw + j0 * SLAB_BYTES), a1 = lds128(rw + j1 * SLAB_BYTES);
+					const float2 b0 = lds64(rw + j0 * SLAB_BYTES + 16), b1 = lds64(rw + j1 * SLAB_BYTES + 16);
+					if (!conic_reject(a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, fx, fy)) bits |= 1u << j0;
+					if (!conic_reject(a1.x, a1.y, a1.z, a1.w, b1.x, b1.y, fx, fy)) bits |= 1u << j1;
 				}
-				if (valid < 32) bits &= (1u << valid) - 1u;   // stale records beyond the list end
 				if (w == 0) m0 = bits; else if (w == 1) m1 = bits; else if (w == 2) m2 = bits; else m3 = bits;
 			}
 			if (done) { m0 = 0; m1 = 0; m2 = 0; m3 = 0; }
 			// ---- pass 2: each pixel blends its own survivors, in list order.  ONE loop over the whole
 			// chunk: the warp iterates max-over-lanes(survivors in 128 records) times, m0 is the word being
 			// consumed, m1..m3 shift down when it runs empty.
-			// `cur` = the word being consumed, `wsel` its index; m1..m3 stay loop-invariant.
+			// `cur` = the word being consumed, `wsel` its index; m1..m3 stay loop-invariant.  Two survivors are
+			// taken per trip: their exact evaluations (double division, exp) are independent dependency chains
+			// that interleave, the two blends then run in list order.
 			uint32_t cur = m0, wsel = 0;
+			auto refill = [&]() -> bool {      // make `cur` non-empty; false when the lane has no survivors left
+				if (cur != 0) return true;
+				if (wsel < 1 && m1 != 0) { cur = m1; wsel = 1; return true; }
+				if (wsel < 2 && m2 != 0) { cur = m2; wsel = 2; return true; }
+				if (wsel < 3 && m3 != 0) { cur = m3; wsel = 3; return true; }
+				return false;
+			};
 			for (;;) {
-				if (cur == 0) {   // next non-empty word of this lane, or leave the loop
-					if (wsel < 1 && m1 != 0) { cur = m1; wsel = 1; }
-					else if (wsel < 2 && m2 != 0) { cur = m2; wsel = 2; }
-					else if (wsel < 3 && m3 != 0) { cur = m3; wsel = 3; }
-					else break;
-				}
-				const uint32_t j = 32u * wsel + (uint32_t)__ffs((int)cur) - 1u;
+				if (!refill()) break;
+				const uint32_t ja = 32u * wsel + (uint32_t)__ffs((int)cur) - 1u;
 				cur &= cur - 1u;
-				const uint32_t r = rec + j * SLAB_BYTES;
-				const float4 k1 = lds128(r + 16), k2 = lds128(r + 32), k3 = lds128(r + 48), k4 = lds128(r + 64);
-				const PairGeom g = pair_geom(k1, k2, k3, rx, ry);
-				float t, alpha, G;
-				if (pair_alpha_exact(g, k4.x, k1.z, t, alpha, G)) {
-					const float4 d = make_float4(k4.y, k4.z, k4.w, 0.0f);
-					if (blend_pair<EXACT>(st, g, t, alpha, d, base + j + 1)) { done = true; break; }
-				}
+				const bool hb = refill();
+				uint32_t jb = ja;
+				if (hb) { jb = 32u * wsel + (uint32_t)__ffs((int)cur) - 1u; cur &= cur - 1u; }
+				const uint32_t ra = rec + ja * SLAB_BYTES, rb = rec + jb * SLAB_BYTES;
+				const float4 a1 = lds128(ra + 16), a2 = lds128(ra + 32), a3 = lds128(ra + 48), a4 = lds128(ra + 64);
+				const float4 b1 = lds128(rb + 16), b2 = lds128(rb + 32), b3 = lds128(rb + 48), b4 = lds128(rb + 64);
+				const PairGeom ga = pair_geom(a1, a2, a3, rx, ry);
+				const PairGeom gb = pair_geom(b1, b2, b3, rx, ry);
+				float ta, alpha_a, tb, alpha_b;
+				const bool oka = pair_alpha_eval(ga, a4.x, a1.z, ta, alpha_a);
+				const bool okb = pair_alpha_eval(gb, b4.x, b1.z, tb, alpha_b) && hb;
+				if (oka && blend_pair<EXACT>(st, ga, ta, alpha_a, make_float4(a4.y, a4.z, a4.w, 0.0f), base + ja + 1)) { done = true; break; }
+				if (okb && blend_pair<EXACT>(st, gb, tb, alpha_b, make_float4(b4.y, b4.z, b4.w, 0.0f), base + jb + 1)) { done = true; break; }
 			}
 			warp_done = __all_sync(0xffffffffu, done);
 		}
@@ -263,10 +289,10 @@ int launch_render_fwd(const GofParams& prm, const Frame& f, const GeomState& g, 
 	}
 	if (prm.flags & GOF_FLAG_EXACT_BLEND)
 		render_fwd_kernel<true><<<grid, FWD_THREADS, smem, s>>>(im.ranges, b.slab, prm.W, prm.H, f.focal_x, f.focal_y,
-		                                                     background, bg_stride, im.final_T, im.n_contrib, out_color, g.mailbox);
+		                                                     background, bg_stride, im.final_T, im.n_contrib, out_color, g.mailbox, b.block_mask);
 	else
 		render_fwd_kernel<false><<<grid, FWD_THREADS, smem, s>>>(im.ranges, b.slab, prm.W, prm.H, f.focal_x, f.focal_y,
-		                                                      background, bg_stride, im.final_T, im.n_contrib, out_color, g.mailbox);
+		                                                      background, bg_stride, im.final_T, im.n_contrib, out_color, g.mailbox, b.block_mask);
 	GOF_CUDA_CHECK(cudaGetLastError());
 	return GOF_OK;
 }

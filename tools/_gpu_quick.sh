@@ -1,4 +1,4 @@
-timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -4
 timeout 300 python bench.py --no-cpu-baseline --steps 20 | python -c "
 import sys,json
 d=json.loads(sys.stdin.read()); r=d['roofline']

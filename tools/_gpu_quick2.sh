@@ -1,1 +1,3 @@
-timeout 600 python tools/bench_config5.py > gpurun_out/config5.json 2>gpurun_out/config5.err; cat gpurun_out/config5.json; tail -3 gpurun_out/config5.err
+mkdir -p gpurun_out/bm
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_fwd_kernel -s 4 -c 1 -o gpurun_out/bm/fwd python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bm/log.txt 2>&1
+ls -la gpurun_out/bm
