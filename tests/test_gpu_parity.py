@@ -164,17 +164,23 @@ def test_backward(name):
     n = lambda t: t.detach().cpu().numpy()
     clamped = n(of["clamped"]) if c.get("shs") is not None else n(torch.zeros_like(of["clamped"]))
     ex = oracle_cpu.preprocess_backward(cn, n(radii), clamped, n(ref["dL_dview2gaussian"]), n(ref["dL_dcolors"]), f64=True)
+    # the same exact map applied to OUR blend gradients: how far the (in-tolerance, ~1e-7) difference of the blend
+    # gradients is carried by the ill-conditioned map itself, independent of any float32 rounding in K10
+    ex_o = oracle_cpu.preprocess_backward(cn, n(radii), clamped, n(ours["dL_dview2gaussian"]), n(ours["dL_dcolors"]), f64=True)
     stage = {"dL_dmeans3D": gm3, "dL_dscales": gsc, "dL_drotations": grot}
     for k in QUADRIC_GRADS:
         exact = torch.from_numpy(ex[k])
         e_ref, e_ours = rel_l2(ref[k].cpu(), exact), rel_l2(stage[k].cpu(), exact)
         # (the absolute floor covers tiny, well-conditioned cases where the reference happens to round exactly)
         assert e_ours <= 2 * e_ref + 3e-3, f"{k}: ours {e_ours:.3e} vs reference {e_ref:.3e} from the float64 value"
-        # (2) end to end: within the bar, or indistinguishable from the reference's own float32 noise
-        #     (run-to-run atomics order, and its rounding distance from the float64 value)
+        # (2) end to end: within the bar, or indistinguishable from the reference's own float32 noise (run-to-run
+        #     atomics order, its rounding distance from the float64 value) plus the exactly propagated difference
+        #     of the blend gradients
         noise = max(rel_l2(refs[1][k], ref[k]), e_ref)
+        carried = rel_l2(torch.from_numpy(ex_o[k]), exact)
         e = rel_l2(ours[k], ref[k])
-        assert e <= 1e-3 + 8 * noise, f"{k}: end-to-end rel L2 {e:.3e} vs reference float32 noise {noise:.3e}"
+        assert e <= 1e-3 + 8 * noise + 2 * carried, \
+            f"{k}: end-to-end rel L2 {e:.3e} vs reference float32 noise {noise:.3e}, carried {carried:.3e}"
     if c.get("shs") is not None:
         grad_close("dL_dsh(stage)", gsh, ref["dL_dsh"])
 
