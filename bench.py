@@ -179,6 +179,8 @@ class OursArm:
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.gathered = None
         self.sink = None
+        self.peer = None
+        self.exchange = None
 
     def _prepare(self, flat):
         c = flat[0]
@@ -229,9 +231,21 @@ class OursArm:
             dev_pc[k].copy_(host_pc[k], non_blocking=True)
         self.sink.render(dev_pc, 0, cams_dev[0], cams_dev[1], cams_dev[2], bg, cfg)
         if self.world > 1:
-            # the path's one exchange step: every rank receives all scenes' frames
+            # the path's one exchange step: every rank receives all scenes' frames -- one kernel that
+            # packs the consumed channels and stores them into every rank's buffer over NVLink peer memory
+            # (sharding.PeerFrameGather); NCCL all_gather if symmetric memory cannot be set up
             from f3d_gaus_b200 import sharding
-            self.gathered = sharding.gather_frames(self.sink.staging.unsqueeze(0), self.world)
+            if self.peer is None:
+                try:
+                    self.peer = sharding.PeerFrameGather(self.world, VIEWS, RES, RES, self.device)
+                    self.exchange = "fused pack + all-gather over NVLink peer memory (gof_pack_gather, torch symmetric memory)"
+                except Exception as ex:      # noqa: BLE001
+                    self.peer = False
+                    self.exchange = f"NCCL all_gather_into_tensor (peer memory unavailable: {type(ex).__name__})"
+            if self.peer:
+                self.gathered = self.peer.push(self.sink.last_raster, first_scene=int(os.environ.get("RANK", "0")))
+            else:
+                self.gathered = sharding.gather_frames(self.sink.staging.unsqueeze(0), self.world)
 
     def e2e_finish(self):
         return self.sink.finish()
@@ -497,8 +511,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / K,
-                "exchange": (f"all_gather_into_tensor of [1,{VIEWS},5,{RES},{RES}] f32 per rank (NCCL)"
-                             if (world > 1 and args.impl == "ours") else None)},
+                "exchange": (getattr(arm, "exchange", None) if (world > 1 and args.impl == "ours") else None)},
         "gpu_launches": launches,
     }
     if args.impl == "ours":

@@ -219,7 +219,8 @@ int gof_forward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* in
 	BinState b;
 	if (binning != nullptr) {
 		// sync-free mode: capacity is whatever fits in the caller's blob; R stays on the device
-		capacity = binning_capacity(binning_bytes - (size_t)(align_base(binning) - (char*)binning));
+		const size_t skew = (size_t)(align_base(binning) - (char*)binning);
+		capacity = binning_bytes > skew ? binning_capacity(binning_bytes - skew) : 0;
 		if ((rc = launch_tile_scan(f, g, im, capacity, s)) != GOF_OK) return rc;
 		GOF_STAGE_CHECK(prm, s);
 		GOF_PROF_MARK(ctx, marks, s);
@@ -467,6 +468,48 @@ int64_t gof_state_get(const char* name, int32_t P, int32_t W, int32_t H, int64_t
                       void* dst, int64_t dst_bytes, gof_stream_t stream)
 {
 	return gof_state_get_batch(name, P, W, H, 1, R, geom, binning, img, dst, dst_bytes, stream);
+}
+
+// ---- pack + all-gather over peer memory -----------------------------------------------------------
+// The path's one exchange step: every rank needs the rgb / median depth / alpha of all frames.
+// Instead of packing the five consumed channels and then calling an all-gather, ONE kernel reads this rank's
+// raster output [F,9,N] and stores the packed [F,5,N] block straight into the gather buffer of EVERY rank over
+// NVLink (peer pointers of a symmetric allocation), or into all of them at once through the NVSwitch multicast
+// address (multimem.st) when the allocation has one.  A symmetric-memory barrier afterwards makes the frames visible.
+__device__ __forceinline__ void multimem_st_v4(float* addr, float4 v)
+{
+	asm volatile("multimem.st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__global__ void pack_gather_kernel(const float* __restrict__ raster, int F, size_t N, const long long* __restrict__ peer_ptrs,
+                                   int world, float* multicast, size_t dst_frame0)
+{
+	const int f = blockIdx.y;
+	const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;   // N % 4 == 0 is checked by the launcher
+	if (i4 >= N || f >= F) return;
+	const int src_ch[5] = { 0, 1, 2, CH_DEPTH, CH_ALPHA };
+#pragma unroll
+	for (int c = 0; c < 5; c++) {
+		const float4 v = *reinterpret_cast<const float4*>(raster + ((size_t)f * OUT_CH + src_ch[c]) * N + i4);
+		const size_t off = ((dst_frame0 + f) * 5 + c) * N + i4;
+		if (multicast != nullptr) {
+			multimem_st_v4(multicast + off, v);
+		} else {
+			for (int r = 0; r < world; r++) *reinterpret_cast<float4*>(reinterpret_cast<float*>(peer_ptrs[r]) + off) = v;
+		}
+	}
+}
+
+int gof_pack_gather(const float* raster, int32_t frames, int64_t pixels, const int64_t* peer_ptrs_dev, int32_t world,
+                    void* multicast_ptr, int64_t dst_frame0, gof_stream_t stream)
+{
+	if (!raster || frames <= 0 || pixels <= 0 || world <= 0 || (!peer_ptrs_dev && !multicast_ptr)) { set_error("gof_pack_gather: bad argument"); return GOF_EINVAL; }
+	if (pixels % 4 != 0) { set_error("gof_pack_gather: pixel count must be a multiple of 4"); return GOF_EINVAL; }
+	dim3 grid((unsigned)((pixels / 4 + 255) / 256), frames);
+	pack_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(raster, frames, (size_t)pixels, (const long long*)peer_ptrs_dev, world,
+	                                                          (float*)multicast_ptr, (size_t)dst_frame0);
+	GOF_CUDA_CHECK(cudaGetLastError());
+	return GOF_OK;
 }
 
 // ---- fused L2 epilogue -----------------------------------------------------------------------

@@ -281,12 +281,9 @@ int launch_render_fwd(const GofParams& prm, const Frame& f, const GeomState& g, 
 {
 	const dim3 grid(f.grid.x, f.grid.y, f.V);
 	const size_t smem = (size_t)STAGES * CHUNK * SLAB_BYTES + 2 * STAGES * sizeof(uint64_t);
-	static bool attr_set = false;
-	if (!attr_set) {
-		GOF_CUDA_CHECK(cudaFuncSetAttribute(render_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		GOF_CUDA_CHECK(cudaFuncSetAttribute(render_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		attr_set = true;
-	}
+	// per device and per function; cheap enough to set on every launch (one process may drive several GPUs)
+	GOF_CUDA_CHECK(cudaFuncSetAttribute(render_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	GOF_CUDA_CHECK(cudaFuncSetAttribute(render_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	if (prm.flags & GOF_FLAG_EXACT_BLEND)
 		render_fwd_kernel<true><<<grid, FWD_THREADS, smem, s>>>(im.ranges, b.slab, prm.W, prm.H, f.focal_x, f.focal_y,
 		                                                     background, bg_stride, im.final_T, im.n_contrib, out_color, g.mailbox, b.block_mask);

@@ -248,6 +248,7 @@ class HostFrameSink:
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.workspaces = [BatchWorkspace(self.device) for _ in range(self.chunks)]
         self.done = torch.cuda.Event()
+        self.last_raster = None
 
     def render(self, pc, bs, world_view_transforms, full_proj_transforms, camera_centers, bg_color, cfg, **kw):
         main = torch.cuda.current_stream(self.device)
@@ -260,6 +261,7 @@ class HostFrameSink:
                 break
             o = render_views(pc, bs, wv[lo:hi], fp[lo:hi], cc[lo:hi], bg_color, cfg, workspace=self.workspaces[ci],
                              epilogue=False, **kw)
+            self.last_raster = o["raster"]            # [v,9,H,W] of the last pass (the whole batch when chunks == 1)
             st = self.staging[lo:hi]
             st[:, 0:3].copy_(o["render"])
             st[:, 3:4].copy_(o["rendered_depth"])

@@ -31,7 +31,9 @@
  *   - every function returns 0 on success or a negative GOF_E* code; gof_last_error() gives the
  *     message.  No C++ exception crosses this boundary;
  *   - kernels are launched on the caller's `stream` (the reference uses the legacy default
- *     stream only; passing 0 reproduces that).
+ *     stream only; passing 0 reproduces that);
+ *   - a GofContext belongs to one device and is not thread-safe (it owns the pinned mailbox and the
+ *     backward accumulator): use one context per calling thread, as the reference is used under the GIL.
  */
 #ifndef GOF_B200_H_
 #define GOF_B200_H_
@@ -223,6 +225,15 @@ int gof_render_epilogue(const float* out_color, const float* viewmatrix, int32_t
 int gof_render_epilogue_batch(const float* out_color, const float* viewmatrix, int32_t V, int32_t W, int32_t H,
                               float fovx, float fovy, float* normal_world, float* depth_normal,
                               gof_stream_t stream);
+
+/* Fused pack + all-gather of rendered frames over NVLink peer memory (the scene-sharded runner's one exchange
+ * step; no reference counterpart -- the reference is single-GPU).  raster: this rank's [frames,9,H*W] output;
+ * peer_ptrs_dev: DEVICE array of `world` pointers to every rank's gather buffer [total_frames,5,H*W] (a symmetric
+ * allocation, e.g. torch symmetric memory); multicast_ptr: the allocation's NVSwitch multicast address or NULL;
+ * dst_frame0: index of this rank's first frame in the gathered order.  Writes rgb, median depth, alpha of every
+ * local frame into all ranks' buffers; the caller issues the symmetric-memory barrier that publishes them. */
+int gof_pack_gather(const float* raster, int32_t frames, int64_t pixels, const int64_t* peer_ptrs_dev, int32_t world,
+                    void* multicast_ptr, int64_t dst_frame0, gof_stream_t stream);
 
 /* Test accessor: copy one named array of the opaque state into dst (device pointer).
  * Names: depths[P] f32, means2D[P,2] f32, conic_opacity[P,4] f32, view2gaussian[P,10] f32,
