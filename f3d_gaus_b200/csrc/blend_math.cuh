@@ -154,13 +154,13 @@ __device__ __forceinline__ bool pair_alpha_eval(const PairGeom& g, float C, floa
 
 // Exact alpha of the pair.  Returns false if the reference `continue`s (t <= near plane or
 // alpha < 1/255).  Outputs t, alpha and G = exp(power) (the backward needs G).
-__device__ __forceinline__ bool pair_alpha_exact(const PairGeom& g, float C, float w, float& t, float& alpha, float& G)
+__device__ __forceinline__ bool pair_alpha_exact(const PairGeom& g, float C, float w, float& t, float& alpha, float& G, double& u)
 {
 	const double AA = g.AA;
 	const double BB = g.BB;
 	// -BB/(2AA) == (-BB/AA) * 0.5 exactly (power-of-two scaling), so one IEEE division serves
 	// both t and the BB/AA factor of the ray minimum.
-	const double u = (-BB) / AA;
+	u = (-BB) / AA;
 	t = (float)(u * 0.5);
 	// The reference compares the float t with the DOUBLE constant 0.2 (NEAR_PLANE, auxiliary.h:26).  0.2 is not a
 	// float: the floats around it are 0.19999998807907104 (0x3E4CCCCC) and 0.20000000298023224 (0x3E4CCCCD), so
@@ -173,6 +173,11 @@ __device__ __forceinline__ bool pair_alpha_exact(const PairGeom& g, float C, flo
 	alpha = min(0.99f, __fmul_rn(w, G));
 	if (alpha < 1.0f / 255.0f) return false;
 	return true;
+}
+__device__ __forceinline__ bool pair_alpha_exact(const PairGeom& g, float C, float w, float& t, float& alpha, float& G)
+{
+	double u;
+	return pair_alpha_exact(g, C, w, t, alpha, G, u);
 }
 
 }  // namespace gof

@@ -43,6 +43,14 @@ __device__ __forceinline__ void red_global_v4(float* addr, float4 v)
 	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// 1/x for a float x to ~48 bits: correctly rounded float reciprocal + one Newton step in double (2 DFMA instead
+// of an IEEE double division; only used for gradient VALUES, never for alpha / T / the contributing set).
+__device__ __forceinline__ double rcp_refined(float x)
+{
+	const double r = (double)__frcp_rn(x);
+	return fma(r, fma(-(double)x, r, 1.0), r);
+}
+
 __global__ void __launch_bounds__(BWD_THREADS, GOF_BWD_MIN_CTAS)
 render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ slab, const uint32_t* __restrict__ point_list,
                   int P, int W, int H,
@@ -185,19 +193,25 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 				const PairGeom g = pair_geom(k1, k2, k3, rx, ry);
 				const float w = k1.z;
 				float t, alpha, G;
-				if (pair_alpha_exact(g, k4.x, w, t, alpha, G)) {
+				double u;                                       // -BB/AA, from the forward's own double division
+				if (pair_alpha_exact(g, k4.x, w, t, alpha, G, u)) {
 					const uint32_t contributor = base + j;   // 0-based position in the tile list
 					const int gid = (int)__ldg(&tile_ids[contributor]);
-					const double td = t;
-					const float mapped = (float)(fma(td, 100.0, -(100.0 * 0.2)) / ((100.0 - 0.2) * td));
-					const float dmax_t_dd = (float)((100.0 * 0.2) / ((100.0 - 0.2) * td * td));
-					const float length = (float)sqrt((double)(g.n0 * g.n0 + g.n1 * g.n1 + g.n2 * g.n2) + 1e-7);
-					const float nn[3] = { -g.n0 / length, -g.n1 / length, -g.n2 / length };
+					// Gradient arithmetic: the reference spends ~8 double and ~8 float divisions per pair here
+					// (backward.cu:843-925).  The contributing SET and alpha, T are bit-exact (shared with the
+					// forward); the gradient VALUES only have to meet the 1e-3 relative bar, so each group of
+					// divisions by the same quantity is one reciprocal and multiplies (differences ~1e-7).
+					const double inv_t = rcp_refined(t);
+					const float mapped = (float)((100.0 / (100.0 - 0.2)) - ((100.0 * 0.2) / (100.0 - 0.2)) * inv_t);
+					const float dmax_t_dd = (float)(((100.0 * 0.2) / (100.0 - 0.2)) * inv_t * inv_t);
+					const float inv_len = __frcp_rn(sqrtf(g.n0 * g.n0 + g.n1 * g.n1 + g.n2 * g.n2 + 1e-7f));
+					const float nn[3] = { -g.n0 * inv_len, -g.n1 * inv_len, -g.n2 * inv_len };
 					const float nraw[3] = { g.n0, g.n1, g.n2 };
+					const float inv_1ma = __frcp_rn(1.f - alpha);
 					float* dst = gacc + (size_t)gid * GACC_FLOATS;
 					float gcol[3];
 
-					T = T / (1.f - alpha);
+					T = T * inv_1ma;
 					const float weight = alpha * T;
 					float dL_dalpha = 0.0f;
 					const float col[3] = { k4.y, k4.z, k4.w };
@@ -220,17 +234,17 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 						dL_dnn[ch] = weight * dL_dnormal2D[ch];
 					}
 					float dL_dlength = dL_dnn[0] * nraw[0] + dL_dnn[1] * nraw[1] + dL_dnn[2] * nraw[2];
-					dL_dlength *= 1.f / (length * length);
-					float dL_dn[3] = { (-dL_dnn[0] + dL_dlength * nraw[0]) / length,
-					                   (-dL_dnn[1] + dL_dlength * nraw[1]) / length,
-					                   (-dL_dnn[2] + dL_dlength * nraw[2]) / length };
+					dL_dlength *= inv_len * inv_len;
+					float dL_dn[3] = { (-dL_dnn[0] + dL_dlength * nraw[0]) * inv_len,
+					                   (-dL_dnn[1] + dL_dlength * nraw[1]) * inv_len,
+					                   (-dL_dnn[2] + dL_dlength * nraw[2]) * inv_len };
 
 					float dL_dt = dL_dmax_t;
 					if (contributor == max_contributor - 1) dL_dt += dL_dmax_depth;
 
 					dL_dalpha *= T;
 					last_alpha = alpha;
-					dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+					dL_dalpha += (-T_final * inv_1ma) * bg_dot_dpixel;
 
 					const float dL_dG = w * dL_dalpha;
 					const float2 xy = __ldg(&means2D[gid]);
@@ -243,12 +257,13 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 					const float gmy = dL_dG * dG_ddely * ddely_dy;
 
 					const float dL_dmin_value = dL_dG * G * -0.5f;
-					const double AA = g.AA, BB = g.BB;
-					double dL_dA = dL_dmin_value * (BB / AA) * (BB / AA) / 4.f;
-					double dL_dB = dL_dmin_value * -BB / (2 * AA);
-					const double dL_dC = dL_dmin_value * 1.0f;
-					dL_dA += dL_dt * BB / (2 * AA * AA);
-					dL_dB += dL_dt * -1.f / (2 * AA);
+					const double ba = -u;                          // BB / AA
+					const double half_inv_AA = 0.5 * rcp_refined(g.AA);
+					double dL_dA = (double)dL_dmin_value * ba * ba * 0.25;
+					double dL_dB = (double)dL_dmin_value * ba * -0.5;
+					const double dL_dC = dL_dmin_value;
+					dL_dA += (double)dL_dt * ba * half_inv_AA;
+					dL_dB -= (double)dL_dt * half_inv_AA;
 					dL_dn[0] += dL_dA * rx;
 					dL_dn[1] += dL_dA * ry;
 					dL_dn[2] += dL_dA;
