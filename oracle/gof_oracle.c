@@ -9,6 +9,7 @@
  *   oracle_binning             RAST/cuda_rasterizer/rasterizer_impl.cu:35-50,70-111,149-171,332-373
  *   oracle_render_forward      RAST/cuda_rasterizer/forward.cu:409-612
  *   oracle_render_backward     RAST/cuda_rasterizer/backward.cu:634-955
+ *   oracle_integrate           RAST/cuda_rasterizer/forward.cu:722-766,803-1218, rasterizer_impl.cu:113-144,530-792
  *   oracle_preprocess_backward RAST/cuda_rasterizer/backward.cu:20-139,381-631
  *
  * Pinning: checked against tests/golden/*.npz, which hold the outputs of the UNMODIFIED reference
@@ -421,6 +422,222 @@ void oracle_render_forward(int W, int H, float tan_fovx, float tan_fovy, const u
 				out_color[8 * N + pix] = (float)((double)distortion / ((double)((1 - T) * (1 - T)) + 1e-7));
 			}
 	}
+}
+
+/* ------------------------------------------------------------------ point integration -- */
+/* Rasterizer::integrate (rasterizer_impl.cu:530-792): preprocessPointsCUDA (forward.cu:722-766), createWithKeys
+ * (rasterizer_impl.cu:113-144) + stable sort by (tile, depth), integrateCUDA (forward.cu:803-1218).
+ * The per-ray float32 quadric uses the roundings of the reference's sm_100a build (tools/sass_symexec.py; the
+ * fused/unfused pattern differs per ray) restated with fmaf, as eval_pair does for the blend.
+ * Control flow follows the kernel, including its 256-points-per-batch re-scan (forward.cu:1029-1206): a tile
+ * iterates while any of its pixels overflowed the batch, and pixels that did not overflow re-examine the tile's
+ * LAST point in every further round (point_counter_last = point_counter - 1), which only affects the
+ * "number of projected points" channel 8.
+ * Inputs: the Gaussian state of oracle_preprocess + oracle_binning.  Outputs: out_color[9,H,W] (zero-initialised
+ * by the caller, as the glue does), final_T[N], n_contrib[N], out_alpha[PN] (initialised to 1), out_rgb[PN,3]. */
+#define MAX_CONTRIBUTED 1024   /* MAX_NUM_CONTRIBUTORS * 4 */
+#define MAX_PROJECTED 256
+
+typedef struct { float AA, BB, CC; } rayquad;
+static rayquad ray_quadric(const float* v, float rx, float ry, int variant)
+{
+	float n0, n1, n2, bb;
+	if (variant == 0) {
+		n0 = v[2] + fmaf(rx, v[0], ry * v[1]);
+		n1 = v[4] + fmaf(rx, v[1], ry * v[3]);
+		n2 = v[5] + fmaf(ry, v[4], rx * v[2]);
+		bb = v[8] + fmaf(rx, v[6], ry * v[7]);
+	} else {
+		n0 = v[2] + (rx * v[0] + ry * v[1]);
+		n1 = (variant == 1) ? v[4] + fmaf(rx, v[1], ry * v[3]) : v[4] + (rx * v[1] + ry * v[3]);
+		n2 = v[5] + fmaf(rx, v[2], ry * v[4]);
+		bb = v[8] + (rx * v[6] + ry * v[7]);
+	}
+	rayquad q;
+	q.AA = n2 + fmaf(rx, n0, ry * n1);
+	q.BB = bb + bb;
+	q.CC = v[9];
+	return q;
+}
+
+int oracle_integrate(int P, int PN, int W, int H, float tan_fovx, float tan_fovy, const float* viewmatrix,
+                     const float* points3D, const uint32_t* ranges, const uint32_t* point_list, const float* v2g,
+                     const float* conic_opacity, const float* features, const float* bg, float* out_color,
+                     float* final_T, uint32_t* n_contrib, float* out_alpha, float* out_rgb)
+{
+	(void)P;
+	const float focal_y = H / (2.0f * tan_fovy);
+	const float focal_x = W / (2.0f * tan_fovx);
+	const int gx = (W + BLOCK_X - 1) / BLOCK_X, gy = (H + BLOCK_Y - 1) / BLOCK_Y;
+	const int T = gx * gy;
+	const size_t N = (size_t)W * H;
+	/* ---- points: project, bin by tile, stable sort by (tile, depth) ---- */
+	float* p2d = (float*)malloc(sizeof(float) * 2 * (size_t)(PN > 0 ? PN : 1));
+	float* pdepth = (float*)malloc(sizeof(float) * (size_t)(PN > 0 ? PN : 1));
+	kv_t* kv = (kv_t*)malloc(sizeof(kv_t) * (size_t)(PN > 0 ? PN : 1));
+	kv_t* tmp = (kv_t*)malloc(sizeof(kv_t) * (size_t)(PN > 0 ? PN : 1));
+	uint32_t* pranges = (uint32_t*)calloc((size_t)2 * T, sizeof(uint32_t));
+	size_t np = 0;
+	const float* vm = viewmatrix;
+	for (int i = 0; i < PN; i++) {
+		const float x = points3D[3 * i], y = points3D[3 * i + 1], z = points3D[3 * i + 2];
+		const float vx = vm[0] * x + vm[4] * y + vm[8] * z + vm[12];
+		const float vy = vm[1] * x + vm[5] * y + vm[9] * z + vm[13];
+		const float vz = vm[2] * x + vm[6] * y + vm[10] * z + vm[14];
+		if (vz <= 0.2f) continue;
+		const float px = (float)(focal_x * vx / (vz + 0.0000001f) + W / 2.);
+		const float py = (float)(focal_y * vy / (vz + 0.0000001f) + H / 2.);
+		if (px < 0 || px >= W || py < 0 || py >= H) continue;
+		p2d[2 * i] = px; p2d[2 * i + 1] = py; pdepth[i] = vz;
+		const int tx = imin(gx - 1, imax(0, (int)(px / BLOCK_X))), ty = imin(gy - 1, imax(0, (int)(py / BLOCK_Y)));
+		uint32_t dbits;
+		memcpy(&dbits, &vz, 4);
+		kv[np].key = ((uint64_t)(uint32_t)(ty * gx + tx) << 32) | dbits;
+		kv[np].val = (uint32_t)i;
+		np++;
+	}
+	radix_sort_pairs(kv, tmp, np, 64);
+	for (size_t i = 0; i < np; i++) {
+		const uint32_t t = (uint32_t)(kv[i].key >> 32);
+		if (i == 0 || (uint32_t)(kv[i - 1].key >> 32) != t) pranges[2 * t] = (uint32_t)i;
+		pranges[2 * t + 1] = (uint32_t)i + 1;
+	}
+#pragma omp parallel for schedule(dynamic, 1)
+	for (int tile = 0; tile < T; tile++) {
+		const int tx = tile % gx, ty = tile / gx;
+		const uint32_t r0 = ranges[2 * tile], r1 = ranges[2 * tile + 1];
+		const uint32_t p0 = pranges[2 * tile], p1 = pranges[2 * tile + 1];
+		/* per-pixel state of the tile */
+		uint16_t* contributed = (uint16_t*)malloc(sizeof(uint16_t) * MAX_CONTRIBUTED * BLOCK_X * BLOCK_Y);
+		uint32_t ncontrib[BLOCK_X * BLOCK_Y], lastc[BLOCK_X * BLOCK_Y], counter_last[BLOCK_X * BLOCK_Y];
+		int total_proj[BLOCK_X * BLOCK_Y], pdone[BLOCK_X * BLOCK_Y];
+		float pix_rgb[BLOCK_X * BLOCK_Y][3];
+		/* ---- phase 1: five rays per pixel ---- */
+		for (int l = 0; l < BLOCK_X * BLOCK_Y; l++) {
+			const int lx = l % BLOCK_X, ly = l / BLOCK_X;
+			const int px = tx * BLOCK_X + lx, py = ty * BLOCK_Y + ly;
+			ncontrib[l] = 0; lastc[l] = 0; counter_last[l] = 0; total_proj[l] = 0;
+			pdone[l] = !(px < W && py < H);
+			if (pdone[l]) continue;
+			const size_t pix = (size_t)W * py + px;
+			const float pfx = (float)px + 0.5f, pfy = (float)py + 0.5f;
+			static const float offx[5] = { 0.0f, -0.5f, 0.5f, -0.5f, 0.5f }, offy[5] = { 0.0f, -0.5f, -0.5f, 0.5f, 0.5f };
+			static const int variant[5] = { 0, 1, 2, 1, 2 };
+			float rxs[5], rys[5], Ts[5] = { 1, 1, 1, 1, 1 };
+			for (int k = 0; k < 5; k++) {
+				rxs[k] = (float)(((double)(pfx + offx[k]) - W / 2.) / (double)focal_x);
+				rys[k] = (float)(((double)(pfy + offy[k]) - H / 2.) / (double)focal_y);
+			}
+			float C0 = 0, C1 = 0, C2 = 0, Cdepth = 0, Calpha = 0;
+			uint32_t contributor = 0;
+			int done = 0;
+			for (uint32_t kk = r0; kk < r1 && !done; kk++) {
+				contributor++;
+				const uint32_t id = point_list[kk];
+				const float* v = v2g + 10 * (size_t)id;
+				const float w = conic_opacity[4 * (size_t)id + 3];
+				int used = 0;
+				for (int k = 0; k < 5; k++) {
+					const rayquad q = ray_quadric(v, rxs[k], rys[k], variant[k]);
+					const float t = -q.BB / (2 * q.AA);
+					if ((double)t <= NEAR_PLANE) continue;
+					const double min_value = fma((double)(-q.BB / q.AA), (double)q.BB * 0.25, (double)q.CC);
+					float power = (float)(min_value * -0.5);
+					if (power > 0.0f) power = 0.0f;
+					const float alpha = fminf(0.99f, w * expf(power));
+					if (alpha < 1.0f / 255.0f) continue;
+					const float test_T = Ts[k] * (1 - alpha);
+					if (test_T < 0.0001f) continue;
+					if (k == 0) {
+						C0 = fmaf(Ts[0], alpha * features[3 * (size_t)id + 0], C0);
+						C1 = fmaf(Ts[0], alpha * features[3 * (size_t)id + 1], C1);
+						C2 = fmaf(Ts[0], alpha * features[3 * (size_t)id + 2], C2);
+					}
+					if (t > Cdepth) Cdepth = t;
+					if (k == 0) Calpha = fmaf(Ts[0], alpha, Calpha);
+					Ts[k] = test_T;
+					used = 1;
+				}
+				if (used) {
+					lastc[l] = contributor;
+					contributed[(size_t)l * MAX_CONTRIBUTED + ncontrib[l]] = (uint16_t)contributor;
+					ncontrib[l]++;
+					if (ncontrib[l] >= MAX_CONTRIBUTED) done = 1;
+				}
+			}
+			final_T[pix] = Ts[0];
+			n_contrib[pix] = lastc[l];
+			pix_rgb[l][0] = C0 + Ts[0] * bg[0]; pix_rgb[l][1] = C1 + Ts[0] * bg[1]; pix_rgb[l][2] = C2 + Ts[0] * bg[2];
+			for (int ch = 0; ch < 3; ch++) out_color[ch * N + pix] = pix_rgb[l][ch];
+			out_color[6 * N + pix] = Cdepth;
+			out_color[7 * N + pix] = Calpha;
+		}
+		/* ---- phase 2: rounds of at most 256 projected points per pixel, block-wide loop ---- */
+		for (;;) {
+			int all_done = 1;
+			for (int l = 0; l < BLOCK_X * BLOCK_Y; l++) all_done &= pdone[l];
+			if (all_done) break;
+			for (int l = 0; l < BLOCK_X * BLOCK_Y; l++) {
+				const int lx = l % BLOCK_X, ly = l / BLOCK_X;
+				const int px = tx * BLOCK_X + lx, py = ty * BLOCK_Y + ly;
+				if (!(px < W && py < H)) continue;
+				const float pfx = (float)px + 0.5f, pfy = (float)py + 0.5f;
+				int ids[MAX_PROJECTED], nproj = 0, exceeded = 0;
+				float xs[MAX_PROJECTED], ys[MAX_PROJECTED], ds[MAX_PROJECTED];
+				uint32_t counter = 0;
+				for (uint32_t kk = p0; kk < p1; kk++) {
+					counter++;
+					if (counter <= counter_last[l]) continue;
+					const uint32_t pid = kv[kk].val;
+					const float x = p2d[2 * pid], y = p2d[2 * pid + 1];
+					if (((double)x >= (double)pfx - 0.5) && ((double)x < (double)pfx + 0.5) && ((double)y >= (double)pfy - 0.5) && ((double)y < (double)pfy + 0.5)) {
+						if (nproj >= MAX_PROJECTED) { exceeded = 1; break; }
+						ids[nproj] = (int)pid; xs[nproj] = x; ys[nproj] = y; ds[nproj] = pdepth[pid]; nproj++;
+					}
+				}
+				counter_last[l] = counter - 1;        /* uint32 wrap when the tile has no points, as in the kernel */
+				pdone[l] = !exceeded;
+				total_proj[l] += nproj;
+				float acc[MAX_PROJECTED], Tp[MAX_PROJECTED];
+				for (int k = 0; k < nproj; k++) { acc[k] = 0; Tp[k] = 1; }
+				uint32_t iterated = 0;
+				uint32_t second = 0;
+				for (uint32_t kk = r0; kk < r1; kk++) {
+					iterated++;
+					if (iterated > lastc[l]) break;
+					if (second >= ncontrib[l] || iterated != (uint32_t)contributed[(size_t)l * MAX_CONTRIBUTED + second]) continue;
+					second++;
+					const uint32_t id = point_list[kk];
+					const float* v = v2g + 10 * (size_t)id;
+					const float w = conic_opacity[4 * (size_t)id + 3];
+					for (int k = 0; k < nproj; k++) {
+						const float rx = (float)(((double)xs[k] - W / 2.) / (double)focal_x);
+						const float ry = (float)(((double)ys[k] - H / 2.) / (double)focal_y);
+						const rayquad q = ray_quadric(v, rx, ry, 0);
+						float t = -q.BB / (2 * q.AA);
+						if (t > ds[k]) t = ds[k];
+						const float power = (q.CC + fmaf(q.BB, t, t * (q.AA * t))) * -0.5f;
+						const float alpha = fminf(0.99f, w * expf(power));
+						if (alpha < 1.0f / 255.0f) continue;
+						acc[k] = fmaf(alpha, Tp[k], acc[k]);
+						Tp[k] = Tp[k] * (1 - alpha);
+					}
+				}
+				for (int k = 0; k < nproj; k++) {
+					out_alpha[ids[k]] = acc[k];
+					for (int ch = 0; ch < 3; ch++) out_rgb[3 * (size_t)ids[k] + ch] = pix_rgb[l][ch];
+				}
+			}
+		}
+		for (int l = 0; l < BLOCK_X * BLOCK_Y; l++) {
+			const int lx = l % BLOCK_X, ly = l / BLOCK_X;
+			const int px = tx * BLOCK_X + lx, py = ty * BLOCK_Y + ly;
+			if (px < W && py < H) out_color[8 * N + (size_t)W * py + px] = (float)total_proj[l];
+		}
+		free(contributed);
+	}
+	free(p2d); free(pdepth); free(kv); free(tmp); free(pranges);
+	return (int)np;
 }
 
 /* ------------------------------------------------------------------ backward blend ---- */

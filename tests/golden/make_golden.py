@@ -22,6 +22,10 @@ import cases  # noqa: E402
 import refgpu  # noqa: E402
 
 
+# golden cases that also carry the outputs of Rasterizer::integrate: name -> number of query points
+INTEGRATE_CASES = {"unit_p1200_120x88_sh3": 4000, "f3d_s32_r96_colors_ks": 3000}
+
+
 def main(out_dir):
     os.makedirs(out_dir, exist_ok=True)
     for name, build in cases.GOLDEN_CASES.items():
@@ -39,6 +43,18 @@ def main(out_dir):
             blob["fwd_" + k] = v.cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
         for k, v in bwd.items():
             blob["bwd_" + k] = v.cpu().numpy()
+        if name in INTEGRATE_CASES:
+            # point integration (Rasterizer::integrate) on seeded query points around the Gaussians
+            g = torch.Generator().manual_seed(11)
+            P = c_cpu["means3D"].shape[0]
+            idx = torch.randint(0, P, (INTEGRATE_CASES[name],), generator=g)
+            pts = c_cpu["means3D"][idx] + 2.0 * c_cpu["scales"][idx].max(dim=1, keepdim=True).values * \
+                torch.randn(len(idx), 3, generator=g)
+            pts[:20] += 50.0
+            integ = refgpu.ref_integrate(c, pts.to("cuda"))
+            blob["in_points3D"] = pts.numpy()
+            for k in ("out_color", "alpha_integrated", "color_integrated"):
+                blob["int_" + k] = integ[k].cpu().numpy()
         path = os.path.join(out_dir, name + ".npz")
         np.savez_compressed(path, **blob)
         print(name, "R =", fwd["num_rendered"], "visible =", int((fwd["radii"] > 0).sum()),

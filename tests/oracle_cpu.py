@@ -131,6 +131,25 @@ def preprocess_backward(c, radii, clamped, dL_dv2g, dL_dcolor, f64: bool = False
     return out
 
 
+def integrate(c: dict, points3D, ranges, point_list, v2g, conic_opacity, features) -> dict:
+    """Rasterizer::integrate on the CPU (oracle_integrate): state arrays as produced by preprocess() + binning()."""
+    W, H = int(c["W"]), int(c["H"])
+    N = W * H
+    pts = _f(points3D)
+    PN = pts.shape[0]
+    out = {"out_color": np.zeros((9, H, W), np.float32), "final_T": np.zeros(N, np.float32),
+           "n_contrib": np.zeros(N, np.uint32), "alpha_integrated": np.ones(PN, np.float32),
+           "color_integrated": np.zeros((PN, 3), np.float32)}
+    keep = [_f(c["viewmatrix"]), pts, np.ascontiguousarray(ranges, np.uint32), np.ascontiguousarray(point_list, np.uint32),
+            _f(v2g), _f(conic_opacity), _f(features), _f(c["bg"])]
+    L = lib()
+    L.oracle_integrate.restype = c_int
+    L.oracle_integrate(c_int(v2g.shape[0]), c_int(PN), c_int(W), c_int(H), c_float(c["tanfovx"]), c_float(c["tanfovy"]),
+                       *[_p(k) for k in keep], _p(out["out_color"]), _p(out["final_T"]), _p(out["n_contrib"]),
+                       _p(out["alpha_integrated"]), _p(out["color_integrated"]))
+    return out
+
+
 def forward_all(c: dict) -> dict:
     """Whole forward pipeline on the CPU (the cpu_baseline unit of work)."""
     pre = preprocess(c)

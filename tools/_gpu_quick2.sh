@@ -1,1 +1,1 @@
-timeout 300 python tools/diag_bwd.py f3d_s256_r256_view2 2>&1 | grep -v worst | head -30
+python tests/golden/make_golden.py gpurun_out/golden 2>&1 | tail -5
