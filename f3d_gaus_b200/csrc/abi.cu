@@ -5,7 +5,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 namespace gof {
@@ -27,6 +29,8 @@ struct GofContext {
 	int32_t* pinned = nullptr;      // host mailbox for num_rendered (callback mode)
 	float* gacc = nullptr;          // backward gradient accumulator, grown on demand
 	size_t gacc_floats = 0;
+	int64_t spec_capacity = 0;      // callback mode: binning capacity to allocate speculatively (1.25 x the last R)
+	cudaEvent_t handoff = nullptr;  // completion of the mailbox copy
 	// optional per-stage CUDA-event timing (gof_profile_*): one event per stage boundary
 	bool profiling = false;
 	std::vector<cudaEvent_t> pool;          // reusable events
@@ -75,6 +79,7 @@ void gof_context_destroy(GofContext* c)
 	if (!c) return;
 	if (c->pinned) cudaFreeHost(c->pinned);
 	if (c->gacc) cudaFree(c->gacc);
+	if (c->handoff) cudaEventDestroy(c->handoff);
 	for (cudaEvent_t e : c->pool) cudaEventDestroy(e);
 	for (int k = 0; k < 2; k++) for (auto& m : c->calls[k]) for (cudaEvent_t e : m) cudaEventDestroy(e);
 	delete c;
@@ -146,6 +151,25 @@ int gof_state_sizes(int32_t P, int32_t W, int32_t H, int64_t num_rendered,
 }
 
 static char* align_base(const void* p) { return reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(p))); }
+
+// The binning blob's layout depends on the capacity it was carved for, which is >= num_rendered when the blob
+// was allocated speculatively.  Forward remembers the capacity per blob address (the latest forward that used an
+// address wins, so allocator reuse is harmless); backward and the test accessor look it up and fall back to
+// num_rendered, the exact-size layout.
+static std::mutex g_cap_mu;
+static std::unordered_map<const void*, int64_t> g_bin_caps;
+static void remember_capacity(const void* blob, int64_t cap)
+{
+	std::lock_guard<std::mutex> lk(g_cap_mu);
+	if (g_bin_caps.size() > 8192) g_bin_caps.clear();
+	g_bin_caps[blob] = cap;
+}
+static int64_t lookup_capacity(const void* blob, int64_t num_rendered)
+{
+	std::lock_guard<std::mutex> lk(g_cap_mu);
+	auto it = g_bin_caps.find(blob);
+	return (it != g_bin_caps.end() && it->second >= num_rendered) ? it->second : num_rendered;
+}
 
 // Largest R whose binning layout fits in `bytes` (host arithmetic only).
 static int64_t binning_capacity(size_t bytes)
@@ -225,21 +249,60 @@ int gof_forward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* in
 		GOF_STAGE_CHECK(prm, s);
 		GOF_PROF_MARK(ctx, marks, s);
 		b = BinState::carve(align_base(binning), (size_t)capacity);
+		remember_capacity(binning, capacity);
 		if (num_rendered) for (int v = 0; v < V; v++) num_rendered[v] = -1;
 	} else {
 		if (!alloc) { set_error("gof_forward: neither a binning blob nor an allocation callback"); return GOF_EINVAL; }
-		if ((rc = launch_tile_scan(f, g, im, (int64_t)1 << 40, s)) != GOF_OK) return rc;
-		GOF_STAGE_CHECK(prm, s);
-		GOF_PROF_MARK(ctx, marks, s);
-		GOF_CUDA_CHECK(cudaMemcpyAsync(ctx->pinned, g.mailbox, (MAILBOX_HEAD + V) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-		GOF_CUDA_CHECK(cudaStreamSynchronize(s));
-		capacity = ctx->pinned[0];
-		if (num_rendered) for (int v = 0; v < V; v++) num_rendered[v] = ctx->pinned[MAILBOX_HEAD + v];
-		const size_t need = BinState::carve(nullptr, (size_t)capacity).total;
-		void* blob = alloc(alloc_user, need);
-		if (!blob) { set_error("gof_forward: binning allocation callback returned NULL for %zu bytes", need); return GOF_ENOMEM; }
-		if (binning_out) *binning_out = blob;
-		b = BinState::carve(align_base(blob), (size_t)capacity);
+		if (!ctx->handoff) GOF_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->handoff, cudaEventDisableTiming));
+		bool done = false;
+		if (ctx->spec_capacity > 0 && !prm->debug) {
+			// Speculative hand-off: allocate the binning blob for 1.25x the previous call's num_rendered and enqueue
+			// EVERYTHING before waiting for R, so the GPU never idles behind the host round trip of the reference's
+			// protocol (rasterizer_impl.cu:336-340).  The host still returns R as soon as the scan has finished.
+			capacity = ctx->spec_capacity;
+			const size_t need = BinState::carve(nullptr, (size_t)capacity).total;
+			void* blob = alloc(alloc_user, need);
+			if (!blob) { set_error("gof_forward: binning allocation callback returned NULL for %zu bytes", need); return GOF_ENOMEM; }
+			b = BinState::carve(align_base(blob), (size_t)capacity);
+			if ((rc = launch_tile_scan(f, g, im, capacity, s)) != GOF_OK) return rc;
+			GOF_PROF_MARK(ctx, marks, s);
+			GOF_CUDA_CHECK(cudaMemcpyAsync(ctx->pinned, g.mailbox, (MAILBOX_HEAD + V) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+			GOF_CUDA_CHECK(cudaEventRecord(ctx->handoff, s));
+			GOF_PROF_MARK(ctx, marks, s);
+			if ((rc = launch_binning(f, g, im, b, capacity, s)) != GOF_OK) return rc;
+			GOF_PROF_MARK(ctx, marks, s);
+			if ((rc = launch_render_fwd(*prm, f, g, im, b, in->background, bg_stride, out_color, s)) != GOF_OK) return rc;
+			GOF_PROF_MARK(ctx, marks, s);
+			GOF_CUDA_CHECK(cudaEventSynchronize(ctx->handoff));
+			const int64_t R = ctx->pinned[0];
+			ctx->spec_capacity = R + R / 4 + 4096;
+			if (!ctx->pinned[1]) {
+				if (num_rendered) for (int v = 0; v < V; v++) num_rendered[v] = ctx->pinned[MAILBOX_HEAD + v];
+				if (binning_out) *binning_out = blob;
+				remember_capacity(blob, capacity);
+				if (ctx->profiling) ctx->calls[0].push_back(std::move(marks));
+				return GOF_OK;
+			}
+			// the guess was too small: every kernel after the scan degenerated to empty lists; redo exactly
+			while (marks.size() > 2) { ctx->pool.push_back(marks.back()); marks.pop_back(); }
+			done = false;
+		}
+		if (!done) {
+			if ((rc = launch_tile_scan(f, g, im, (int64_t)1 << 40, s)) != GOF_OK) return rc;
+			GOF_STAGE_CHECK(prm, s);
+			GOF_PROF_MARK(ctx, marks, s);
+			GOF_CUDA_CHECK(cudaMemcpyAsync(ctx->pinned, g.mailbox, (MAILBOX_HEAD + V) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+			GOF_CUDA_CHECK(cudaStreamSynchronize(s));
+			capacity = ctx->pinned[0];
+			ctx->spec_capacity = capacity + capacity / 4 + 4096;
+			if (num_rendered) for (int v = 0; v < V; v++) num_rendered[v] = ctx->pinned[MAILBOX_HEAD + v];
+			const size_t need = BinState::carve(nullptr, (size_t)capacity).total;
+			void* blob = alloc(alloc_user, need);
+			if (!blob) { set_error("gof_forward: binning allocation callback returned NULL for %zu bytes", need); return GOF_ENOMEM; }
+			if (binning_out) *binning_out = blob;
+			b = BinState::carve(align_base(blob), (size_t)capacity);
+			remember_capacity(blob, capacity);
+		}
 	}
 
 	GOF_PROF_MARK(ctx, marks, s);   // after the num_rendered hand-off
@@ -350,7 +413,7 @@ int gof_backward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* i
 	BinState b{};
 	if (num_rendered > 0) {
 		if (!binning) { set_error("gof_backward: binning blob is NULL but num_rendered=%lld", (long long)num_rendered); return GOF_EINVAL; }
-		b = BinState::carve(align_base(binning), (size_t)num_rendered);
+		b = BinState::carve(align_base(binning), (size_t)lookup_capacity(binning, num_rendered));
 	}
 
 	const size_t need = (size_t)P * V * GACC_FLOATS;
@@ -431,7 +494,7 @@ int64_t gof_state_get_batch(const char* name, int32_t P, int32_t W, int32_t H, i
 	const size_t N = (size_t)W * H, n = (size_t)P * V, VT = (size_t)V * f.T;
 	GeomState g = GeomState::carve(align_base(geom), (size_t)P, (size_t)V);
 	ImgState im = ImgState::carve(align_base(img), N, (size_t)f.T, (size_t)V);
-	BinState b = BinState::carve(align_base(binning), (size_t)R);
+	BinState b = BinState::carve(align_base(binning), (size_t)lookup_capacity(binning, R));
 	const std::string nm(name);
 	const void* src = nullptr;
 	size_t bytes = 0;

@@ -142,8 +142,12 @@ int gof_state_sizes_batch(int32_t P, int32_t W, int32_t H, int32_t V, int64_t nu
  *                    host synchronisation happens (num_rendered is then read back lazily, see
  *                    gof_num_rendered); GOF_EOVERFLOW is reported by gof_num_rendered if it was
  *                    too small (outputs are then invalid).
- *                    If NULL, `alloc`(`alloc_user`, bytes) is called after one stream
- *                    synchronisation, exactly like the reference (rasterizer_impl.cu:336-340).
+ *                    If NULL, `alloc`(`alloc_user`, bytes) supplies the blob, as in the reference
+ *                    (rasterizer_impl.cu:336-340).  After the first call of a context the blob is
+ *                    requested speculatively (1.25x the previous num_rendered) and all kernels are
+ *                    enqueued BEFORE the host waits for R, so the GPU does not idle behind the round
+ *                    trip; if the guess was too small the callback is invoked a second time with the
+ *                    exact size.  The blob must be passed to gof_backward at the same address.
  *   out_color      : [9,H,W], radii: [P] int32.  Both fully written.
  *   num_rendered   : host pointer; receives R in the callback mode, -1 in the sync-free mode.
  *   binning_out    : host pointer; receives the binning blob actually used. */
