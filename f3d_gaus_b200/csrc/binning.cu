@@ -60,6 +60,7 @@ ImgState ImgState::carve(char* base, size_t N, size_t T, size_t V)
 	take(p, im.ranges, T * V);
 	take(p, im.tile_counts, T * V);
 	take(p, im.tile_cursor, T * V);
+	take(p, im.tile_order, T * V);
 	im.total = align_up((size_t)(p - base)) + ALIGN;
 	return im;
 }
@@ -85,10 +86,12 @@ constexpr int SCAN_THREADS = 1024;
 // mailbox = {R_total, overflow, max count, 0, R_view[0..V-1]}.
 __global__ void __launch_bounds__(SCAN_THREADS)
 tile_scan_kernel(int VT, int T, int V, const uint32_t* __restrict__ counts, uint2* __restrict__ ranges,
-                 uint32_t* __restrict__ cursor, int32_t* __restrict__ mailbox, long long capacity)
+                 uint32_t* __restrict__ cursor, int32_t* __restrict__ mailbox, long long capacity,
+                 uint32_t* __restrict__ order)
 {
 	__shared__ uint32_t s_part[SCAN_THREADS];
 	__shared__ uint32_t s_max[SCAN_THREADS / 32];
+	__shared__ uint32_t s_bucket[64], s_bmax;
 	const int tid = threadIdx.x;
 	const int per = (VT + SCAN_THREADS - 1) / SCAN_THREADS;
 	const int lo = min(VT, tid * per), hi = min(VT, lo + per);
@@ -115,6 +118,28 @@ tile_scan_kernel(int VT, int T, int V, const uint32_t* __restrict__ counts, uint
 		if ((i + 1) % T == 0) mailbox[MAILBOX_HEAD + i / T] = (int32_t)run;   // inclusive prefix; differenced below
 	}
 	__syncthreads();
+	if (order != nullptr) {
+		// Launch order of the blend CTAs: longest tile lists first (64 length classes, counting sort), so that the
+		// last wave of a launch is made of short tiles instead of whatever the row-major order leaves.
+		if (tid == 0) {
+			uint32_t m = 0;
+			for (int k = 0; k < SCAN_THREADS / 32; k++) m = max(m, s_max[k]);
+			s_bmax = m;
+		}
+		if (tid < 64) s_bucket[tid] = 0;
+		__syncthreads();
+		const uint32_t bm = s_bmax + 1;
+		for (int i = lo; i < hi; i++) atomicAdd(&s_bucket[63 - min(63u, (uint32_t)(((unsigned long long)counts[i] * 64) / bm))], 1u);
+		__syncthreads();
+		if (tid == 0) {
+			uint32_t run2 = 0;
+			for (int k = 0; k < 64; k++) { const uint32_t c = s_bucket[k]; s_bucket[k] = run2; run2 += c; }
+		}
+		__syncthreads();
+		for (int i = lo; i < hi; i++)
+			order[atomicAdd(&s_bucket[63 - min(63u, (uint32_t)(((unsigned long long)counts[i] * 64) / bm))], 1u)] = (uint32_t)i;
+		__syncthreads();
+	}
 	if (tid == 0) {
 		const uint32_t total = s_part[SCAN_THREADS - 1];
 		uint32_t m = 0;
@@ -393,14 +418,14 @@ extract_offsets_kernel(int P, const uint32_t* __restrict__ tiles_touched, uint32
 int launch_tile_scan(const Frame& f, const GeomState& g, const ImgState& im, int64_t capacity, cudaStream_t s)
 {
 	tile_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(f.V * f.T, f.T, f.V, im.tile_counts, im.ranges, im.tile_cursor, g.mailbox,
-	                                            (long long)capacity);
+	                                            (long long)capacity, im.tile_order);
 	GOF_CUDA_CHECK(cudaGetLastError());
 	return GOF_OK;
 }
 
 int launch_tile_scan_raw(int T, const uint32_t* counts, uint2* ranges, uint32_t* cursor, int32_t* mailbox, cudaStream_t s)
 {
-	tile_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(T, T, 1, counts, ranges, cursor, mailbox, (long long)1 << 40);
+	tile_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(T, T, 1, counts, ranges, cursor, mailbox, (long long)1 << 40, nullptr);
 	GOF_CUDA_CHECK(cudaGetLastError());
 	return GOF_OK;
 }

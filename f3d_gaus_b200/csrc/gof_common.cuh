@@ -63,6 +63,7 @@ struct ImgState {
 	uint2* ranges;          // [V*T]    (0,0) for untouched tiles, offsets into the whole batch's list
 	uint32_t* tile_counts;  // [V*T]
 	uint32_t* tile_cursor;  // [V*T]
+	uint32_t* tile_order;   // [V*T]    tiles by decreasing list length (launch order of the blend CTAs)
 	size_t total;
 	static ImgState carve(char* base, size_t N, size_t T, size_t V);
 };

@@ -52,8 +52,8 @@ __device__ __forceinline__ double rcp_refined(float x)
 }
 
 __global__ void __launch_bounds__(BWD_THREADS, GOF_BWD_MIN_CTAS)
-render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ slab, const uint32_t* __restrict__ point_list,
-                  int P, int W, int H,
+render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int tiles_per_view, int tiles_x,
+                  const float* __restrict__ slab, const uint32_t* __restrict__ point_list, int P, int W, int H,
                   float focal_x, float focal_y, const float* __restrict__ bg_colors, int bg_stride,
                   const float2* __restrict__ means2D_all, const float4* __restrict__ conic_opacity_all,
                   const float* __restrict__ final_Ts_all, const uint32_t* __restrict__ n_contrib_all,
@@ -68,11 +68,15 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 
 	const int tid = threadIdx.x;
 	const int warp = tid >> 5, lane = tid & 31;
-	const int view = blockIdx.z;
+	// CTAs are launched longest-list-first: blockIdx.x -> (view, tile) through tile_order (render_fwd.cu)
+	const uint32_t gt = tile_order[blockIdx.x];
+	const int view = (int)(gt / (uint32_t)tiles_per_view);
+	const int tile = (int)(gt - (uint32_t)view * (uint32_t)tiles_per_view);
+	const int tile_y = tile / tiles_x, tile_x = tile - tile_y * tiles_x;
 	const bool consumer = warp < CONSUMER_WARPS;
 	const int lx = (warp & 1) * 8 + (lane & 7), ly = ((warp >> 1) & 3) * 4 + (lane >> 3);
-	const uint32_t px = blockIdx.x * TILE_X + lx;
-	const uint32_t py = blockIdx.y * TILE_Y + ly;
+	const uint32_t px = tile_x * TILE_X + lx;
+	const uint32_t py = tile_y * TILE_Y + ly;
 	const bool inside = consumer && px < (uint32_t)W && py < (uint32_t)H;
 	const uint32_t pix_id = W * py + px;
 	const size_t N = (size_t)W * H;
@@ -85,7 +89,7 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 	const float* dL_dpixels = dL_dpixels_all + (size_t)view * OUT_CH * N;
 	float* gacc = gacc_all + (size_t)view * P * GACC_FLOATS;
 
-	const uint2 range = ranges[((size_t)view * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x];
+	const uint2 range = ranges[gt];
 	const int n = (int)(range.y - range.x);
 	const float* tile_slab = slab + (size_t)range.x * SLAB_FLOATS;
 	const uint32_t* tile_ids = point_list + range.x;
@@ -287,9 +291,9 @@ int launch_render_bwd(const GofParams& prm, const Frame& f, const GeomState& g, 
                       const BinState& b, const float* background, int bg_stride, const float* dL_dpix, float* gacc,
                       cudaStream_t s)
 {
-	const dim3 grid(f.grid.x, f.grid.y, f.V);
+	const dim3 grid((unsigned)(f.T * f.V), 1, 1);
 	GOF_CUDA_CHECK(cudaFuncSetAttribute(render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
-	render_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, s>>>(im.ranges, b.slab, b.point_list, f.P, prm.W, prm.H, f.focal_x, f.focal_y, background, bg_stride,
+	render_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, s>>>(im.ranges, im.tile_order, f.T, (int)f.grid.x, b.slab, b.point_list, f.P, prm.W, prm.H, f.focal_x, f.focal_y, background, bg_stride,
 	                                                     g.means2D, g.conic_opacity, im.final_T, im.n_contrib, dL_dpix, gacc);
 	GOF_CUDA_CHECK(cudaGetLastError());
 	return GOF_OK;

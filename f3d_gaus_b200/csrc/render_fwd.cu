@@ -107,7 +107,8 @@ constexpr int REC_F4 = SLAB_FLOATS / 4;                // float4 per slab record
 
 template <bool EXACT>
 __global__ void __launch_bounds__(FWD_THREADS, GOF_FWD_MIN_CTAS)
-render_fwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ slab, int W, int H,
+render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int T, int tiles_x,
+                  const float* __restrict__ slab, int W, int H,
                   float focal_x, float focal_y, const float* __restrict__ bg_colors, int bg_stride,
                   float* __restrict__ final_T_all, uint32_t* __restrict__ n_contrib_all, float* __restrict__ out_color_all,
                   const int32_t* __restrict__ mailbox, const uint8_t* __restrict__ block_mask)
@@ -119,10 +120,14 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 
 	const int tid = threadIdx.x;
 	const int warp = tid >> 5, lane = tid & 31;
-	const int view = blockIdx.z;
+	// CTAs are launched longest-list-first: blockIdx.x -> (view, tile) through tile_order
+	const uint32_t gt = tile_order[blockIdx.x];
+	const int view = (int)(gt / (uint32_t)T);
+	const int tile = (int)(gt - (uint32_t)view * (uint32_t)T);
+	const int tile_y = tile / tiles_x, tile_x = tile - tile_y * tiles_x;
 	const size_t N = (size_t)W * H;
 
-	const uint2 range = ranges[((size_t)view * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x];
+	const uint2 range = ranges[gt];
 	// sync-free mode: if the binning blob was too small nothing was binned -- blend empty lists (the
 	// caller sees the overflow flag in the mailbox and re-runs the batch with a larger blob)
 	const int n = mailbox[1] ? 0 : (int)(range.y - range.x);
@@ -153,8 +158,8 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 
 	// -------------------- consumer warps: 8x4 pixel block each --------------------------------
 	const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);   // tile-local pixel
-	const uint32_t px = blockIdx.x * TILE_X + lx;
-	const uint32_t py = blockIdx.y * TILE_Y + ly;
+	const uint32_t px = tile_x * TILE_X + lx;
+	const uint32_t py = tile_y * TILE_Y + ly;
 	const bool inside = px < (uint32_t)W && py < (uint32_t)H;
 	const uint32_t pix_id = W * py + px;
 	const float rx = pixel_ray(px, W, focal_x);
@@ -279,16 +284,16 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const float* __restrict__ sl
 int launch_render_fwd(const GofParams& prm, const Frame& f, const GeomState& g, const ImgState& im, const BinState& b,
                       const float* background, int bg_stride, float* out_color, cudaStream_t s)
 {
-	const dim3 grid(f.grid.x, f.grid.y, f.V);
+	const dim3 grid((unsigned)(f.T * f.V), 1, 1);
 	const size_t smem = (size_t)STAGES * CHUNK * SLAB_BYTES + 2 * STAGES * sizeof(uint64_t);
 	// per device and per function; cheap enough to set on every launch (one process may drive several GPUs)
 	GOF_CUDA_CHECK(cudaFuncSetAttribute(render_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	GOF_CUDA_CHECK(cudaFuncSetAttribute(render_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	if (prm.flags & GOF_FLAG_EXACT_BLEND)
-		render_fwd_kernel<true><<<grid, FWD_THREADS, smem, s>>>(im.ranges, b.slab, prm.W, prm.H, f.focal_x, f.focal_y,
+		render_fwd_kernel<true><<<grid, FWD_THREADS, smem, s>>>(im.ranges, im.tile_order, f.T, (int)f.grid.x, b.slab, prm.W, prm.H, f.focal_x, f.focal_y,
 		                                                     background, bg_stride, im.final_T, im.n_contrib, out_color, g.mailbox, b.block_mask);
 	else
-		render_fwd_kernel<false><<<grid, FWD_THREADS, smem, s>>>(im.ranges, b.slab, prm.W, prm.H, f.focal_x, f.focal_y,
+		render_fwd_kernel<false><<<grid, FWD_THREADS, smem, s>>>(im.ranges, im.tile_order, f.T, (int)f.grid.x, b.slab, prm.W, prm.H, f.focal_x, f.focal_y,
 		                                                      background, bg_stride, im.final_T, im.n_contrib, out_color, g.mailbox, b.block_mask);
 	GOF_CUDA_CHECK(cudaGetLastError());
 	return GOF_OK;
