@@ -315,11 +315,12 @@ __global__ void __launch_bounds__(SORT_THREADS, 3)
 tile_sort_gather_kernel(int P, int T, dim3 grid, int W, int H, float focal_x, float focal_y, float ray_pad,
                         const uint2* __restrict__ ranges, uint64_t* __restrict__ entries,
                         const float* __restrict__ rec_all, uint32_t* __restrict__ point_list,
-                        float* __restrict__ slab, uint8_t* __restrict__ block_mask, const int32_t* __restrict__ mailbox)
+                        float* __restrict__ slab, uint8_t* __restrict__ block_mask, const int32_t* __restrict__ mailbox,
+                        const uint32_t* __restrict__ tile_order)
 {
 	__shared__ uint64_t s_e[SORT_CAP];
 	if (mailbox[1]) return;
-	const int gt = blockIdx.x;            // global tile index: view * T + tile
+	const int gt = (int)tile_order[blockIdx.x];   // global tile index (view * T + tile), largest buckets first
 	const uint2 range = ranges[gt];
 	const int n = (int)(range.y - range.x);
 	if (n <= 0) return;
@@ -439,7 +440,7 @@ int launch_binning(const Frame& f, const GeomState& g, const ImgState& im, const
 	                                      g.mailbox);
 	GOF_CUDA_CHECK(cudaGetLastError());
 	tile_sort_gather_kernel<<<f.V * f.T, SORT_THREADS, 0, s>>>(f.P, f.T, f.grid, f.W, f.H, f.focal_x, f.focal_y, ray_pad, im.ranges,
-	                                                           b.entries, g.rec, b.point_list, b.slab, b.block_mask, g.mailbox);
+	                                                           b.entries, g.rec, b.point_list, b.slab, b.block_mask, g.mailbox, im.tile_order);
 	GOF_CUDA_CHECK(cudaGetLastError());
 	return GOF_OK;
 }
