@@ -226,7 +226,10 @@ class OursArm:
         (gaussian_renderer.HostFrameSink), D2H of rgb/depth/alpha into pinned host memory."""
         from f3d_gaus_b200.gaussian_renderer import HostFrameSink
         if self.sink is None:
-            self.sink = HostFrameSink(VIEWS, RES, RES, self.device, chunks=1)   # measured: 2 x 4-view passes are slower (tools/e2e_breakdown.py)
+            # frames are stored into pinned host memory by the blend kernel itself (gof_set_frame_sink);
+            # GOF_BENCH_READBACK=dma selects the packed DMA copy instead (tools/e2e_breakdown.py compares them)
+            self.sink = HostFrameSink(VIEWS, RES, RES, self.device, chunks=1,
+                                      zero_copy=os.environ.get("GOF_BENCH_READBACK", "kernel") != "dma")
         for k in host_pc:
             dev_pc[k].copy_(host_pc[k], non_blocking=True)
         self.sink.render(dev_pc, 0, cams_dev[0], cams_dev[1], cams_dev[2], bg, cfg)
@@ -245,7 +248,8 @@ class OursArm:
             if self.peer:
                 self.gathered = self.peer.push(self.sink.last_raster, first_scene=int(os.environ.get("RANK", "0")))
             else:
-                self.gathered = sharding.gather_frames(self.sink.staging.unsqueeze(0), self.world)
+                r = self.sink.last_raster
+                self.gathered = sharding.gather_frames(sharding.pack_frames(r[None, :, 0:3], r[None, :, 6:7], r[None, :, 7:8]), self.world)
 
     def e2e_finish(self):
         return self.sink.finish()
@@ -505,8 +509,8 @@ def main():
         "config": {"workload": "nvs256: 65536 f3d-like Gaussians (SH deg 1) per GPU, 8 orbit views, 256x256, forward "
                                "(BASELINE configs[1])", "frames_per_step": VIEWS, "num_rendered_per_step": R_step,
                    "l2": "flushed (256 MB write) between timed steps",
-                   "api": ("value: gof_forward_batch (8 views per call, sync-free); e2e: HostFrameSink.render (render_views + D2H of "
-                           "rgb/depth/alpha) from pinned host buffers" if args.impl == "ours"
+                   "api": ("value: gof_forward_batch (8 views per call, sync-free); e2e: HostFrameSink.render from pinned host buffers (H2D of "
+                           "the Gaussians, render_views, rgb/depth/alpha stored to pinned host memory by the blend kernel)" if args.impl == "ours"
                            else "one Rasterizer::forward call per frame")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

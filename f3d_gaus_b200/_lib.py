@@ -22,7 +22,9 @@ def default_flags() -> int:
 
 GOF_OK = 0
 GOF_EINVAL, GOF_ECUDA, GOF_ENOMEM, GOF_EOVERFLOW = -1, -2, -3, -4
+SINK_CHW, SINK_HWC = 0, 1
 OUTPUT_CHANNELS = 9
+SINK_CHANNELS = 5
 
 
 class GofParams(Structure):
@@ -68,6 +70,7 @@ SIGNATURES = {
     "gof_integrate": (c_int32, [c_void_p, POINTER(GofParams), POINTER(GofInputs), c_int32, c_void_p, c_void_p, c_size_t,
                                 c_void_p, c_size_t, ALLOC_FN, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 POINTER(c_int32), c_void_p]),
+    "gof_set_frame_sink": (c_int32, [c_void_p, c_void_p, c_size_t, c_int32]),
     "gof_num_rendered": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, POINTER(c_int32)]),
     "gof_backward": (c_int32, [c_void_p, POINTER(GofParams), POINTER(GofInputs), c_int32, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_void_p, POINTER(GofGrads), c_void_p]),

@@ -31,6 +31,9 @@ struct GofContext {
 	size_t gacc_floats = 0;
 	int64_t spec_capacity = 0;      // callback mode: binning capacity to allocate speculatively (1.25 x the last R)
 	cudaEvent_t handoff = nullptr;  // completion of the mailbox copy
+	float* sink = nullptr;          // frame sink of the NEXT forward call (device-visible address), gof_set_frame_sink
+	size_t sink_bytes = 0;
+	int sink_layout = 0;
 	// optional per-stage CUDA-event timing (gof_profile_*): one event per stage boundary
 	bool profiling = false;
 	std::vector<cudaEvent_t> pool;          // reusable events
@@ -182,6 +185,26 @@ static int64_t binning_capacity(size_t bytes)
 	return lo;
 }
 
+int gof_set_frame_sink(GofContext* ctx, void* sink, size_t sink_bytes, int32_t layout)
+{
+	if (!ctx) { set_error("gof_set_frame_sink: ctx is NULL"); return GOF_EINVAL; }
+	ctx->sink = nullptr;
+	ctx->sink_bytes = 0;
+	if (!sink) return GOF_OK;
+	if (layout != GOF_SINK_CHW && layout != GOF_SINK_HWC) { set_error("gof_set_frame_sink: unknown layout %d", layout); return GOF_EINVAL; }
+	if ((uintptr_t)sink % 16 != 0) { set_error("gof_set_frame_sink: the sink must be 16-byte aligned"); return GOF_EINVAL; }
+	cudaPointerAttributes at;
+	GOF_CUDA_CHECK(cudaPointerGetAttributes(&at, sink));
+	if (at.type == cudaMemoryTypeUnregistered || at.devicePointer == nullptr) {
+		set_error("gof_set_frame_sink: %p is pageable host memory; the sink must be device memory or pinned (page-locked) host memory", sink);
+		return GOF_EINVAL;
+	}
+	ctx->sink = static_cast<float*>(at.devicePointer);   // pinned host memory: its address in the device's space
+	ctx->sink_bytes = sink_bytes;
+	ctx->sink_layout = layout;
+	return GOF_OK;
+}
+
 int gof_forward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* in, int32_t V, int32_t bg_stride,
                       void* geom, size_t geom_bytes, void* img, size_t img_bytes,
                       void* binning, size_t binning_bytes, GofAllocFn alloc, void* alloc_user,
@@ -189,6 +212,12 @@ int gof_forward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* in
                       int32_t* num_rendered, void** binning_out, gof_stream_t stream)
 {
 	if (!ctx || !prm || !in) { set_error("gof_forward: NULL argument"); return GOF_EINVAL; }
+	// one-shot frame sink (gof_set_frame_sink): consumed by this call whatever its outcome
+	float* const sink = ctx->sink;
+	const size_t sink_bytes = ctx->sink_bytes;
+	const int sink_hwc = ctx->sink_layout == GOF_SINK_HWC;
+	ctx->sink = nullptr;
+	ctx->sink_bytes = 0;
 	cudaStream_t s = (cudaStream_t)stream;
 	const int P = prm->P, W = prm->W, H = prm->H;
 	if (W <= 0 || H <= 0 || P < 0 || V <= 0) { set_error("gof_forward: bad sizes P=%d W=%d H=%d V=%d", P, W, H, V); return GOF_EINVAL; }
@@ -197,8 +226,13 @@ int gof_forward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* in
 	if (num_rendered) for (int v = 0; v < V; v++) num_rendered[v] = 0;
 	if (binning_out) *binning_out = binning;
 	const size_t N = (size_t)W * H;
+	if (sink && sink_bytes < (size_t)V * SINK_CH * N * sizeof(float)) {
+		set_error("gof_forward: frame sink too small (%zu < %zu)", sink_bytes, (size_t)V * SINK_CH * N * sizeof(float));
+		return GOF_ENOMEM;
+	}
 	if (P == 0) {   // rasterize_points.cu:85: nothing is launched, outputs stay zero
 		GOF_CUDA_CHECK(cudaMemsetAsync(out_color, 0, (size_t)V * N * OUT_CH * sizeof(float), s));
+		if (sink) GOF_CUDA_CHECK(cudaMemsetAsync(sink, 0, (size_t)V * SINK_CH * N * sizeof(float), s));
 		return GOF_OK;
 	}
 	if (!in->means3D || !in->opacities || !in->viewmatrix || !in->projmatrix || !in->campos || !in->background || !radii) {
@@ -271,7 +305,7 @@ int gof_forward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* in
 			GOF_PROF_MARK(ctx, marks, s);
 			if ((rc = launch_binning(f, g, im, b, capacity, s)) != GOF_OK) return rc;
 			GOF_PROF_MARK(ctx, marks, s);
-			if ((rc = launch_render_fwd(*prm, f, g, im, b, in->background, bg_stride, out_color, s)) != GOF_OK) return rc;
+			if ((rc = launch_render_fwd(*prm, f, g, im, b, in->background, bg_stride, out_color, sink, sink_hwc, s)) != GOF_OK) return rc;
 			GOF_PROF_MARK(ctx, marks, s);
 			GOF_CUDA_CHECK(cudaEventSynchronize(ctx->handoff));
 			const int64_t R = ctx->pinned[0];
@@ -309,7 +343,7 @@ int gof_forward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* in
 	if ((rc = launch_binning(f, g, im, b, capacity, s)) != GOF_OK) return rc;
 	GOF_STAGE_CHECK(prm, s);
 	GOF_PROF_MARK(ctx, marks, s);
-	if ((rc = launch_render_fwd(*prm, f, g, im, b, in->background, bg_stride, out_color, s)) != GOF_OK) return rc;
+	if ((rc = launch_render_fwd(*prm, f, g, im, b, in->background, bg_stride, out_color, sink, sink_hwc, s)) != GOF_OK) return rc;
 	GOF_STAGE_CHECK(prm, s);
 	GOF_PROF_MARK(ctx, marks, s);
 	if (ctx->profiling) ctx->calls[0].push_back(std::move(marks));

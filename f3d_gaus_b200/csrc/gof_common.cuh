@@ -17,6 +17,7 @@ constexpr int TILE_Y = 16;
 constexpr int TILE_PIX = TILE_X * TILE_Y;
 constexpr int OUT_CH = GOF_OUTPUT_CHANNELS;
 constexpr int CH_DEPTH = 6, CH_ALPHA = 7, CH_DIST = 8;
+constexpr int SINK_CH = GOF_SINK_CHANNELS;      // frame sink: rgb, median depth, alpha
 
 // Per-(view, Gaussian) "geometry record" written by the preprocess, 64 B:
 //  [0..5] Sigma_v (xx,xy,xz,yy,yz,zz)  [6..8] B  [9] C      (view2gaussian, forward.cu:268-277)
@@ -122,7 +123,7 @@ int launch_integrate(const GofParams& prm, const GofInputs& in, const Frame& f, 
                      float* out_alpha_integrated, float* out_color_integrated, cudaStream_t s);
 int launch_tile_scan_raw(int T, const uint32_t* counts, uint2* ranges, uint32_t* cursor, int32_t* mailbox, cudaStream_t s);
 int launch_render_fwd(const GofParams& prm, const Frame& f, const GeomState& g, const ImgState& im, const BinState& b,
-                      const float* background, int bg_stride, float* out_color, cudaStream_t s);
+                      const float* background, int bg_stride, float* out_color, float* sink, int sink_hwc, cudaStream_t s);
 int launch_render_bwd(const GofParams& prm, const Frame& f, const GeomState& g, const ImgState& im,
                       const BinState& b, const float* background, int bg_stride, const float* dL_dpix, float* gacc,
                       cudaStream_t s);

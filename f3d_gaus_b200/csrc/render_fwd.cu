@@ -105,18 +105,19 @@ constexpr int CONSUMER_WARPS = TILE_PIX / 32;          // 8
 constexpr int FWD_THREADS = TILE_PIX + 32;             // + 1 producer warp
 constexpr int REC_F4 = SLAB_FLOATS / 4;                // float4 per slab record (6)
 
-template <bool EXACT>
+template <bool EXACT, bool SINK>
 __global__ void __launch_bounds__(FWD_THREADS, GOF_FWD_MIN_CTAS)
 render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int T, int tiles_x,
                   const float* __restrict__ slab, int W, int H,
                   float focal_x, float focal_y, const float* __restrict__ bg_colors, int bg_stride,
                   float* __restrict__ final_T_all, uint32_t* __restrict__ n_contrib_all, float* __restrict__ out_color_all,
-                  const int32_t* __restrict__ mailbox, const uint8_t* __restrict__ block_mask)
+                  const int32_t* __restrict__ mailbox, const uint8_t* __restrict__ block_mask, float* __restrict__ sink_all, int sink_hwc)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	float4 (*s_rec)[CHUNK * REC_F4] = reinterpret_cast<float4 (*)[CHUNK * REC_F4]>(smem_raw);
 	uint64_t* s_full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * CHUNK * SLAB_BYTES);
 	uint64_t* s_empty = s_full + STAGES;
+	float* s_out = reinterpret_cast<float*>(s_empty + STAGES);      // [SINK_CH * 256] tile of the frame sink
 
 	const int tid = threadIdx.x;
 	const int warp = tid >> 5, lane = tid & 31;
@@ -277,24 +278,65 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 		for (int ch = 3; ch < 8; ch++) out_color[ch * N + pix_id] = st.C[ch];
 		out_color[CH_DIST * N + pix_id] = dnorm;
 	}
+	if constexpr (SINK) {
+		// Frame sink = rgb, median depth, alpha (what the render loops read back, visualize.py:304-306), usually
+		// pinned host memory mapped into the device address space: the stores are posted PCIe writes that drain
+		// while the other tiles still blend.  PCIe efficiency is set by the length of the contiguous runs, so the
+		// tile is transposed through shared memory and written as whole tile rows with 16-byte stores: 64-byte
+		// runs for [V,5,H,W], 320-byte runs for the channels-last layout [V,H,W,5].
+		float* sink = sink_all + (size_t)view * SINK_CH * N;
+		const bool whole = (W % 4 == 0) && (tile_x * TILE_X + TILE_X <= W) && (tile_y * TILE_Y + TILE_Y <= H);   // CTA-uniform
+		float v[SINK_CH];
+		{
+			const float* bg_color = bg_colors + (size_t)view * bg_stride;
+#pragma unroll
+			for (int ch = 0; ch < 3; ch++) v[ch] = __fmaf_rn(st.T, bg_color[ch], st.C[ch]);
+			v[3] = st.C[CH_DEPTH];
+			v[4] = st.C[CH_ALPHA];
+		}
+		if (!whole) {
+			if (inside) {
+#pragma unroll
+				for (int ch = 0; ch < SINK_CH; ch++) sink[sink_hwc ? (size_t)pix_id * SINK_CH + ch : (size_t)ch * N + pix_id] = v[ch];
+			}
+			return;
+		}
+		const int lp = ly * TILE_X + lx;
+#pragma unroll
+		for (int ch = 0; ch < SINK_CH; ch++) s_out[sink_hwc ? lp * SINK_CH + ch : ch * TILE_PIX + lp] = v[ch];
+		asm volatile("bar.sync 1, %0;" :: "n"(TILE_PIX) : "memory");    // the 8 consumer warps (the producer has left)
+		const size_t row0 = (size_t)(tile_y * TILE_Y) * W + (size_t)tile_x * TILE_X;   // first pixel of the tile
+		for (int i = tid; i < SINK_CH * TILE_PIX / 4; i += TILE_PIX) {
+			const float4 q = reinterpret_cast<const float4*>(s_out)[i];
+			size_t at;
+			if (sink_hwc) {
+				const int row = i / (TILE_X * SINK_CH / 4), c4 = i - row * (TILE_X * SINK_CH / 4);
+				at = (row0 + (size_t)row * W) * SINK_CH + (size_t)c4 * 4;
+			} else {
+				const int ch = i / (TILE_PIX / 4), r = i - ch * (TILE_PIX / 4), row = r / (TILE_X / 4), c4 = r - row * (TILE_X / 4);
+				at = (size_t)ch * N + row0 + (size_t)row * W + (size_t)c4 * 4;
+			}
+			*reinterpret_cast<float4*>(sink + at) = q;
+		}
+	}
 }
 
 }  // namespace
 
 int launch_render_fwd(const GofParams& prm, const Frame& f, const GeomState& g, const ImgState& im, const BinState& b,
-                      const float* background, int bg_stride, float* out_color, cudaStream_t s)
+                      const float* background, int bg_stride, float* out_color, float* sink, int sink_hwc, cudaStream_t s)
 {
 	const dim3 grid((unsigned)(f.T * f.V), 1, 1);
-	const size_t smem = (size_t)STAGES * CHUNK * SLAB_BYTES + 2 * STAGES * sizeof(uint64_t);
-	// per device and per function; cheap enough to set on every launch (one process may drive several GPUs)
-	GOF_CUDA_CHECK(cudaFuncSetAttribute(render_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	GOF_CUDA_CHECK(cudaFuncSetAttribute(render_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	if (prm.flags & GOF_FLAG_EXACT_BLEND)
-		render_fwd_kernel<true><<<grid, FWD_THREADS, smem, s>>>(im.ranges, im.tile_order, f.T, (int)f.grid.x, b.slab, prm.W, prm.H, f.focal_x, f.focal_y,
-		                                                     background, bg_stride, im.final_T, im.n_contrib, out_color, g.mailbox, b.block_mask);
-	else
-		render_fwd_kernel<false><<<grid, FWD_THREADS, smem, s>>>(im.ranges, im.tile_order, f.T, (int)f.grid.x, b.slab, prm.W, prm.H, f.focal_x, f.focal_y,
-		                                                      background, bg_stride, im.final_T, im.n_contrib, out_color, g.mailbox, b.block_mask);
+	const size_t smem = (size_t)STAGES * CHUNK * SLAB_BYTES + 2 * STAGES * sizeof(uint64_t) + (sink ? (size_t)SINK_CH * TILE_PIX * sizeof(float) : 0);
+	auto launch = [&](auto kernel) {
+		// per device and per function; cheap enough to set on every launch (one process may drive several GPUs)
+		if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return;
+		kernel<<<grid, FWD_THREADS, smem, s>>>(im.ranges, im.tile_order, f.T, (int)f.grid.x, b.slab, prm.W, prm.H, f.focal_x, f.focal_y,
+		                                       background, bg_stride, im.final_T, im.n_contrib, out_color, g.mailbox, b.block_mask, sink, sink_hwc);
+	};
+	const bool exact = (prm.flags & GOF_FLAG_EXACT_BLEND) != 0;
+	if (sink) { if (exact) launch(render_fwd_kernel<true, true>); else launch(render_fwd_kernel<false, true>); }
+	else      { if (exact) launch(render_fwd_kernel<true, false>); else launch(render_fwd_kernel<false, false>); }
 	GOF_CUDA_CHECK(cudaGetLastError());
 	return GOF_OK;
 }

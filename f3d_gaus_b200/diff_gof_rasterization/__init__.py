@@ -300,14 +300,16 @@ class BatchWorkspace:
 
 def rasterize_views(background, means3D, colors, opacity, scales, rotations, scale_modifier, viewmatrices, projmatrices,
                     tan_fovx, tan_fovy, kernel_size, image_height, image_width, sh, degree, campos, prefiltered=False,
-                    debug=False, workspace: BatchWorkspace | None = None, out_color=None):
+                    debug=False, workspace: BatchWorkspace | None = None, out_color=None, sink=None):
     """V views of one Gaussian set in ONE pass of the pipeline (gof_forward_batch).
 
     viewmatrices/projmatrices: [V,4,4] (or [V,1,4,4]), campos: [V,3]; background [3] or [V,3].
     Returns (num_rendered, color[V,9,H,W], radii[V,P], geom, binning, img).  Frame v is bit-identical
     to `_C.rasterize_gaussians` with camera v.  Without a workspace num_rendered is a list of ints and
     one host synchronisation happens (as in the reference); with one, it is None until
-    `workspace.finish()`."""
+    `workspace.finish()`.  `sink`: optional float32 [V,5,H,W] tensor (contiguous or channels_last) in device or PINNED
+    host memory that the blend kernel additionally fills with rgb / median depth / alpha (gof_set_frame_sink) -- with
+    pinned memory the frames reach the host while the kernel runs (valid once the stream has been synchronised)."""
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     if not means3D.is_cuda:
@@ -324,6 +326,8 @@ def rasterize_views(background, means3D, colors, opacity, scales, rotations, sca
             out_color = torch.empty((V, _lib.OUTPUT_CHANNELS, H, W), **f32)
         if P == 0:
             out_color.zero_()
+            if sink is not None:
+                sink.zero_()
             e = torch.empty(0, dtype=torch.uint8, device=device)
             return [0] * V, out_color, torch.zeros((V, 0), dtype=torch.int32, device=device), e, e.clone(), e.clone()
         radii = torch.empty((V, P), dtype=torch.int32, device=device)
@@ -339,6 +343,17 @@ def rasterize_views(background, means3D, colors, opacity, scales, rotations, sca
         Rv = (ctypes.c_int32 * V)()
         bin_out = ctypes.c_void_p()
         ctx = _lib.context(device.index)
+        if sink is not None:
+            if sink.dtype != torch.float32 or tuple(sink.shape) != (V, _lib.SINK_CHANNELS, H, W) \
+                    or not (sink.is_cuda or sink.is_pinned()):
+                raise RuntimeError(f"sink must be a float32 [{V},{_lib.SINK_CHANNELS},{H},{W}] tensor in device or pinned host memory")
+            if sink.is_contiguous():
+                layout = _lib.SINK_CHW
+            elif sink.is_contiguous(memory_format=torch.channels_last):
+                layout = _lib.SINK_HWC
+            else:
+                raise RuntimeError("sink must be contiguous (NCHW) or channels_last")
+            _lib.check(_lib.lib.gof_set_frame_sink(ctx, sink.data_ptr(), sink.numel() * 4, layout), "gof_set_frame_sink")
         if workspace is None:
             gsz, isz, bsz = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
             _lib.check(_lib.lib.gof_state_sizes_batch(P, W, H, V, 0, ctypes.byref(gsz), ctypes.byref(isz),

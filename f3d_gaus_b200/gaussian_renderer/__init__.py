@@ -184,7 +184,7 @@ def render_predicted_more_v2_gof_in(points3D, pc: dict, bs, world_view_transform
 
 def render_views(pc: dict, bs, world_view_transforms, full_proj_transforms, camera_centers, bg_color: torch.Tensor, cfg,
                  kernel_size=0.0, scaling_modifier=1.0, override_color=None, workspace: BatchWorkspace | None = None,
-                 epilogue: bool = True, out_color: torch.Tensor | None = None):
+                 epilogue: bool = True, out_color: torch.Tensor | None = None, sink: torch.Tensor | None = None):
     """All V views of scene `bs` in one pass of the pipeline: the batched form of the reference's
     `for th in range(num_frames): render_predicted_more_v2_gof(pc, bs, wvt[th:th+1], ...)` loops
     (visualize.py:293-306,387-402).  Inference only (no autograd graph).
@@ -194,7 +194,7 @@ def render_views(pc: dict, bs, world_view_transforms, full_proj_transforms, came
     (render[V,3,H,W], rendered_depth[V,1,H,W], rendered_alpha[V,1,H,W], distortion_map[V,1,H,W],
     radii[V,P], visibility_filter[V,P]; rendered_normal / depth_normal [V,3,H,W] when `epilogue`),
     plus `raster` = the full [V,9,H,W] rasterizer output.  Frame v is bit-identical to the per-view call.
-    With a `workspace` the call does not synchronise the host (see BatchWorkspace)."""
+    With a `workspace` the call does not synchronise the host (see BatchWorkspace).  `sink`: see `rasterize_views`."""
     xyz = pc["xyz"][bs]
     device = xyz.device
     fov = cfg['model']['fov']
@@ -211,7 +211,7 @@ def render_views(pc: dict, bs, world_view_transforms, full_proj_transforms, came
         R, raster, radii, _, _, _ = rasterize_views(
             bg_color, xyz, colors, pc["opacity"][bs], pc["scaling"][bs], pc["rotation"][bs], scaling_modifier,
             world_view_transforms, full_proj_transforms, tanfov, tanfov, kernel_size, H, W, shs,
-            cfg['model']['max_sh_degree'], camera_centers, workspace=workspace, out_color=out_color)
+            cfg['model']['max_sh_degree'], camera_centers, workspace=workspace, out_color=out_color, sink=sink)
         out = {"raster": raster, "render": raster[:, 0:3], "rendered_depth": raster[:, 6:7],
                "rendered_alpha": raster[:, 7:8], "distortion_map": raster[:, 8:9], "radii": radii,
                "visibility_filter": radii > 0, "num_rendered": R}
@@ -231,21 +231,31 @@ def render_views(pc: dict, bs, world_view_transforms, full_proj_transforms, came
 
 class HostFrameSink:
     """Return path of the render loops to HOST memory (the reference does `.cpu()` on rgb, depth and alpha of every
-    frame, visualize.py:304-306): the V views are rendered in `chunks` batched passes and each pass's
-    [v,5,H,W] (rgb, median depth, alpha) block is copied to pinned host memory on a side stream while the next
-    pass renders (at 8 views of 256x256 one pass is fastest -- tools/e2e_breakdown.py -- so chunks defaults to 1; long
-    orbits such as the reference's 128-view loop are the use case for more).  `finish()` waits for the copies and returns the per-view num_rendered (None => a binning blob
-    overflowed and was grown: call `render` again)."""
+    frame, visualize.py:304-306).  `host` is a pinned [V,5,H,W] buffer (rgb, median depth, alpha).
 
-    def __init__(self, V: int, H: int, W: int, device, chunks: int = 1):
+    zero_copy (default): the blend kernel itself stores the five channels into `host` (gof_set_frame_sink) -- posted
+    PCIe writes that drain while the remaining tiles blend, so the read-back adds little time after the kernel.
+    `host` is then channels_last in memory ([V,H,W,5] storage, the layout image writers want and the one that gives
+    320-byte PCIe bursts per tile row) unless channels_last=False.
+    Otherwise the V views are rendered in `chunks` batched passes and each pass's block is packed on the device and
+    copied by the DMA engine on a side stream while the next pass renders (tools/e2e_breakdown.py compares them).
+    `finish()` waits for the frames and returns the per-view num_rendered (None => a binning blob overflowed and was
+    grown: call `render` again)."""
+
+    def __init__(self, V: int, H: int, W: int, device, chunks: int = 1, zero_copy: bool = True,
+                 channels_last: bool = True):
         self.V, self.H, self.W, self.device = V, H, W, torch.device(device)
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.chunks = max(1, min(chunks, V))
         self.per = -(-V // self.chunks)
-        self.staging = torch.empty((V, 5, H, W), dtype=torch.float32, device=self.device)
-        self.host = torch.empty((V, 5, H, W), dtype=torch.float32).pin_memory()
-        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.zero_copy = bool(zero_copy)
+        if self.zero_copy and channels_last:
+            self.host = torch.empty((V, H, W, 5), dtype=torch.float32).pin_memory().permute(0, 3, 1, 2)
+        else:
+            self.host = torch.empty((V, 5, H, W), dtype=torch.float32).pin_memory()
+        self.staging = None if self.zero_copy else torch.empty((V, 5, H, W), dtype=torch.float32, device=self.device)
+        self.copy_stream = None if self.zero_copy else torch.cuda.Stream(device=self.device)
         self.workspaces = [BatchWorkspace(self.device) for _ in range(self.chunks)]
         self.done = torch.cuda.Event()
         self.last_raster = None
@@ -260,8 +270,10 @@ class HostFrameSink:
             if lo >= hi:
                 break
             o = render_views(pc, bs, wv[lo:hi], fp[lo:hi], cc[lo:hi], bg_color, cfg, workspace=self.workspaces[ci],
-                             epilogue=False, **kw)
+                             epilogue=False, sink=self.host[lo:hi] if self.zero_copy else None, **kw)
             self.last_raster = o["raster"]            # [v,9,H,W] of the last pass (the whole batch when chunks == 1)
+            if self.zero_copy:
+                continue
             st = self.staging[lo:hi]
             st[:, 0:3].copy_(o["render"])
             st[:, 3:4].copy_(o["rendered_depth"])
@@ -271,8 +283,11 @@ class HostFrameSink:
             self.copy_stream.wait_event(ready)
             with torch.cuda.stream(self.copy_stream):
                 self.host[lo:hi].copy_(st, non_blocking=True)
-        self.done.record(self.copy_stream)
-        main.wait_event(self.done)          # a later synchronisation of the main stream covers the copies
+        if self.zero_copy:
+            self.done.record(main)
+        else:
+            self.done.record(self.copy_stream)
+            main.wait_event(self.done)      # a later synchronisation of the main stream covers the copies
         return self.host
 
     def finish(self):

@@ -53,6 +53,9 @@ extern "C" {
 
 #define GOF_OUTPUT_CHANNELS 9   /* rgb(3) normal(3) depth alpha distortion: auxiliary.h:21-24 */
 #define GOF_MAX_VIEWS      64   /* views per gof_forward_batch call */
+#define GOF_SINK_CHANNELS   5   /* frame sink: rgb(3), median depth, alpha -- what visualize.py:304-306 reads back */
+#define GOF_SINK_CHW        0   /* sink layout [V,5,H,W] */
+#define GOF_SINK_HWC        1   /* sink layout [V,H,W,5] (channels last: 320-byte contiguous runs per tile row) */
 
 typedef struct GofContext GofContext;   /* per-device handle (scratch, pinned mailbox) */
 typedef void* gof_stream_t;             /* cudaStream_t */
@@ -182,6 +185,15 @@ int gof_integrate(GofContext* ctx, const GofParams* prm, const GofInputs* in, in
                   void* geom, size_t geom_bytes, void* img, size_t img_bytes, GofAllocFn alloc, void* alloc_user,
                   float* out_color, int32_t* radii, float* out_alpha_integrated, float* out_color_integrated,
                   int32_t* num_rendered, gof_stream_t stream);
+
+/* Frame sink for the NEXT gof_forward / gof_forward_batch call on `ctx` (one-shot: the call consumes it).
+ * The blend then ALSO stores rgb, median depth and alpha of every frame at `sink` (16-byte aligned, V*5*H*W
+ * floats; layout GOF_SINK_CHW = [V,5,H,W] or GOF_SINK_HWC = [V,H,W,5]) from inside the kernel, as whole tile rows.
+ * `sink` is device memory or pinned host memory (cudaHostAlloc / cudaHostRegister); with pinned host memory the
+ * frames arrive on the host as posted PCIe writes while other tiles still blend, i.e. the `.cpu()` of the render
+ * loops (visualize.py:304-306, 396-398) costs no time of its own; channels-last gives the longest PCIe bursts.
+ * The frames are complete when the work enqueued on the call's stream has finished.  NULL clears a pending sink. */
+int gof_set_frame_sink(GofContext* ctx, void* sink, size_t sink_bytes, int32_t layout);
 
 /* Sync-free mode: blocks on `stream` and returns the per-view R ([V]) of the last forward that used
  * `geom` (or GOF_EOVERFLOW if the binning blob was too small for it). */

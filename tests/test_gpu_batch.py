@@ -227,14 +227,18 @@ def test_batched_backward_equals_sum_of_per_view_backwards(kind):
         assert rel(g2[k], g1[k]) <= tol, (k, rel(g2[k], g1[k]))
 
 
-def test_host_frame_sink_pipelined_copy():
+@pytest.mark.parametrize("chunks,zero_copy,channels_last", [(3, False, False), (1, True, False), (1, True, True), (3, True, True)])
+def test_host_frame_sink(chunks, zero_copy, channels_last):
+    """Frames read back to pinned host memory: DMA copies pipelined behind the passes, or stored by the blend kernel
+    itself (gof_set_frame_sink); both bit-identical to the device result."""
     from f3d_gaus_b200.gaussian_renderer import HostFrameSink, render_views
     pc, cams, cfg = _scene(128, 256)
     dev = "cuda"
     wv, fp, cc = cams.world_view.to(dev), cams.full_proj.to(dev), cams.centers.to(dev)
     bg = torch.tensor([0.1, 0.2, 0.3], device=dev)
     want = render_views(pc, 0, wv, fp, cc, bg, cfg, epilogue=False)
-    sink = HostFrameSink(8, 256, 256, dev, chunks=3)
+    sink = HostFrameSink(8, 256, 256, dev, chunks=chunks, zero_copy=zero_copy, channels_last=channels_last)
+    sink.host.fill_(-7.0)
     for _ in range(2):                      # first call sizes the binning blobs (may overflow and grow)
         host = sink.render(pc, 0, wv, fp, cc, bg, cfg)
         R = sink.finish()
@@ -244,3 +248,47 @@ def test_host_frame_sink_pipelined_copy():
     assert torch.equal(host[:, 0:3], want["render"].cpu())
     assert torch.equal(host[:, 3:4], want["rendered_depth"].cpu())
     assert torch.equal(host[:, 4:5], want["rendered_alpha"].cpu())
+
+
+def test_frame_sink_abi_errors():
+    """gof_set_frame_sink: pageable host memory is refused; a sink smaller than [V,5,H,W] fails the forward call, and
+    the sink is one-shot (the next call does not write it)."""
+    import ctypes
+    from f3d_gaus_b200 import _lib
+    from f3d_gaus_b200.gaussian_renderer import render_views
+    pc, cams, cfg = _scene(32, 64)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    wv, fp, cc = cams.world_view.to(dev), cams.full_proj.to(dev), cams.centers.to(dev)
+    bg = torch.zeros(3, device=dev)
+    ctx = _lib.context(dev.index)
+    pageable = torch.empty(8 * 5 * 64 * 64)
+    assert _lib.lib.gof_set_frame_sink(ctx, pageable.data_ptr(), pageable.numel() * 4, 0) == _lib.GOF_EINVAL
+    assert "pinned" in _lib.last_error()
+    small = torch.empty(5 * 64 * 64, device=dev)
+    _lib.check(_lib.lib.gof_set_frame_sink(ctx, small.data_ptr(), small.numel() * 4, _lib.SINK_HWC), "set")
+    with pytest.raises(RuntimeError, match="frame sink too small"):
+        render_views(pc, 0, wv, fp, cc, bg, cfg, epilogue=False)
+    on_dev = torch.full((8, 5, 64, 64), -7.0, device=dev)
+    want = render_views(pc, 0, wv, fp, cc, bg, cfg, epilogue=False, sink=on_dev)
+    assert torch.equal(on_dev[:, 0:3], want["render"]) and torch.equal(on_dev[:, 4:5], want["rendered_alpha"])
+    on_dev.fill_(-7.0)
+    render_views(pc, 0, wv, fp, cc, bg, cfg, epilogue=False)          # no sink pending any more
+    assert bool((on_dev == -7.0).all())
+
+
+@pytest.mark.parametrize("res", [100, 72])
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_frame_sink_ragged_tiles(res, channels_last):
+    """Image sizes that are not multiples of the 16x16 tile (partial tiles take the per-pixel store path)."""
+    from f3d_gaus_b200.gaussian_renderer import render_views
+    pc, cams, cfg = _scene(64, res)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    wv, fp, cc = cams.world_view.to(dev), cams.full_proj.to(dev), cams.centers.to(dev)
+    bg = torch.tensor([0.3, 0.1, 0.2], device=dev)
+    sink = torch.full((8, res, res, 5) if channels_last else (8, 5, res, res), -7.0, device=dev)
+    if channels_last:
+        sink = sink.permute(0, 3, 1, 2)
+    o = render_views(pc, 0, wv, fp, cc, bg, cfg, epilogue=False, sink=sink)
+    assert torch.equal(sink[:, 0:3], o["render"])
+    assert torch.equal(sink[:, 3:4], o["rendered_depth"])
+    assert torch.equal(sink[:, 4:5], o["rendered_alpha"])

@@ -47,13 +47,17 @@ print(f"D2H 10.5 MB           : {wall(d2h):.3f} ms")
 def full():
     h2d(); pack(render()); d2h()
 print(f"full step             : {wall(full):.3f} ms")
-sink = HostFrameSink(8, 256, 256, dev, chunks=2)
-def full2():
-    h2d(); sink.render(dev_pc, 0, wv, fp, cc, bg, cfg)
-full2(); torch.cuda.synchronize(); sink.finish(); full2(); torch.cuda.synchronize(); sink.finish()
-print(f"full step, sink x2    : {wall(full2):.3f} ms  host-side {host_only(full2):.3f} ms")
-sink4 = HostFrameSink(8, 256, 256, dev, chunks=1)
-def full1():
-    h2d(); sink4.render(dev_pc, 0, wv, fp, cc, bg, cfg)
-full1(); torch.cuda.synchronize(); sink4.finish(); full1(); torch.cuda.synchronize(); sink4.finish()
-print(f"full step, sink x1    : {wall(full1):.3f} ms")
+for chunks, zc, cl in ((2, False, False), (1, False, False), (1, True, False), (1, True, True), (2, True, True)):
+    sk = HostFrameSink(8, 256, 256, dev, chunks=chunks, zero_copy=zc, channels_last=cl)
+    def fullk():
+        h2d(); sk.render(dev_pc, 0, wv, fp, cc, bg, cfg)
+    fullk(); torch.cuda.synchronize(); sk.finish(); fullk(); torch.cuda.synchronize(); sk.finish()
+    how = ("kernel stores to pinned host, " + ("[V,H,W,5]" if cl else "[V,5,H,W]")) if zc else "pack + DMA copy"
+    print(f"full step, sink chunks={chunks} {how:42s}: {wall(fullk):.3f} ms  host-side {host_only(fullk):.3f} ms")
+for cl in (False, True):
+    oh = torch.empty((8, 256, 256, 5)).pin_memory().permute(0, 3, 1, 2) if cl else out_host
+    def render_sink():
+        return render_views(dev_pc, 0, wv, fp, cc, bg, cfg, workspace=ws, epilogue=False, sink=oh)
+    print(f"render_views + kernel stores to pinned host {'[V,H,W,5]' if cl else '[V,5,H,W]'} (no H2D): {wall(render_sink):.3f} ms")
+od = torch.empty((8, 5, 256, 256), device=dev)
+print(f"render_views + kernel stores to a DEVICE sink: {wall(lambda: render_views(dev_pc, 0, wv, fp, cc, bg, cfg, workspace=ws, epilogue=False, sink=od)):.3f} ms")
