@@ -50,6 +50,7 @@ def dist_setup(n_gpus: int):
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the one JSON line
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     else:
         torch.cuda.set_device(0)
@@ -418,7 +419,7 @@ def main():
         ms = 0.0
         for i in range(K):
             flush.zero_()
-            torch.cuda.synchronize()
+            barrier(world)          # ranks start each step together: the exchange step would otherwise time their skew
             t0 = time.perf_counter()
             step_fn()
             torch.cuda.synchronize()
