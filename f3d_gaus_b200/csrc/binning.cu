@@ -310,8 +310,12 @@ __device__ __forceinline__ void bitonic_sort_regs(uint64_t* s, int n)
 	__syncthreads();
 }
 
+#ifndef GOF_SORT_MIN_CTAS
+#define GOF_SORT_MIN_CTAS 3
+#endif
+
 // One CTA per tile of the batch: sort the bucket, write point_list and the slab.
-__global__ void __launch_bounds__(SORT_THREADS, 3)
+__global__ void __launch_bounds__(SORT_THREADS, GOF_SORT_MIN_CTAS)
 tile_sort_gather_kernel(int P, int T, dim3 grid, int W, int H, float focal_x, float focal_y, float ray_pad,
                         const uint2* __restrict__ ranges, uint64_t* __restrict__ entries,
                         const float* __restrict__ rec_all, uint32_t* __restrict__ point_list,
