@@ -41,6 +41,11 @@ class GofInputs(Structure):
         "cov3D_precomp", "view2gaussian_precomp", "viewmatrix", "projmatrix", "campos")]
 
 
+class GofHeadParams(Structure):
+    _fields_ = [("BV", c_int32), ("H", c_int32), ("W", c_int32), ("C", c_int32), ("with_offset", c_int32),
+                ("sh_degree", c_int32), ("isotropic", c_int32), ("squre_clip", c_float)]
+
+
 class GofGrads(Structure):
     _fields_ = [(n, c_void_p) for n in (
         "dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh",
@@ -70,6 +75,7 @@ SIGNATURES = {
     "gof_integrate": (c_int32, [c_void_p, POINTER(GofParams), POINTER(GofInputs), c_int32, c_void_p, c_void_p, c_size_t,
                                 c_void_p, c_size_t, ALLOC_FN, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 POINTER(c_int32), c_void_p]),
+    "gof_predictor_head": (c_int32, [POINTER(GofHeadParams)] + [c_void_p] * 15),
     "gof_set_frame_sink": (c_int32, [c_void_p, c_void_p, c_size_t, c_int32]),
     "gof_num_rendered": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, POINTER(c_int32)]),
     "gof_backward": (c_int32, [c_void_p, POINTER(GofParams), POINTER(GofInputs), c_int32, c_void_p,

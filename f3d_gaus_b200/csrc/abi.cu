@@ -682,6 +682,30 @@ __global__ void epilogue_kernel(const float* __restrict__ out_color_all, const f
 	}
 }
 
+int gof_predictor_head(const GofHeadParams* prm, const float* net, const float* depth, const float* const_offset,
+                       const float* ray_x, const float* ray_y, const float* view_to_world, const float* quat,
+                       const float* sh_transform, float* xyz, float* opacity, float* scaling, float* rotation,
+                       float* features_dc, float* features_rest, gof_stream_t stream)
+{
+	if (!prm) { set_error("gof_predictor_head: prm is NULL"); return GOF_EINVAL; }
+	if (prm->BV < 0 || prm->H <= 0 || prm->W <= 0) { set_error("gof_predictor_head: bad sizes BV=%d H=%d W=%d", prm->BV, prm->H, prm->W); return GOF_EINVAL; }
+	if (prm->sh_degree != 0 && prm->sh_degree != 1) { set_error("gof_predictor_head: only SH degree 0 or 1 (gaussian_predictor.py:993), got %d", prm->sh_degree); return GOF_EINVAL; }
+	const int need = (prm->with_offset ? 3 : 0) + 11 + (prm->sh_degree > 0 ? 9 : 0);
+	if (prm->C != need) { set_error("gof_predictor_head: the network output has %d channels, this configuration needs %d", prm->C, need); return GOF_EINVAL; }
+	if (prm->BV == 0) return GOF_OK;
+	if (!net || !depth || !ray_x || !ray_y || !view_to_world || !quat || !xyz || !opacity || !scaling || !rotation || !features_dc ||
+	    (prm->sh_degree > 0 && !features_rest)) {
+		set_error("gof_predictor_head: a required pointer is NULL");
+		return GOF_EINVAL;
+	}
+	if (((uintptr_t)xyz | (uintptr_t)scaling | (uintptr_t)rotation | (uintptr_t)features_dc | (uintptr_t)features_rest) % 16 != 0) {
+		set_error("gof_predictor_head: output arrays must be 16-byte aligned");
+		return GOF_EINVAL;
+	}
+	return launch_predictor_head(*prm, net, depth, const_offset, ray_x, ray_y, view_to_world, quat, sh_transform, xyz, opacity,
+	                             scaling, rotation, features_dc, features_rest, (cudaStream_t)stream);
+}
+
 int gof_render_epilogue(const float* out_color, const float* viewmatrix, int32_t W, int32_t H,
                         float fovx, float fovy, float* normal_world, float* depth_normal, gof_stream_t stream)
 {

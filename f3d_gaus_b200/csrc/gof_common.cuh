@@ -124,6 +124,10 @@ int launch_integrate(const GofParams& prm, const GofInputs& in, const Frame& f, 
 int launch_tile_scan_raw(int T, const uint32_t* counts, uint2* ranges, uint32_t* cursor, int32_t* mailbox, cudaStream_t s);
 int launch_render_fwd(const GofParams& prm, const Frame& f, const GeomState& g, const ImgState& im, const BinState& b,
                       const float* background, int bg_stride, float* out_color, float* sink, int sink_hwc, cudaStream_t s);
+int launch_predictor_head(const GofHeadParams& prm, const float* net, const float* depth, const float* const_offset,
+                          const float* ray_x, const float* ray_y, const float* view_to_world, const float* quat,
+                          const float* sh_transform, float* xyz, float* opacity, float* scaling, float* rotation,
+                          float* features_dc, float* features_rest, cudaStream_t s);
 int launch_render_bwd(const GofParams& prm, const Frame& f, const GeomState& g, const ImgState& im,
                       const BinState& b, const float* background, int bg_stride, const float* dL_dpix, float* gacc,
                       cudaStream_t s);

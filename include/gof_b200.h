@@ -229,6 +229,32 @@ int gof_preprocess_backward(GofContext* ctx, const GofParams* prm, const GofInpu
 int gof_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
                      const float* projmatrix, uint8_t* present /* [P] bool */, gof_stream_t stream);
 
+/* Scalar settings of the predictor output head (cfg['model'] of the reference + the call's squre_clip). */
+typedef struct GofHeadParams {
+	int32_t BV;             /* images in the call: batch * views (x.reshape(B*N_views, ...), gaussian_predictor.py:913) */
+	int32_t H, W;           /* training_resolution */
+	int32_t C;              /* channels of the network output: [3 +] 1 + 3 + 4 + 3 [+ 9] (get_splits_and_inits, :683-728) */
+	int32_t with_offset;    /* network_with_offset: the first 3 channels are the xyz offset */
+	int32_t sh_degree;      /* max_sh_degree: 0 or 1 (the reference asserts 1, :993) */
+	int32_t isotropic;      /* cfg['model']['isotropic']: scaling channel 0 replicated (:951-952) */
+	float squre_clip;       /* x/y clamp of the world position, active when < 10 (:968-970) */
+} GofHeadParams;
+
+/* Predictor output head: everything GaussianSplatPredictor_gtunet.forward does after the UNet
+ * (src/gaussian_predictor.py:954-1008) in one kernel: channel split, ray * depth + offset, view_to_world (row-vector
+ * convention) and homogeneous divide, squre_clip, sigmoid / exp / normalize, rotation and degree-1 SH to the world
+ * frame, NCHW -> point-list layout.  All pointers are device memory, float32, contiguous:
+ *   net [BV,C,H,W]; depth [BV,1,H,W]; const_offset [BV,1,H,W] or NULL (origin_distances, :915-917,:872);
+ *   ray_x [W], ray_y [H]: the x / y rows of the module's ray_dirs buffer (init_ray_dirs, :657-681);
+ *   view_to_world [BV,16]; quat [BV,4] (source_cv2wT_quat); sh_transform [BV,9] = sh_to_v @ V2W[:3,:3] @ v_to_sh
+ *   (:824-832; NULL = derive it in the kernel from the module's constant v_to_sh matrix, :649-655);
+ *   outputs xyz [BV*N,3], opacity [BV*N,1], scaling [BV*N,3], rotation [BV*N,4], features_dc [BV*N,1,3],
+ *   features_rest [BV*N,3,3] (NULL when sh_degree == 0) -- i.e. [B, V*N, .] after multi_view_union (:796-800). */
+int gof_predictor_head(const GofHeadParams* prm, const float* net, const float* depth, const float* const_offset,
+                       const float* ray_x, const float* ray_y, const float* view_to_world, const float* quat,
+                       const float* sh_transform, float* xyz, float* opacity, float* scaling, float* rotation,
+                       float* features_dc, float* features_rest, gof_stream_t stream);
+
 /* Fused epilogue of render_predicted_more_v2_gof: from out_color[9,H,W] and the camera produce
  *   normal_world[3,H,W] = R_c2w * normalize(out_color[3:6])   and
  *   depth_normal[3,H,W] = normalize(cross(dP/dy, dP/dx)) of the back-projected median depth
