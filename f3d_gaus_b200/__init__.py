@@ -6,7 +6,9 @@ Layout (only what the hot path needs):
   diff_gof_rasterization/  drop-in for the reference's rasterizer package
   gaussian_renderer/       drop-in for src/gaussian_renderer (render_predicted_more_v2_gof, render)
   cycle.py                 the cycle-aggregative render loop of visualize.py:281-340
-  sharding.py              scene-sharded multi-GPU runner (one process per GPU, NCCL gather)
+  predictor_head.py        the predictor's post-network output head (src/gaussian_predictor.py:954-1008), one kernel
+  sharding.py              scene-sharded multi-GPU runner (one process per GPU, fused peer-memory gather, NCCL fallback)
+  ply.py                   Gaussian-set export helpers (visualize.py:146-179)
 """
 from __future__ import annotations
 

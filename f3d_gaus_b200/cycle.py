@@ -45,6 +45,26 @@ def from_unet_gs(model, background, squre_clip: bool = True) -> Callable:
     return predict
 
 
+def from_network(network, cfg: dict, device, squre_clip: float = 10000.0) -> Callable:
+    """Predictor = the reference's UNet alone (`gaussian_predictor.network_with_offset` / `network_wo_offset`, called as
+    src/gaussian_predictor.py:929-945) followed by the fused output head (predictor_head.PredictorHead, one kernel
+    instead of :954-1008).  `network(x[B*V,C_in,H,W], film_camera_emb=None, N_views_xa=...) -> [B*V,C,H,W]`."""
+    from .predictor_head import PredictorHead
+    head = PredictorHead(cfg, device)
+    xa = bool(cfg["model"].get("cross_view_attention", True))
+
+    def predict(novel_img, view_to_world, quat, depth):
+        B, V = novel_img.shape[:2]
+        x = novel_img.reshape(B * V, *novel_img.shape[2:])
+        const_offset = None
+        if head.origin_distances:                                   # :915-917
+            const_offset, x = x[:, 3:], x[:, :3]
+        raw = network(x, film_camera_emb=None, N_views_xa=V if xa else 1)
+        out = head(raw, depth, view_to_world, quat, B, V, squre_clip=squre_clip, const_offset=const_offset)
+        return {k: out[k] for k in PC_KEYS}
+    return predict
+
+
 def unproject_predictor(cfg: dict, scale: float = 0.01) -> Callable:
     """Stand-in predictor with the reference's output contract (src/gaussian_predictor.py:857-881,954-1002):
     one Gaussian per pixel at `ray_dir * depth` (y inverted, :657-670), moved to the world frame with the

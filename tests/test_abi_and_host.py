@@ -110,3 +110,20 @@ def test_synthetic_is_seeded_and_shaped():
     assert torch.allclose(a["rotation"].norm(dim=-1), torch.ones(1, 1024), atol=1e-5)
     m = synthetic.concat_sets([a, c])
     assert m["xyz"].shape == (1, 2048, 3)
+
+
+def test_ply_export_roundtrip(tmp_path):
+    """ply.flat_attributes reproduces load_ply(path=None) of visualize.py:146-179; save_ply/read_ply round-trip."""
+    from f3d_gaus_b200 import ply, synthetic
+    pc = synthetic.f3d_like(3, 16)
+    xyz, f_dc, f_rest, opac, scale, rot = ply.flat_attributes(pc, 0)
+    P = 256
+    assert xyz.shape == (P, 3) and f_dc.shape == (P, 3) and f_rest.shape == (P, 45) and opac.shape == (P, 1)
+    assert torch.equal(f_dc, pc["features_dc"][0].reshape(P, 3)) and not f_rest.any()
+    path = str(tmp_path / "sub" / "scene.ply")
+    assert ply.save_ply(pc, 0, path) == P
+    back = ply.read_ply(path)
+    assert list(back)[:6] == ["x", "y", "z", "nx", "ny", "nz"] and len(back) == 6 + 3 + 45 + 1 + 3 + 4
+    assert np.array_equal(back["x"], xyz[:, 0].numpy()) and np.array_equal(back["rot_3"], rot[:, 3].numpy())
+    assert np.array_equal(back["opacity"], opac[:, 0].numpy()) and np.array_equal(back["scale_1"], scale[:, 1].numpy())
+    assert not back["nx"].any() and not back["f_rest_44"].any()

@@ -182,3 +182,35 @@ def test_head_errors_and_rasterizer_hand_off():
                      torch.zeros(3, device=dev), cfg, epilogue=False)
     assert o["render"].shape == (8, 3, 64, 64) and bool(torch.isfinite(o["raster"]).all())
     assert float(o["rendered_alpha"].max()) > 0.0
+
+
+@pytest.mark.gpu
+def test_cycle_loop_with_network_and_fused_head():
+    """cycle.from_network: a stand-in UNet (one conv, reference call signature) + the fused head inside the
+    cycle-aggregative loop; the merged set has (1 + K) * H * W Gaussians and renders."""
+    from f3d_gaus_b200 import cameras, cycle, synthetic
+    from f3d_gaus_b200.gaussian_renderer import render_views
+    dev = torch.device("cuda", torch.cuda.current_device())
+    res, K = 64, 2
+    cfg = synthetic.cfg_for(res)
+    cfg["model"].update(network_with_offset=True, network_without_offset=False, cross_view_attention=True)
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(4, 23, 3, padding=1).to(dev)
+    with torch.no_grad():
+        conv.weight.mul_(0.05)
+        conv.bias.copy_(torch.tensor([0.0] * 3 + [2.0] + [-4.6] * 3 + [1.0, 0, 0, 0] + [0.5] * 3 + [0.0] * 9))
+
+    def network(x, film_camera_emb=None, N_views_xa=1):
+        with torch.no_grad():
+            return conv(x)
+
+    predict = cycle.from_network(network, cfg, dev)
+    pc = {k: v.to(dev) for k, v in synthetic.f3d_like(0, res).items()}
+    orbit = cameras.orbit_cameras(8)
+    cams = cameras.Cameras(*[t[[2, 5]].to(dev) for t in orbit])
+    bg = torch.zeros(3, device=dev)
+    merged, frames = cycle.cycle_aggregate(pc, predict, cams, cfg, bg)
+    assert merged["xyz"].shape == (1, (1 + K) * res * res, 3) and merged["features_rest"].shape[2:] == (3, 3)
+    assert bool(torch.isfinite(merged["xyz"]).all())
+    o = render_views(merged, 0, cams.world_view, cams.full_proj, cams.centers, bg, cfg, epilogue=False)
+    assert bool(torch.isfinite(o["raster"]).all()) and float(o["rendered_alpha"].max()) > 0.5
