@@ -11,6 +11,8 @@ timeout 600 python bench.py --impl reference > $OUT/bench_reference.json 2> $OUT
 timeout 600 python bench.py > $OUT/bench_ours.json 2> $OUT/bench_ours.err
 cat $OUT/bench_reference.json $OUT/bench_ours.json
 timeout 300 python tools/quick_bench.py 256 256 50 > $OUT/quick_bench.log 2>&1; cat $OUT/quick_bench.log
+(timeout 120 python tools/bench_head.py 8 256; timeout 120 python tools/bench_head.py 64 256) > $OUT/head_bench.json 2> $OUT/head_bench.err; cat $OUT/head_bench.json
+(timeout 300 python tools/train_bench.py 8 256 256; timeout 300 python tools/train_bench.py 3 256 256) > $OUT/train_bench.json 2> $OUT/train_bench.err; cat $OUT/train_bench.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/launches_bench.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'render_fwd_kernel|tile_sort_gather|preprocess_kernel|scatter_kernel' -s 12 -c 5 \

@@ -96,7 +96,7 @@ def main():
         full(rep, os.path.join(prof, f"{tag}_blend_ncu.md"),
              f"{tag}: ncu --set full, blend kernels (65,536 Gaussians, 256x256)",
              os.path.join(prof, "render_fwd_traffic.json"))
-    for name in ("bench_ours.json", "bench_reference.json", "quick_bench.log"):
+    for name in ("bench_ours.json", "bench_reference.json", "quick_bench.log", "head_bench.json", "train_bench.json"):
         p = os.path.join(src, name)
         if os.path.exists(p):
             with open(p) as f, open(os.path.join(prof, f"{tag}_{name}"), "w") as g:
