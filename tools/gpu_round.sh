@@ -19,4 +19,6 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:'ren
     -o $OUT/prof_blend python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'render_bwd_kernel' -s 6 -c 1 \
     -o $OUT/prof_bwd python tools/quick_bench.py 256 256 3 > $OUT/ncu_full_bwd.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'predictor_head_kernel' -s 8 -c 1 \
+    -o $OUT/prof_head python tools/bench_head.py 64 256 > $OUT/ncu_full_head.log 2>&1
 ls -la $OUT

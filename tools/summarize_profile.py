@@ -96,6 +96,11 @@ def main():
         full(rep, os.path.join(prof, f"{tag}_blend_ncu.md"),
              f"{tag}: ncu --set full, blend kernels (65,536 Gaussians, 256x256)",
              os.path.join(prof, "render_fwd_traffic.json"))
+    for stem, what in (("prof_bwd", "backward blend (65,536 Gaussians, 256x256, one view)"),
+                       ("prof_head", "predictor output head (64 images of 256x256, 23 channels)")):
+        rep = os.path.join(src, stem + ".ncu-rep")
+        if os.path.exists(rep):
+            full(rep, os.path.join(prof, f"{tag}_{stem[5:]}_ncu.md"), f"{tag}: ncu --set full, {what}")
     for name in ("bench_ours.json", "bench_reference.json", "quick_bench.log", "head_bench.json", "train_bench.json"):
         p = os.path.join(src, name)
         if os.path.exists(p):
