@@ -151,13 +151,15 @@ def measured_peak_gbs():
 
 
 def traffic_from_profiles():
-    """dram bytes per render launch from the committed ncu --set full summary, if present."""
+    """(dram bytes per render launch, issue-side figures) from the committed ncu --set full summary, if present."""
     path = os.path.join(ROOT, "profiles", "render_fwd_traffic.json")
     try:
         with open(path) as f:
-            return json.load(f).get("dram_bytes_per_launch")
+            d = json.load(f)
+        issue = {k: d[k] for k in ("issue_active_pct", "active_lanes_per_instruction", "warp_instructions") if d.get(k) is not None}
+        return d.get("dram_bytes_per_launch"), (issue or None)
     except Exception:
-        return None
+        return None, None
 
 
 # ------------------------------------------------------------------------------ arms --------
@@ -490,10 +492,11 @@ def main():
         blend_ms = prof["fwd_ms"]["blend"] / n_calls
         abytes = sum(algorithmic_bytes_render_fwd(P, r, RES, RES) for r in R_views)
         achieved = abytes / (blend_ms * 1e-3) / 1e9
-        traffic = traffic_from_profiles()
+        traffic, issue = traffic_from_profiles()
         roofline = {"bound": "hbm", "kernel": "render_fwd_kernel (one launch blends the 8 frames of a step)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "issue_side_from_ncu": issue,
                     "algorithmic_bytes_per_launch": abytes, "avg_launch_ms": blend_ms,
                     "num_rendered_per_view": R_views,
                     "stage_ms_per_step": {k: v / n_calls for k, v in prof["fwd_ms"].items()},

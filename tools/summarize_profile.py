@@ -78,10 +78,17 @@ def full(rep, out_md, title, traffic_json=None, traffic_kernel="render_fwd"):
         vals = [to_bytes(r, hdr.index("dram__bytes_read.sum")) + to_bytes(r, hdr.index("dram__bytes_write.sum"))
                 for r, n in zip(rows[2:], names) if traffic_kernel in n]
         if vals:
+            def metric(name):
+                sel = [float(r[hdr.index(name)].replace(",", "")) for r, n in zip(rows[2:], names) if traffic_kernel in n]
+                return sum(sel) / len(sel) if (name in hdr and sel) else None
             with open(traffic_json, "w") as f:
                 json.dump({"kernel": traffic_kernel, "dram_bytes_per_launch": sum(vals) / len(vals),
                            "launches": len(vals), "source": os.path.relpath(rep, ROOT),
-                           "workload": "tools/quick_bench.py: 65536 f3d-like Gaussians, 256x256"}, f, indent=1)
+                           "issue_active_pct": metric("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                           "active_lanes_per_instruction": metric("smsp__thread_inst_executed_per_inst_executed.ratio"),
+                           "warp_instructions": metric("smsp__inst_executed.sum"),
+                           "workload": "bench.py step: one launch blends 8 views of 65536 f3d-like Gaussians, 256x256"},
+                          f, indent=1)
 
 
 def main():
