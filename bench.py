@@ -50,7 +50,10 @@ def dist_setup(n_gpus: int):
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the one JSON line
+        # keep stdout for the one JSON line: NCCL_DEBUG=VERSION printf()s its banner to stdout, other levels log to the file
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     else:
         torch.cuda.set_device(0)
