@@ -236,8 +236,7 @@ class OursArm:
             # GOF_BENCH_READBACK=dma selects the packed DMA copy instead (tools/e2e_breakdown.py compares them)
             self.sink = HostFrameSink(VIEWS, RES, RES, self.device, chunks=1,
                                       zero_copy=os.environ.get("GOF_BENCH_READBACK", "kernel") != "dma")
-        for k in host_pc:
-            dev_pc[k].copy_(host_pc[k], non_blocking=True)
+        dev_pc = host_pc.upload()                     # gaussian_renderer.PinnedScene: one copy for the whole set
         self.sink.render(dev_pc, 0, cams_dev[0], cams_dev[1], cams_dev[2], bg, cfg)
         if self.world > 1:
             # the path's one exchange step: every rank receives all scenes' frames -- one kernel that
@@ -263,8 +262,7 @@ class OursArm:
     def e2e_per_view_step(self, host_pc, dev_pc, cams_dev, cfg, bg, out_dev, out_host):
         """The same through the reference's own one-frame function (render_predicted_more_v2_gof)."""
         from f3d_gaus_b200.gaussian_renderer import render_predicted_more_v2_gof
-        for k in host_pc:
-            dev_pc[k].copy_(host_pc[k], non_blocking=True)
+        dev_pc = host_pc.upload()
         with torch.no_grad():
             for v in range(VIEWS):
                 o = render_predicted_more_v2_gof(dev_pc, 0, cams_dev[0][v:v + 1], cams_dev[1][v:v + 1],
@@ -320,8 +318,7 @@ class ReferenceArm:
 
     def e2e_step(self, host_pc, dev_pc, cams_dev, cfg, bg, out_dev, out_host):
         import math
-        for k in host_pc:
-            dev_pc[k].copy_(host_pc[k], non_blocking=True)
+        dev_pc = host_pc.upload()
         tanfov = math.tan(cfg["model"]["fov"] * math.pi / 360)
         shs = torch.cat([dev_pc["features_dc"][0], dev_pc["features_rest"][0]], dim=1).contiguous()
         for v in range(VIEWS):
@@ -463,8 +460,9 @@ def main():
         per_view_value = frames / (pv_ms * 1e-3)
 
     # ---------------- end to end through the public API, host buffers -------------------------
-    host_pc = {k: v.pin_memory() for k, v in pc_cpu.items()}
-    dev_pc = {k: torch.empty_like(v, device=device) for k, v in pc_cpu.items()}
+    from f3d_gaus_b200.staging import PinnedScene      # pure torch (also re-exported by gaussian_renderer)
+    host_pc = PinnedScene(pc_cpu, device)          # both arms: the set in one pinned slab, one H2D copy per step
+    dev_pc = host_pc.dev
     cams_dev = (cams.world_view.to(device), cams.full_proj.to(device), cams.centers.to(device))
     bg = torch.zeros(3, device=device)
     out_dev = torch.empty((VIEWS, 5, RES, RES), dtype=torch.float32, device=device)

@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from .. import _lib
+from ..staging import PinnedScene  # noqa: F401  (public here; defined in a module that does not load the CUDA library)
 from ..diff_gof_rasterization import (BatchWorkspace, GaussianRasterizationSettings_GOF, GaussianRasterizer_GOF,
                                      rasterize_views)
 

@@ -292,3 +292,19 @@ def test_frame_sink_ragged_tiles(res, channels_last):
     assert torch.equal(sink[:, 0:3], o["render"])
     assert torch.equal(sink[:, 3:4], o["rendered_depth"])
     assert torch.equal(sink[:, 4:5], o["rendered_alpha"])
+
+
+def test_pinned_scene_single_upload():
+    """PinnedScene: one pinned slab + one device slab; the device views equal the per-key copies and feed the renderer."""
+    from f3d_gaus_b200 import synthetic
+    from f3d_gaus_b200.gaussian_renderer import PinnedScene
+    dev = torch.device("cuda", torch.cuda.current_device())
+    pc_cpu = synthetic.f3d_like(2, 64)
+    scene = PinnedScene(pc_cpu, dev)
+    assert scene.host_slab.is_pinned() and scene.nbytes == sum(v.numel() * 4 for v in pc_cpu.values())
+    d = scene.upload()
+    torch.cuda.synchronize()
+    for k, v in pc_cpu.items():
+        assert d[k].shape == v.shape and d[k].data_ptr() % 256 == 0 and torch.equal(d[k].cpu(), v), k
+    scene.host["opacity"].mul_(0.5)                      # the pinned views are writable in place
+    assert torch.equal(scene.upload()["opacity"].cpu(), pc_cpu["opacity"] * 0.5)
