@@ -43,11 +43,15 @@ __device__ __forceinline__ void red_global_v4(float* addr, float4 v)
 	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// 1/x for a float x to ~48 bits: correctly rounded float reciprocal + one Newton step in double (2 DFMA instead
-// of an IEEE double division; only used for gradient VALUES, never for alpha / T / the contributing set).
+// 1/x for a float x to ~44 bits: one MUFU.RCP (<= 1 ulp) + one Newton step in double (2 DFMA instead of an IEEE
+// double division; only used for gradient VALUES, never for alpha / the contributing set).
+#ifndef GOF_BWD_IEEE_RCP
+#define GOF_BWD_IEEE_RCP 0        // 1: the correctly rounded float reciprocal / sqrt sequences (A/B switch)
+#endif
+__device__ __forceinline__ float rcp_f32(float x) { return GOF_BWD_IEEE_RCP ? __frcp_rn(x) : rcp_approx(x); }
 __device__ __forceinline__ double rcp_refined(float x)
 {
-	const double r = (double)__frcp_rn(x);
+	const double r = (double)rcp_f32(x);
 	return fma(r, fma(-(double)x, r, 1.0), r);
 }
 
@@ -208,10 +212,11 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 					const double inv_t = rcp_refined(t);
 					const float mapped = (float)((100.0 / (100.0 - 0.2)) - ((100.0 * 0.2) / (100.0 - 0.2)) * inv_t);
 					const float dmax_t_dd = (float)(((100.0 * 0.2) / (100.0 - 0.2)) * inv_t * inv_t);
-					const float inv_len = __frcp_rn(sqrtf(g.n0 * g.n0 + g.n1 * g.n1 + g.n2 * g.n2 + 1e-7f));
+					const float len2 = g.n0 * g.n0 + g.n1 * g.n1 + g.n2 * g.n2 + 1e-7f;
+					const float inv_len = GOF_BWD_IEEE_RCP ? __frcp_rn(sqrtf(len2)) : rsqrt_approx(len2);
 					const float nn[3] = { -g.n0 * inv_len, -g.n1 * inv_len, -g.n2 * inv_len };
 					const float nraw[3] = { g.n0, g.n1, g.n2 };
-					const float inv_1ma = __frcp_rn(1.f - alpha);
+					const float inv_1ma = rcp_f32(1.f - alpha);
 					float* dst = gacc + (size_t)gid * GACC_FLOATS;
 					float gcol[3];
 
