@@ -38,8 +38,12 @@ namespace {
 #ifndef GOF_FWD_MIN_CTAS
 #define GOF_FWD_MIN_CTAS 3
 #endif
-constexpr int CHUNK = 128;                 // records per pipeline stage (10 KB)
+#ifndef GOF_FWD_CHUNK
+#define GOF_FWD_CHUNK 128
+#endif
+constexpr int CHUNK = GOF_FWD_CHUNK;       // records per pipeline stage (10 KB at 128)
 constexpr int STAGES = GOF_FWD_STAGES;
+constexpr int NW = CHUNK / 32;             // 32-record words per chunk
 
 struct PixState {
 	float T;
@@ -184,13 +188,14 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 		const int cnt = min(CHUNK, n - c * CHUNK);
 		// this lane's share of the chunk's block masks (records lane, 32+lane, 64+lane, 96+lane): read from
 		// L2 before waiting for the TMA stage so that the latency overlaps it
-		uint32_t bm0 = 0, bm1 = 0, bm2 = 0, bm3 = 0;
+		uint32_t bm[NW];
+#pragma unroll
+		for (int k = 0; k < NW; k++) bm[k] = 0;
 		if (!warp_done) {
 			const uint8_t* q = tile_bm + c * CHUNK + lane;
-			if (lane < cnt) bm0 = __ldg(q);
-			if (32 + lane < cnt) bm1 = __ldg(q + 32);
-			if (64 + lane < cnt) bm2 = __ldg(q + 64);
-			if (96 + lane < cnt) bm3 = __ldg(q + 96);
+#pragma unroll
+			for (int k = 0; k < NW; k++)
+				if (32 * k + lane < cnt) bm[k] = __ldg(q + 32 * k);
 		}
 		mbar_wait(&s_full[s], (uint32_t)((c / STAGES) & 1));
 		if (!warp_done) {
@@ -198,13 +203,17 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 			const uint32_t base = (uint32_t)c * CHUNK;
 			// ---- pass 1: conic sweep over the chunk's records that can touch this warp's 8x4 block (bit `warp`
 			// of the record's block mask, ~1/3 of them); coefficients are warp-broadcast shared-memory reads.
-			uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;   // survivors among records [0,32) [32,64) [64,96) [96,128)
+			uint32_t m[NW];                            // survivors among records [32k, 32k+32)
+#pragma unroll
+			for (int k = 0; k < NW; k++) m[k] = 0;
 #pragma unroll 1
-			for (int w = 0; w < CHUNK / 32; w++) {
+			for (int w = 0; w < NW; w++) {
 				const int valid = cnt - 32 * w;
 				if (valid <= 0) break;
-				const uint32_t bm = (w == 0) ? bm0 : (w == 1) ? bm1 : (w == 2) ? bm2 : bm3;
-				uint32_t rel = __ballot_sync(0xffffffffu, (bm >> warp) & 1u);
+				uint32_t bmw = bm[0];
+#pragma unroll
+				for (int k = 1; k < NW; k++) bmw = (w == k) ? bm[k] : bmw;
+				uint32_t rel = __ballot_sync(0xffffffffu, (bmw >> warp) & 1u);
 				uint32_t bits = 0;
 				const uint32_t rw = rec + (uint32_t)w * (32 * SLAB_BYTES);
 				while (rel != 0) {                       // warp-uniform; two records per trip for ILP
@@ -217,21 +226,25 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 					if (!conic_reject(a0.x, a0.y, a0.z, a0.w, b0.x, b0.y, fx, fy)) bits |= 1u << j0;
 					if (!conic_reject(a1.x, a1.y, a1.z, a1.w, b1.x, b1.y, fx, fy)) bits |= 1u << j1;
 				}
-				if (w == 0) m0 = bits; else if (w == 1) m1 = bits; else if (w == 2) m2 = bits; else m3 = bits;
+#pragma unroll
+				for (int k = 0; k < NW; k++)
+					if (w == k) m[k] = bits;
 			}
-			if (done) { m0 = 0; m1 = 0; m2 = 0; m3 = 0; }
+			if (done) {
+#pragma unroll
+				for (int k = 0; k < NW; k++) m[k] = 0;
+			}
 			// ---- pass 2: each pixel blends its own survivors, in list order.  ONE loop over the whole
-			// chunk: the warp iterates max-over-lanes(survivors in 128 records) times, m0 is the word being
-			// consumed, m1..m3 shift down when it runs empty.
-			// `cur` = the word being consumed, `wsel` its index; m1..m3 stay loop-invariant.  Two survivors are
+			// chunk: the warp iterates max-over-lanes(survivors in the chunk) / 2 times.
+			// `cur` = the word being consumed, `wsel` its index; m[1..] stay loop-invariant.  Two survivors are
 			// taken per trip: their exact evaluations (double division, exp) are independent dependency chains
 			// that interleave, the two blends then run in list order.
-			uint32_t cur = m0, wsel = 0;
+			uint32_t cur = m[0], wsel = 0;
 			auto refill = [&]() -> bool {      // make `cur` non-empty; false when the lane has no survivors left
 				if (cur != 0) return true;
-				if (wsel < 1 && m1 != 0) { cur = m1; wsel = 1; return true; }
-				if (wsel < 2 && m2 != 0) { cur = m2; wsel = 2; return true; }
-				if (wsel < 3 && m3 != 0) { cur = m3; wsel = 3; return true; }
+#pragma unroll
+				for (int k = 1; k < NW; k++)
+					if (wsel < (uint32_t)k && m[k] != 0) { cur = m[k]; wsel = k; return true; }
 				return false;
 			};
 			for (;;) {
