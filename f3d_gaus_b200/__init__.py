@@ -8,6 +8,7 @@ Layout (only what the hot path needs):
   cycle.py                 the cycle-aggregative render loop of visualize.py:281-340
   predictor_head.py        the predictor's post-network output head (src/gaussian_predictor.py:954-1008), one kernel
   sharding.py              scene-sharded multi-GPU runner (one process per GPU, fused peer-memory gather, NCCL fallback)
+  staging.py               PinnedScene: a Gaussian set in one pinned host slab, one H2D copy (pure torch)
   ply.py                   Gaussian-set export helpers (visualize.py:146-179)
 """
 from __future__ import annotations

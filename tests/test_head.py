@@ -45,6 +45,15 @@ def _check(got: dict, want: dict, where: str):
             assert np.allclose(g, w, rtol=RTOL, atol=ATOL), (where, k, float(np.abs(g - w).max()))
 
 
+def _random_case(B, V, res, with_offset, sh, seed):
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_head_golden as mk
+    net, depth, _, v2w, quat = mk.make_inputs(B, V, res, with_offset, sh, False, seed)
+    kw = dict(B=B, V=V, res=res, fov_deg=13.164, with_offset=with_offset, sh_degree=sh, isotropic=False,
+              inverted_x=False, inverted_y=True, squre_clip=10000.0)
+    return net.numpy(), depth.numpy(), v2w.numpy(), quat.numpy(), kw
+
+
 def test_golden_present():
     assert len(GOLDEN) >= 4
 
@@ -83,6 +92,20 @@ def test_torch_restatement_is_bit_identical_on_cpu(path):
         assert np.array_equal(v.numpy(), z["out_" + k]), k
 
 
+def test_config1_plumbing_shapes_on_cpu():
+    """BASELINE configs[0]: one 256x256 image -> per-pixel Gaussian parameters, no raster.  The UNet is the reference's
+    (out of scope); everything after it, on CPU through the oracle: dict keys and [1, 65 536, .] shapes of the
+    reference's output contract (src/gaussian_predictor.py:972-1002)."""
+    net, depth, v2w, quat, kw = _random_case(1, 1, 256, True, 1, seed=0)
+    out = head_oracle.head(net, depth, v2w, quat, **kw)
+    want = {"xyz": (1, 65536, 3), "opacity": (1, 65536, 1), "scaling": (1, 65536, 3), "rotation": (1, 65536, 4),
+            "features_dc": (1, 65536, 1, 3), "features_rest": (1, 65536, 3, 3), "unet_depth": (1, 65536, 1)}
+    assert {k: v.shape for k, v in out.items()} == want
+    assert all(np.isfinite(v).all() for v in out.values())
+    assert (out["opacity"] > 0).all() and (out["opacity"] < 1).all() and (out["scaling"] > 0).all()
+    assert np.allclose(np.linalg.norm(out["rotation"], axis=-1), 1.0, atol=1e-5)      # unit quaternions stay unit
+
+
 def test_head_needs_cuda():
     from f3d_gaus_b200.predictor_head import PredictorHead
     with pytest.raises(RuntimeError, match="no CPU path"):
@@ -109,15 +132,6 @@ def test_head_cuda_vs_golden(path):
     z, kw, co = _load(path)
     got = _run_cuda(z["in_net"], z["in_depth"], z["in_view_to_world"], z["in_quat"], kw, co, origin=co is not None)
     _check(got, {k[4:]: z[k] for k in z.files if k.startswith("out_")}, "cuda")
-
-
-def _random_case(B, V, res, with_offset, sh, seed):
-    sys.path.insert(0, os.path.join(HERE, "golden"))
-    import make_head_golden as mk
-    net, depth, _, v2w, quat = mk.make_inputs(B, V, res, with_offset, sh, False, seed)
-    kw = dict(B=B, V=V, res=res, fov_deg=13.164, with_offset=with_offset, sh_degree=sh, isotropic=False,
-              inverted_x=False, inverted_y=True, squre_clip=10000.0)
-    return net.numpy(), depth.numpy(), v2w.numpy(), quat.numpy(), kw
 
 
 @pytest.mark.gpu
