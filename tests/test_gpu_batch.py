@@ -227,11 +227,13 @@ def test_batched_backward_equals_sum_of_per_view_backwards(kind):
         assert rel(g2[k], g1[k]) <= tol, (k, rel(g2[k], g1[k]))
 
 
+@pytest.mark.parametrize("exact", [False, True])
 @pytest.mark.parametrize("chunks,zero_copy,channels_last", [(3, False, False), (1, True, False), (1, True, True), (3, True, True)])
-def test_host_frame_sink(chunks, zero_copy, channels_last):
+def test_host_frame_sink(chunks, zero_copy, channels_last, exact, monkeypatch):
     """Frames read back to pinned host memory: DMA copies pipelined behind the passes, or stored by the blend kernel
     itself (gof_set_frame_sink); both bit-identical to the device result."""
     from f3d_gaus_b200.gaussian_renderer import HostFrameSink, render_views
+    monkeypatch.setenv("GOF_EXACT_BLEND", "1" if exact else "0")          # both blend kernels have a sink instantiation
     pc, cams, cfg = _scene(128, 256)
     dev = "cuda"
     wv, fp, cc = cams.world_view.to(dev), cams.full_proj.to(dev), cams.centers.to(dev)
