@@ -19,6 +19,9 @@
  *                                                                  RAST/cuda_rasterizer/rasterizer_impl.cu:188-243
  *   gof_render_epilogue  <- the torch post-processing of render_predicted_more_v2_gof
  *                                                                  src/gaussian_renderer/__init__.py:881-909,1043-1053
+ *   gof_set_frame_sink   <- the .cpu() of rgb / depth / alpha after every frame       visualize.py:304-306,396-398
+ *   gof_predictor_head   <- GaussianSplatPredictor_gtunet.forward after the UNet      src/gaussian_predictor.py:954-1008
+ *   gof_pack_gather      <- (no counterpart; the multi-GPU exchange step: pack + all-gather over NVLink peer memory)
  *
  * Conventions (same as the reference unless noted):
  *   - plain pointers and sizes only; all array pointers are DEVICE pointers, float32 unless noted;
