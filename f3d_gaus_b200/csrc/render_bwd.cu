@@ -209,9 +209,17 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 					// (backward.cu:843-925).  The contributing SET and alpha, T are bit-exact (shared with the
 					// forward); the gradient VALUES only have to meet the 1e-3 relative bar, so each group of
 					// divisions by the same quantity is one reciprocal and multiplies (differences ~1e-7).
+#if GOF_BWD_IEEE_RCP
 					const double inv_t = rcp_refined(t);
 					const float mapped = (float)((100.0 / (100.0 - 0.2)) - ((100.0 * 0.2) / (100.0 - 0.2)) * inv_t);
 					const float dmax_t_dd = (float)(((100.0 * 0.2) / (100.0 - 0.2)) * inv_t * inv_t);
+#else
+					// mapped depth far/(far-near) - (far*near/(far-near))/t and its derivative: well conditioned, float32
+					const float inv_t = rcp_approx(t);
+					const float kfn = (float)((100.0 * 0.2) / (100.0 - 0.2));
+					const float mapped = __fmaf_rn(-kfn, inv_t, (float)(100.0 / (100.0 - 0.2)));
+					const float dmax_t_dd = kfn * inv_t * inv_t;
+#endif
 					const float len2 = g.n0 * g.n0 + g.n1 * g.n1 + g.n2 * g.n2 + 1e-7f;
 					const float inv_len = GOF_BWD_IEEE_RCP ? __frcp_rn(sqrtf(len2)) : rsqrt_approx(len2);
 					const float nn[3] = { -g.n0 * inv_len, -g.n1 * inv_len, -g.n2 * inv_len };
