@@ -45,6 +45,9 @@ __device__ __forceinline__ void red_global_v4(float* addr, float4 v)
 
 // 1/x for a float x to ~44 bits: one MUFU.RCP (<= 1 ulp) + one Newton step in double (2 DFMA instead of an IEEE
 // double division; only used for gradient VALUES, never for alpha / the contributing set).
+#ifndef GOF_BWD_F32_QUADRIC
+#define GOF_BWD_F32_QUADRIC 1     // dL/dA, dL/dB in float32 (0: double, as the reference; no measurable accuracy difference)
+#endif
 #ifndef GOF_BWD_IEEE_RCP
 #define GOF_BWD_IEEE_RCP 0        // 1: the correctly rounded float reciprocal / sqrt sequences (A/B switch)
 #endif
@@ -274,6 +277,13 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 					const float gmy = dL_dG * dG_ddely * ddely_dy;
 
 					const float dL_dmin_value = dL_dG * G * -0.5f;
+#if GOF_BWD_F32_QUADRIC
+					const float ba = (float)(-u);                  // BB / AA (from the forward's double division)
+					const float half_inv_AA = 0.5f * rcp_approx(g.AA);
+					const float dL_dA = __fmaf_rn(dL_dt * ba, half_inv_AA, dL_dmin_value * ba * ba * 0.25f);
+					const float dL_dB = __fmaf_rn(-dL_dt, half_inv_AA, dL_dmin_value * ba * -0.5f);
+					const float dL_dC = dL_dmin_value;
+#else
 					const double ba = -u;                          // BB / AA
 					const double half_inv_AA = 0.5 * rcp_refined(g.AA);
 					double dL_dA = (double)dL_dmin_value * ba * ba * 0.25;
@@ -281,6 +291,7 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 					const double dL_dC = dL_dmin_value;
 					dL_dA += (double)dL_dt * ba * half_inv_AA;
 					dL_dB -= (double)dL_dt * half_inv_AA;
+#endif
 					dL_dn[0] += dL_dA * rx;
 					dL_dn[1] += dL_dA * ry;
 					dL_dn[2] += dL_dA;
