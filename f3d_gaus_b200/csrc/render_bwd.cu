@@ -201,13 +201,17 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 				const uint32_t j = jbase + bit;
 				const uint32_t r = rec + j * SLAB_BYTES;
 				const float4 k1 = lds128(r + 16), k2 = lds128(r + 32), k3 = lds128(r + 48), k4 = lds128(r + 64);
+				// the Gaussian's id and its 2-D mean / conic (two dependent L2 round trips) are requested before the exact
+				// evaluation so that they are in flight during its double division; nearly every survivor needs them
+				const uint32_t contributor = base + j;       // 0-based position in the tile list
+				const int gid = (int)__ldg(&tile_ids[contributor]);
+				const float2 xy = __ldg(&means2D[gid]);
+				const float4 con = __ldg(&conic_opacity[gid]);
 				const PairGeom g = pair_geom(k1, k2, k3, rx, ry);
 				const float w = k1.z;
 				float t, alpha, G;
 				double u;                                       // -BB/AA, from the forward's own double division
 				if (pair_alpha_exact(g, k4.x, w, t, alpha, G, u)) {
-					const uint32_t contributor = base + j;   // 0-based position in the tile list
-					const int gid = (int)__ldg(&tile_ids[contributor]);
 					// Gradient arithmetic: the reference spends ~8 double and ~8 float divisions per pair here
 					// (backward.cu:843-925).  The contributing SET and alpha, T are bit-exact (shared with the
 					// forward); the gradient VALUES only have to meet the 1e-3 relative bar, so each group of
@@ -267,8 +271,6 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 					dL_dalpha += (-T_final * inv_1ma) * bg_dot_dpixel;
 
 					const float dL_dG = w * dL_dalpha;
-					const float2 xy = __ldg(&means2D[gid]);
-					const float4 con = __ldg(&conic_opacity[gid]);
 					const float dx = xy.x - (float)px, dy = xy.y - (float)py;
 					const float gdx = G * dx, gdy = G * dy;
 					const float dG_ddelx = -gdx * con.x - gdy * con.y;
