@@ -62,6 +62,13 @@ __device__ __forceinline__ TileRays tile_rays(int tx, int ty, int W, int H, floa
 	return t;
 }
 
+__device__ __forceinline__ float conic_rcp(float x)
+{
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));   // one MUFU.RCP, within 2^-22
+	return r;
+}
+
 // q0 = (Sxx, Sxy, Sxz, Syy), q1 = (Syz, Szz, Bx, By), q2 = (Bz, C, tau, w)
 __device__ __forceinline__ void conic_coefficients(const float4& q0, const float4& q1, const float4& q2,
                                                    const TileRays& t, float* c)
@@ -88,11 +95,16 @@ __device__ __forceinline__ void conic_coefficients(const float4& q0, const float
 	bool ok = (AAlo > 0.0) && (AAc > 0.0) && (tau < 1.0e37);
 	const double dAA = 10.0 * u * Abar, dBB = 5.0 * u * Bbar;
 	ok = ok && (dAA < 0.5 * AAlo);
+	ok = ok && (AAlo > 1.0e-30) && (AAc < 1.0e30);          // float32 reciprocals below stay finite and normal
 	const double AAl = ok ? AAlo : 1.0;
-	// |q_ref - q*| for q = BB^2/(4 AA), |BB| <= 2 bmax, AA >= AAl, perturbed by (dBB, dAA): exact, not first order
-	const double E_bb = (bmax * dBB + 0.25 * dBB * dBB) / AAl;
-	const double Qp = (bmax + 0.5 * dBB) * (bmax + 0.5 * dBB) / AAl;
-	const double E_aa = Qp * dAA / (AAl - (ok ? dAA : 0.0));
+	// |q_ref - q*| for q = BB^2/(4 AA), |BB| <= 2 bmax, AA >= AAl, perturbed by (dBB, dAA): exact, not first order.
+	// The bounds only have to be UPPER bounds, so the divisions are one float32 reciprocal of AAl rounded up by
+	// 2^-20 (MUFU.RCP is within 2^-22) and 1/(1-x) <= 1 + 2x for x = dAA/AAl < 0.5.
+	const double rAAl = (double)conic_rcp((float)AAl) * (1.0 + 9.5367431640625e-07);
+	const double E_bb = (bmax * dBB + 0.25 * dBB * dBB) * rAAl;
+	const double Qp = (bmax + 0.5 * dBB) * (bmax + 0.5 * dBB) * rAAl;
+	const double xa = (ok ? dAA : 0.0) * rAAl;
+	const double E_aa = Qp * xa * (1.0 + 2.0 * xa);
 	const double E = 1.25 * (E_bb + E_aa) + t.rel_extra * Qp;
 	const double K = C - (tau + E);
 
@@ -102,7 +114,8 @@ __device__ __forceinline__ void conic_coefficients(const float4& q0, const float
 	const double a_x = 2.0 * t.ax * (Sxx * t.bx + Sxy * t.by + Sxz);
 	const double a_y = 2.0 * t.ay * (Syy * t.by + Sxy * t.bx + Syz);
 	const double a_0 = Sxx * t.bx * t.bx + 2.0 * Sxy * t.bx * t.by + Syy * t.by * t.by + 2.0 * Sxz * t.bx + 2.0 * Syz * t.by + Szz;
-	const double inv = 1.0 / (ok ? AAc : 1.0);
+	// any positive common scale leaves the sign of g unchanged: 1/AAc only normalises the magnitudes for float32
+	const double inv = (double)conic_rcp((float)(ok ? AAc : 1.0));
 	const double c0 = (r0 * r0 - K * a_0) * inv;
 	const double c1 = (2.0 * p * r0 - K * a_x) * inv;
 	const double c2 = (2.0 * q * r0 - K * a_y) * inv;
