@@ -151,23 +151,26 @@ __device__ __forceinline__ void conic_coefficients(const float4& q0, const float
 //     g(x, y) <= g(c) + |g_x(c)| hx + |g_y(c)| hy + max(c3,0) hx^2 + |c4| hx hy + max(c5,0) hy^2 =: U,
 // and the blend's float32 evaluation exceeds the exact polynomial by at most eta (see conic_coefficients), so
 // U + eta < 0 proves that the whole block rejects the record.  `pad` widens the block for sub-pixel rays.
-__device__ __forceinline__ uint32_t conic_block_mask(const float* c, double pad)
+__device__ __forceinline__ uint32_t conic_block_mask(const float* c, double pad_d)
 {
-	const double c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4], c5 = c[5];
-	if (!(c0 < 1.0e30)) return 0xffu;                  // "never skip" records (and NaNs) stay relevant everywhere
-	const double m = 15.0 + pad;
-	const double eta = 16.0 * 5.9604644775390625e-08 *
-	                   (fabs(c0) + m * (fabs(c1) + fabs(c2)) + m * m * (fabs(c3) + fabs(c4) + fabs(c5)));
-	const double hx = 3.5 + pad, hy = 1.5 + pad;
-	const double quad = fmax(c3, 0.0) * hx * hx + fabs(c4) * hx * hy + fmax(c5, 0.0) * hy * hy + eta;
+	// Evaluated in float32: U is built from ~30 roundings of partial sums that are all below 3 * mag, i.e. within
+	// 90 u mag of its exact value; together with the blend's own evaluation error (16 u mag) the margin is 144 u mag.
+	const float c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4], c5 = c[5];
+	if (!(c0 < 1.0e30f)) return 0xffu;                 // "never skip" records (and NaNs) stay relevant everywhere
+	const float pad = (float)pad_d;
+	const float m = 15.0f + pad;
+	const float mag = fabsf(c0) + m * (fabsf(c1) + fabsf(c2)) + m * m * (fabsf(c3) + fabsf(c4) + fabsf(c5));
+	const float eta = 144.0f * 5.9604644775390625e-08f * mag;
+	const float hx = 3.5f + pad, hy = 1.5f + pad;
+	const float quad = fmaxf(c3, 0.0f) * hx * hx + fabsf(c4) * hx * hy + fmaxf(c5, 0.0f) * hy * hy + eta;
 	uint32_t mask = 0;
 #pragma unroll
 	for (int b = 0; b < 8; b++) {
-		const double cx = 8.0 * (b & 1) + 3.5, cy = 4.0 * (b >> 1) + 1.5;
-		const double gc = c0 + cx * (c1 + c3 * cx + c4 * cy) + cy * (c2 + c5 * cy);
-		const double gx = c1 + 2.0 * c3 * cx + c4 * cy, gy = c2 + c4 * cx + 2.0 * c5 * cy;
-		const double U = gc + fabs(gx) * hx + fabs(gy) * hy + quad;
-		if (!(U < 0.0)) mask |= 1u << b;
+		const float cx = 8.0f * (b & 1) + 3.5f, cy = 4.0f * (b >> 1) + 1.5f;
+		const float gc = c0 + cx * (c1 + c3 * cx + c4 * cy) + cy * (c2 + c5 * cy);
+		const float gx = c1 + 2.0f * c3 * cx + c4 * cy, gy = c2 + c4 * cx + 2.0f * c5 * cy;
+		const float U = gc + fabsf(gx) * hx + fabsf(gy) * hy + quad;
+		if (!(U < 0.0f)) mask |= 1u << b;
 	}
 	return mask;
 }
