@@ -301,7 +301,10 @@ __device__ __forceinline__ void preprocess_one(const int idx, int P, int D, int 
 	uint32_t* __restrict__ tiles_touched, ushort4* __restrict__ rects, uint32_t* s_hist, uint32_t* __restrict__ tile_counts,
 	bool prefiltered);
 
-__global__ void __launch_bounds__(PRE_THREADS)
+#ifndef GOF_PRE_MIN_CTAS
+#define GOF_PRE_MIN_CTAS 4        // 64 registers, 4 CTAs per SM: 40 us against 44 us at 3 (8 views x 65 536 Gaussians)
+#endif
+__global__ void __launch_bounds__(PRE_THREADS, GOF_PRE_MIN_CTAS)
 preprocess_kernel(int P, int D, int M,
 	const float* __restrict__ means3D, const float* __restrict__ scales, const float scale_modifier,
 	const float* __restrict__ rotations, const float* __restrict__ opacities, const float* __restrict__ shs,
