@@ -521,6 +521,14 @@ def preprocess_backward_stage(c_means3D, radii, sh, scales, rotations, viewmatri
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                         view2gaussian_precomp, raster_settings):
+    if not torch.is_grad_enabled() and not raster_settings.debug:
+        # inference (the render loops run under no_grad): same call without the autograd.Function round trip
+        rs = raster_settings
+        _, color, radii, _, _, _ = _C.rasterize_gaussians(
+            rs.bg, means3D, colors_precomp, opacities, scales, rotations, rs.scale_modifier, cov3Ds_precomp,
+            view2gaussian_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.kernel_size,
+            rs.subpixel_offset, rs.image_height, rs.image_width, sh, rs.sh_degree, rs.campos, rs.prefiltered, rs.debug)
+        return color, radii
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
                                      cov3Ds_precomp, view2gaussian_precomp, raster_settings)
 
@@ -598,8 +606,11 @@ class GaussianRasterizationSettings_GOF(NamedTuple):
     debug: bool
 
 
+_ABSENT = torch.Tensor([])          # the reference's "not provided" sentinel (numel() == 0); never written to
+
+
 def _absent() -> torch.Tensor:
-    return torch.Tensor([])
+    return _ABSENT
 
 
 class GaussianRasterizer_GOF(nn.Module):

@@ -97,11 +97,14 @@ def render_predicted_more_v2_gof(pc: dict, bs, world_view_transform, full_proj_t
     """Render scene `bs` of the predicted Gaussian dict `pc` (reference :915-1067)."""
     xyz = pc["xyz"][bs]
     device = xyz.device
-    screenspace_points = torch.zeros_like(xyz, dtype=pc["xyz"].dtype, requires_grad=True, device=device) + 0
-    try:
-        screenspace_points.retain_grad()
-    except Exception:
-        pass
+    if torch.is_grad_enabled():
+        screenspace_points = torch.zeros_like(xyz, dtype=pc["xyz"].dtype, requires_grad=True, device=device) + 0
+        try:
+            screenspace_points.retain_grad()
+        except Exception:
+            pass
+    else:
+        screenspace_points = torch.zeros_like(xyz)          # no graph to retain a gradient in
 
     fov = cfg['model']['fov']
     tanfovx = math.tan(fov * np.pi / 360)
