@@ -109,6 +109,16 @@ def load(path: str = LIB_PATH) -> ctypes.CDLL:
 lib = load()
 
 
+def raw_stream(device) -> int:
+    """cudaStream_t of torch's current stream on `device` (the hot-path form of
+    torch.cuda.current_stream(device).cuda_stream: no Stream object is built)."""
+    import torch
+    try:
+        return torch._C._cuda_getCurrentRawStream(device.index if device.index is not None else torch.cuda.current_device())
+    except AttributeError:                      # private helper not present in this torch build
+        return torch.cuda.current_stream(device).cuda_stream
+
+
 def last_error() -> str:
     msg = lib.gof_last_error()
     return msg.decode() if msg else ""

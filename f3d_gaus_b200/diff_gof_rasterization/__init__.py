@@ -101,7 +101,7 @@ class _CModule:
         M = int(sh.size(1)) if (sh is not None and sh.numel() != 0 and sh.size(0) != 0) else 0
         keep: list = []
         with torch.cuda.device(device):
-            stream = torch.cuda.current_stream(device).cuda_stream
+            stream = _lib.raw_stream(device)
             byte_opts = dict(dtype=torch.uint8, device=device)
             if P == 0:
                 out_color = torch.zeros((_lib.OUTPUT_CHANNELS, H, W), dtype=torch.float32, device=device)
@@ -152,7 +152,7 @@ class _CModule:
         dL_dcov3D, dL_dsh, dL_dscales, dL_drotations, dL_dv2g = e(P, 6), e(P, M, 3), e(P, 3), e(P, 4), e(P, 10)
         keep: list = []
         with torch.cuda.device(device):
-            stream = torch.cuda.current_stream(device).cuda_stream
+            stream = _lib.raw_stream(device)
             prm = _lib.GofParams(P, int(degree), M, W, H, float(tan_fovx), float(tan_fovy), float(kernel_size),
                                  float(scale_modifier), 0, int(bool(debug)), _lib.default_flags())
             inp = _lib.GofInputs(
@@ -187,7 +187,7 @@ class _CModule:
             with torch.cuda.device(device):
                 rc = _lib.lib.gof_mark_visible(P, _dev_ptr(means3D, device, keep), _dev_ptr(viewmatrix, device, keep),
                                                _dev_ptr(projmatrix, device, keep), present.data_ptr(),
-                                               torch.cuda.current_stream(device).cuda_stream)
+                                               _lib.raw_stream(device))
             _lib.check(rc, "mark_visible")
         return present
 
@@ -219,7 +219,7 @@ class _CModule:
             return NumRendered(0), out_color, out_alpha, out_rgb, radii, empty, empty.clone(), empty.clone()
         keep: list = []
         with torch.cuda.device(device):
-            stream = torch.cuda.current_stream(device).cuda_stream
+            stream = _lib.raw_stream(device)
             gsz, isz, bsz = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
             _lib.check(_lib.lib.gof_state_sizes(P, W, H, 0, ctypes.byref(gsz), ctypes.byref(isz), ctypes.byref(bsz)),
                        "gof_state_sizes")
@@ -321,7 +321,7 @@ def rasterize_views(background, means3D, colors, opacity, scales, rotations, sca
     keep: list = []
     f32 = dict(dtype=torch.float32, device=device)
     with torch.cuda.device(device):
-        stream = torch.cuda.current_stream(device).cuda_stream
+        stream = _lib.raw_stream(device)
         if out_color is None:
             out_color = torch.empty((V, _lib.OUTPUT_CHANNELS, H, W), **f32)
         if P == 0:
@@ -426,7 +426,7 @@ class _RasterizeViews(torch.autograd.Function):
                 _lib.context(device.index), ctypes.byref(prm), ctypes.byref(inp), V,
                 3 if (bgf.numel() == 3 * V and V > 1) else 0, ctx.num_rendered, _dev_ptr(radii, device, keep, torch.int32),
                 geom.data_ptr(), binning.data_ptr() if binning.numel() else None, img.data_ptr(),
-                _dev_ptr(grad_color, device, keep), ctypes.byref(grads), torch.cuda.current_stream(device).cuda_stream)
+                _dev_ptr(grad_color, device, keep), ctypes.byref(grads), _lib.raw_stream(device))
             _lib.check(rc, "rasterize_views backward")
         has = lambda t: t is not None and t.numel() != 0
         return (gm3, g2d, gsh if has(sh) else None, gcol if has(colors_precomp) else None, gop.reshape(-1, 1),
@@ -464,7 +464,7 @@ def state_array_batch(name: str, P: int, W: int, H: int, V: int, R: int, geom, b
         n = _lib.lib.gof_state_get_batch(name.encode(), P, W, H, V, R, geom.data_ptr(),
                                          binning.data_ptr() if binning.numel() else None, img.data_ptr(),
                                          out.data_ptr() if out.numel() else None, out.numel() * out.element_size(),
-                                         torch.cuda.current_stream(device).cuda_stream)
+                                         _lib.raw_stream(device))
     if n < 0:
         raise RuntimeError(f"gof_state_get_batch({name}) failed: {_lib.last_error()}")
     return out
@@ -487,7 +487,7 @@ def state_array(name: str, P: int, W: int, H: int, R: int, geom, binning, img):
         n = _lib.lib.gof_state_get(name.encode(), P, W, H, R, geom.data_ptr(),
                                    binning.data_ptr() if binning.numel() else None, img.data_ptr(),
                                    out.data_ptr() if out.numel() else None, out.numel() * out.element_size(),
-                                   torch.cuda.current_stream(device).cuda_stream)
+                                   _lib.raw_stream(device))
     if n < 0:
         raise RuntimeError(f"gof_state_get({name}) failed: {_lib.last_error()}")
     return out
@@ -514,7 +514,7 @@ def preprocess_backward_stage(c_means3D, radii, sh, scales, rotations, viewmatri
         rc = _lib.lib.gof_preprocess_backward(
             _lib.context(device.index), ctypes.byref(prm), ctypes.byref(inp), _dev_ptr(radii, device, keep, torch.int32),
             geom.data_ptr(), _dev_ptr(dL_dview2gaussian, device, keep), _dev_ptr(dL_dcolors, device, keep),
-            ctypes.byref(grads), torch.cuda.current_stream(device).cuda_stream)
+            ctypes.byref(grads), _lib.raw_stream(device))
         _lib.check(rc, "gof_preprocess_backward")
     return gm3, gsh, gsc, grot
 

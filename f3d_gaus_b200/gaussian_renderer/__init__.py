@@ -77,7 +77,7 @@ def fused_epilogue(rendered_image, world_view_transform, W, H, FovX, FovY):
     with torch.cuda.device(dev):
         rc = _lib.lib.gof_render_epilogue(img.data_ptr(), vm.data_ptr(), W, H, ctypes.c_float(FovX),
                                           ctypes.c_float(FovY), normal_world.data_ptr(), depth_normal.data_ptr(),
-                                          torch.cuda.current_stream(dev).cuda_stream)
+                                          _lib.raw_stream(dev))
     _lib.check(rc, "gof_render_epilogue")
     return normal_world, depth_normal
 
@@ -227,7 +227,7 @@ def render_views(pc: dict, bs, world_view_transforms, full_proj_transforms, came
                 rc = _lib.lib.gof_render_epilogue_batch(raster.data_ptr(), vm.data_ptr(), V, W, H, ctypes.c_float(Fov),
                                                         ctypes.c_float(Fov), normal_world.data_ptr(),
                                                         depth_normal.data_ptr(),
-                                                        torch.cuda.current_stream(device).cuda_stream)
+                                                        _lib.raw_stream(device))
             _lib.check(rc, "gof_render_epilogue_batch")
             out["rendered_normal"], out["depth_normal"] = normal_world, depth_normal
     return out
