@@ -127,3 +127,34 @@ def test_ply_export_roundtrip(tmp_path):
     assert np.array_equal(back["x"], xyz[:, 0].numpy()) and np.array_equal(back["rot_3"], rot[:, 3].numpy())
     assert np.array_equal(back["opacity"], opac[:, 0].numpy()) and np.array_equal(back["scale_1"], scale[:, 1].numpy())
     assert not back["nx"].any() and not back["f_rest_44"].any()
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """The ctypes mirrors of the ABI structs (_lib.py) have the size and field offsets the C compiler gives the
+    declarations in include/gof_b200.h (the header must also compile as plain C)."""
+    import shutil
+    import subprocess
+    from f3d_gaus_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    structs = {"GofParams": _lib.GofParams, "GofInputs": _lib.GofInputs, "GofGrads": _lib.GofGrads,
+               "GofHeadParams": _lib.GofHeadParams}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gof_b200.h"', 'int main(void) {']
+    for name, cls in structs.items():
+        lines.append(f'printf("{name} %zu", sizeof({name}));')
+        for field, _ in cls._fields_:
+            lines.append(f'printf(" %zu", offsetof({name}, {field}));')
+        lines.append('printf("\\n");')
+    lines += ['return 0; }']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)],
+                   check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    for line in filter(None, out):
+        name, size, *offsets = line.split()
+        cls = structs[name]
+        assert ctypes.sizeof(cls) == int(size), name
+        assert [getattr(cls, f).offset for f, _ in cls._fields_] == [int(o) for o in offsets], name
