@@ -70,8 +70,8 @@ SIGNATURES = {
     "gof_forward_batch": (c_int32, [c_void_p, POINTER(GofParams), POINTER(GofInputs), c_int32, c_int32, c_void_p, c_size_t,
                                     c_void_p, c_size_t, c_void_p, c_size_t, ALLOC_FN, c_void_p, c_void_p, c_void_p,
                                     POINTER(c_int32), POINTER(c_void_p), c_void_p]),
-    "gof_state_get_batch": (c_int64, [c_char_p, c_int32, c_int32, c_int32, c_int32, c_int64, c_void_p, c_void_p, c_void_p,
-                                      c_void_p, c_int64, c_void_p]),
+    "gof_state_get_batch": (c_int64, [c_char_p, c_int32, c_int32, c_int32, c_int32, c_int64, c_void_p, c_void_p, c_size_t,
+                                      c_void_p, c_void_p, c_int64, c_void_p]),
     "gof_integrate": (c_int32, [c_void_p, POINTER(GofParams), POINTER(GofInputs), c_int32, c_void_p, c_void_p, c_size_t,
                                 c_void_p, c_size_t, ALLOC_FN, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 POINTER(c_int32), c_void_p]),
@@ -79,16 +79,16 @@ SIGNATURES = {
     "gof_set_frame_sink": (c_int32, [c_void_p, c_void_p, c_size_t, c_int32]),
     "gof_num_rendered": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, POINTER(c_int32)]),
     "gof_backward": (c_int32, [c_void_p, POINTER(GofParams), POINTER(GofInputs), c_int32, c_void_p,
-                               c_void_p, c_void_p, c_void_p, c_void_p, POINTER(GofGrads), c_void_p]),
+                               c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, POINTER(GofGrads), c_void_p]),
     "gof_backward_batch": (c_int32, [c_void_p, POINTER(GofParams), POINTER(GofInputs), c_int32, c_int32, c_int64, c_void_p,
-                                     c_void_p, c_void_p, c_void_p, c_void_p, POINTER(GofGrads), c_void_p]),
+                                     c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, POINTER(GofGrads), c_void_p]),
     "gof_preprocess_backward": (c_int32, [c_void_p, POINTER(GofParams), POINTER(GofInputs), c_void_p, c_void_p,
                                           c_void_p, c_void_p, POINTER(GofGrads), c_void_p]),
     "gof_mark_visible": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gof_render_epilogue": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "gof_render_epilogue_batch": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "gof_pack_gather": (c_int32, [c_void_p, c_int32, c_int64, c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
-    "gof_state_get": (c_int64, [c_char_p, c_int32, c_int32, c_int32, c_int64, c_void_p, c_void_p, c_void_p,
+    "gof_state_get": (c_int64, [c_char_p, c_int32, c_int32, c_int32, c_int64, c_void_p, c_void_p, c_size_t, c_void_p,
                                 c_void_p, c_int64, c_void_p]),
 }
 

@@ -5,9 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
-#include <mutex>
 #include <string>
-#include <unordered_map>
 #include <vector>
 
 namespace gof {
@@ -155,25 +153,6 @@ int gof_state_sizes(int32_t P, int32_t W, int32_t H, int64_t num_rendered,
 
 static char* align_base(const void* p) { return reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(p))); }
 
-// The binning blob's layout depends on the capacity it was carved for, which is >= num_rendered when the blob
-// was allocated speculatively.  Forward remembers the capacity per blob address (the latest forward that used an
-// address wins, so allocator reuse is harmless); backward and the test accessor look it up and fall back to
-// num_rendered, the exact-size layout.
-static std::mutex g_cap_mu;
-static std::unordered_map<const void*, int64_t> g_bin_caps;
-static void remember_capacity(const void* blob, int64_t cap)
-{
-	std::lock_guard<std::mutex> lk(g_cap_mu);
-	if (g_bin_caps.size() > 8192) g_bin_caps.clear();
-	g_bin_caps[blob] = cap;
-}
-static int64_t lookup_capacity(const void* blob, int64_t num_rendered)
-{
-	std::lock_guard<std::mutex> lk(g_cap_mu);
-	auto it = g_bin_caps.find(blob);
-	return (it != g_bin_caps.end() && it->second >= num_rendered) ? it->second : num_rendered;
-}
-
 // Largest R whose binning layout fits in `bytes` (host arithmetic only).
 static int64_t binning_capacity(size_t bytes)
 {
@@ -183,6 +162,17 @@ static int64_t binning_capacity(size_t bytes)
 		if (BinState::carve(nullptr, (size_t)mid).total <= bytes) lo = mid; else hi = mid;
 	}
 	return lo;
+}
+
+// The binning blob's layout is a pure function of (address, byte size): the capacity it is carved for is the
+// largest R that fits.  Forward, backward and the test accessor all derive it this way, so a blob that was
+// allocated speculatively (capacity > num_rendered) is decoded identically by every later call that is handed
+// the same tensor -- no per-process side table, nothing to go stale between a forward and its backward.
+static int64_t blob_capacity(const void* blob, size_t bytes)
+{
+	if (!blob) return 0;
+	const size_t skew = (size_t)(align_base(blob) - (const char*)blob);
+	return bytes > skew ? binning_capacity(bytes - skew) : 0;
 }
 
 int gof_set_frame_sink(GofContext* ctx, void* sink, size_t sink_bytes, int32_t layout)
@@ -277,13 +267,11 @@ int gof_forward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* in
 	BinState b;
 	if (binning != nullptr) {
 		// sync-free mode: capacity is whatever fits in the caller's blob; R stays on the device
-		const size_t skew = (size_t)(align_base(binning) - (char*)binning);
-		capacity = binning_bytes > skew ? binning_capacity(binning_bytes - skew) : 0;
+		capacity = blob_capacity(binning, binning_bytes);
 		if ((rc = launch_tile_scan(f, g, im, capacity, s)) != GOF_OK) return rc;
 		GOF_STAGE_CHECK(prm, s);
 		GOF_PROF_MARK(ctx, marks, s);
 		b = BinState::carve(align_base(binning), (size_t)capacity);
-		remember_capacity(binning, capacity);
 		if (num_rendered) for (int v = 0; v < V; v++) num_rendered[v] = -1;
 	} else {
 		if (!alloc) { set_error("gof_forward: neither a binning blob nor an allocation callback"); return GOF_EINVAL; }
@@ -293,10 +281,10 @@ int gof_forward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* in
 			// Speculative hand-off: allocate the binning blob for 1.25x the previous call's num_rendered and enqueue
 			// EVERYTHING before waiting for R, so the GPU never idles behind the host round trip of the reference's
 			// protocol (rasterizer_impl.cu:336-340).  The host still returns R as soon as the scan has finished.
-			capacity = ctx->spec_capacity;
-			const size_t need = BinState::carve(nullptr, (size_t)capacity).total;
+			const size_t need = BinState::carve(nullptr, (size_t)ctx->spec_capacity).total;
 			void* blob = alloc(alloc_user, need);
 			if (!blob) { set_error("gof_forward: binning allocation callback returned NULL for %zu bytes", need); return GOF_ENOMEM; }
+			capacity = blob_capacity(blob, need);          // the layout every later call derives from (blob, need)
 			b = BinState::carve(align_base(blob), (size_t)capacity);
 			if ((rc = launch_tile_scan(f, g, im, capacity, s)) != GOF_OK) return rc;
 			GOF_PROF_MARK(ctx, marks, s);
@@ -313,7 +301,6 @@ int gof_forward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* in
 			if (!ctx->pinned[1]) {
 				if (num_rendered) for (int v = 0; v < V; v++) num_rendered[v] = ctx->pinned[MAILBOX_HEAD + v];
 				if (binning_out) *binning_out = blob;
-				remember_capacity(blob, capacity);
 				if (ctx->profiling) ctx->calls[0].push_back(std::move(marks));
 				return GOF_OK;
 			}
@@ -327,15 +314,15 @@ int gof_forward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* in
 			GOF_PROF_MARK(ctx, marks, s);
 			GOF_CUDA_CHECK(cudaMemcpyAsync(ctx->pinned, g.mailbox, (MAILBOX_HEAD + V) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
 			GOF_CUDA_CHECK(cudaStreamSynchronize(s));
-			capacity = ctx->pinned[0];
-			ctx->spec_capacity = capacity + capacity / 4 + 4096;
+			const int64_t R = ctx->pinned[0];
+			ctx->spec_capacity = R + R / 4 + 4096;
 			if (num_rendered) for (int v = 0; v < V; v++) num_rendered[v] = ctx->pinned[MAILBOX_HEAD + v];
-			const size_t need = BinState::carve(nullptr, (size_t)capacity).total;
+			const size_t need = BinState::carve(nullptr, (size_t)R).total;
 			void* blob = alloc(alloc_user, need);
 			if (!blob) { set_error("gof_forward: binning allocation callback returned NULL for %zu bytes", need); return GOF_ENOMEM; }
 			if (binning_out) *binning_out = blob;
+			capacity = blob_capacity(blob, need);
 			b = BinState::carve(align_base(blob), (size_t)capacity);
-			remember_capacity(blob, capacity);
 		}
 	}
 
@@ -427,7 +414,7 @@ static int ensure_gacc(GofContext* ctx, size_t need, cudaStream_t s);
 
 int gof_backward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* in, int32_t V, int32_t bg_stride,
                        int64_t num_rendered, const int32_t* radii,
-                       const void* geom, const void* binning, const void* img,
+                       const void* geom, const void* binning, size_t binning_bytes, const void* img,
                        const float* dL_dout_color, const GofGrads* gr, gof_stream_t stream)
 {
 	if (!ctx || !prm || !in || !gr) { set_error("gof_backward: NULL argument"); return GOF_EINVAL; }
@@ -447,7 +434,12 @@ int gof_backward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* i
 	BinState b{};
 	if (num_rendered > 0) {
 		if (!binning) { set_error("gof_backward: binning blob is NULL but num_rendered=%lld", (long long)num_rendered); return GOF_EINVAL; }
-		b = BinState::carve(align_base(binning), (size_t)lookup_capacity(binning, num_rendered));
+		const int64_t cap = blob_capacity(binning, binning_bytes);
+		if (cap < num_rendered) {
+			set_error("gof_backward: binning blob of %zu bytes holds %lld duplicates, num_rendered=%lld", binning_bytes, (long long)cap, (long long)num_rendered);
+			return GOF_ENOMEM;
+		}
+		b = BinState::carve(align_base(binning), (size_t)cap);
 	}
 
 	const size_t need = (size_t)P * V * GACC_FLOATS;
@@ -471,10 +463,10 @@ int gof_backward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* i
 
 int gof_backward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
                  int32_t num_rendered, const int32_t* radii,
-                 const void* geom, const void* binning, const void* img,
+                 const void* geom, const void* binning, size_t binning_bytes, const void* img,
                  const float* dL_dout_color, const GofGrads* gr, gof_stream_t stream)
 {
-	return gof_backward_batch(ctx, prm, in, 1, 0, num_rendered, radii, geom, binning, img, dL_dout_color, gr, stream);
+	return gof_backward_batch(ctx, prm, in, 1, 0, num_rendered, radii, geom, binning, binning_bytes, img, dL_dout_color, gr, stream);
 }
 
 // ---- stage entry: per-Gaussian backward (K10) on its own -------------------------------------
@@ -516,7 +508,7 @@ int gof_preprocess_backward(GofContext* ctx, const GofParams* prm, const GofInpu
 
 // ---- test accessor ---------------------------------------------------------------------------
 int64_t gof_state_get_batch(const char* name, int32_t P, int32_t W, int32_t H, int32_t V, int64_t R,
-                            const void* geom, const void* binning, const void* img,
+                            const void* geom, const void* binning, size_t binning_bytes, const void* img,
                             void* dst, int64_t dst_bytes, gof_stream_t stream)
 {
 	if (!name) { set_error("gof_state_get: NULL name"); return GOF_EINVAL; }
@@ -528,7 +520,9 @@ int64_t gof_state_get_batch(const char* name, int32_t P, int32_t W, int32_t H, i
 	const size_t N = (size_t)W * H, n = (size_t)P * V, VT = (size_t)V * f.T;
 	GeomState g = GeomState::carve(align_base(geom), (size_t)P, (size_t)V);
 	ImgState im = ImgState::carve(align_base(img), N, (size_t)f.T, (size_t)V);
-	BinState b = BinState::carve(align_base(binning), (size_t)lookup_capacity(binning, R));
+	const int64_t cap = blob_capacity(binning, binning_bytes);
+	if (cap < R) { set_error("gof_state_get: binning blob of %zu bytes holds %lld duplicates, num_rendered=%lld", binning_bytes, (long long)cap, (long long)R); return GOF_ENOMEM; }
+	BinState b = BinState::carve(align_base(binning), (size_t)cap);
 	const std::string nm(name);
 	const void* src = nullptr;
 	size_t bytes = 0;
@@ -561,10 +555,10 @@ int64_t gof_state_get_batch(const char* name, int32_t P, int32_t W, int32_t H, i
 }
 
 int64_t gof_state_get(const char* name, int32_t P, int32_t W, int32_t H, int64_t R,
-                      const void* geom, const void* binning, const void* img,
+                      const void* geom, const void* binning, size_t binning_bytes, const void* img,
                       void* dst, int64_t dst_bytes, gof_stream_t stream)
 {
-	return gof_state_get_batch(name, P, W, H, 1, R, geom, binning, img, dst, dst_bytes, stream);
+	return gof_state_get_batch(name, P, W, H, 1, R, geom, binning, binning_bytes, img, dst, dst_bytes, stream);
 }
 
 // ---- pack + all-gather over peer memory -----------------------------------------------------------

@@ -133,9 +133,11 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 	const size_t N = (size_t)W * H;
 
 	const uint2 range = ranges[gt];
-	// sync-free mode: if the binning blob was too small nothing was binned -- blend empty lists (the
-	// caller sees the overflow flag in the mailbox and re-runs the batch with a larger blob)
-	const int n = mailbox[1] ? 0 : (int)(range.y - range.x);
+	// sync-free mode: if the binning blob was too small nothing was binned -- no list is walked and every
+	// output of the batch is POISONED with NaN, so that a caller who never reads the overflow flag
+	// (gof_num_rendered / BatchWorkspace.finish) cannot mistake the batch for background-only frames
+	const bool overflow = mailbox[1] != 0;
+	const int n = overflow ? 0 : (int)(range.y - range.x);
 	const int nchunks = (n + CHUNK - 1) / CHUNK;
 	const float* tile_slab = slab + (size_t)range.x * SLAB_FLOATS;
 
@@ -271,6 +273,12 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 		if (lane == 0) mbar_arrive(&s_empty[s]);   // this warp is finished with stage s
 	}
 
+	if (overflow) {
+		const float poison = __int_as_float(0x7fc00000);
+#pragma unroll
+		for (int k = 0; k < 8; k++) st.C[k] = poison;
+		st.distortion = poison;
+	}
 	if (inside) {
 		float* final_T = final_T_all + (size_t)view * 4 * N;
 		uint32_t* n_contrib = n_contrib_all + (size_t)view * 2 * N;

@@ -169,7 +169,7 @@ class _CModule:
                 _lib.context(device.index), ctypes.byref(prm), ctypes.byref(inp), int(R),
                 _dev_ptr(radii, device, keep, torch.int32),
                 geomBuffer.data_ptr(), binningBuffer.data_ptr() if binningBuffer.numel() else None,
-                imageBuffer.data_ptr(), _dev_ptr(dL_dout_color, device, keep), ctypes.byref(grads), stream)
+                binningBuffer.numel(), imageBuffer.data_ptr(), _dev_ptr(dL_dout_color, device, keep), ctypes.byref(grads), stream)
             _lib.check(rc, "rasterize_gaussians_backward")
         return (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations,
                 dL_dv2g)
@@ -256,8 +256,10 @@ class BatchWorkspace:
     With a workspace the forward is SYNC-FREE: the binning blob is a cached buffer (capacity = 1.5x
     the largest batch seen so far) and `num_rendered` stays on the device until `finish()` reads the
     mailbox -- call it after your own synchronisation point (e.g. after the D2H copy of the frames).
-    `finish()` returns the per-view R, or None if the blob was too small for this batch, in which case
-    the buffers have been grown and the caller must re-run the batch (`rasterize_views` does that)."""
+    `finish()` returns the per-view R, or None if the blob was too small for this batch.  In that case
+    every output of the batch (out_color, the frame sink) holds NaN -- never a plausible image --, the
+    workspace has been grown, and the CALLER re-runs the batch (cycle.render_scene_views and
+    HostFrameSink users do; `rasterize_views` itself cannot, it does not synchronise)."""
 
     def __init__(self, device):
         self.device = torch.device(device)
@@ -340,9 +342,8 @@ def rasterize_views(background, means3D, colors, opacity, scales, rotations, sca
             _dev_ptr(colors, device, keep), _dev_ptr(opacity, device, keep), _dev_ptr(scales, device, keep),
             _dev_ptr(rotations, device, keep), None, None, _dev_ptr(viewmatrices.reshape(V, 16), device, keep),
             _dev_ptr(projmatrices.reshape(V, 16), device, keep), _dev_ptr(campos.reshape(V, 3), device, keep))
-        Rv = (ctypes.c_int32 * V)()
-        bin_out = ctypes.c_void_p()
         ctx = _lib.context(device.index)
+        armed = False
         if sink is not None:
             if sink.dtype != torch.float32 or tuple(sink.shape) != (V, _lib.SINK_CHANNELS, H, W) \
                     or not (sink.is_cuda or sink.is_pinned()):
@@ -354,33 +355,46 @@ def rasterize_views(background, means3D, colors, opacity, scales, rotations, sca
             else:
                 raise RuntimeError("sink must be contiguous (NCHW) or channels_last")
             _lib.check(_lib.lib.gof_set_frame_sink(ctx, sink.data_ptr(), sink.numel() * 4, layout), "gof_set_frame_sink")
-        if workspace is None:
-            gsz, isz, bsz = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
-            _lib.check(_lib.lib.gof_state_sizes_batch(P, W, H, V, 0, ctypes.byref(gsz), ctypes.byref(isz),
-                                                      ctypes.byref(bsz)), "gof_state_sizes_batch")
-            byte_opts = dict(dtype=torch.uint8, device=device)
-            geom, img = torch.empty(gsz.value, **byte_opts), torch.empty(isz.value, **byte_opts)
-            holder = {}
+            armed = True
+        try:
+            return _rasterize_views_call(ctx, prm, inp, V, bg_stride, P, W, H, device, stream, out_color, radii, workspace)
+        finally:
+            # the sink is one-shot and consumed by gof_forward_batch; if anything raised before the library got
+            # there (allocation, argument errors), disarm it so that no later forward writes through a stale pointer
+            if armed:
+                _lib.lib.gof_set_frame_sink(ctx, None, 0, 0)
 
-            def _alloc(_user, nbytes):
-                holder["binning"] = torch.empty(int(nbytes), **byte_opts)
-                return holder["binning"].data_ptr()
 
-            rc = _lib.lib.gof_forward_batch(ctx, ctypes.byref(prm), ctypes.byref(inp), V, bg_stride, geom.data_ptr(),
-                                            geom.numel(), img.data_ptr(), img.numel(), None, 0, _lib.ALLOC_FN(_alloc),
-                                            None, out_color.data_ptr(), radii.data_ptr(), Rv, ctypes.byref(bin_out),
-                                            stream)
-            _lib.check(rc, "rasterize_views")
-            binning = holder.get("binning", torch.empty(0, **byte_opts))
-            return [int(x) for x in Rv], out_color, radii, geom, binning, img
-        workspace._ensure(P, W, H, V)
-        rc = _lib.lib.gof_forward_batch(ctx, ctypes.byref(prm), ctypes.byref(inp), V, bg_stride,
-                                        workspace.geom.data_ptr(), workspace.geom.numel(), workspace.img.data_ptr(),
-                                        workspace.img.numel(), workspace.binning.data_ptr(), workspace.binning.numel(),
-                                        _lib.ALLOC_FN(), None, out_color.data_ptr(), radii.data_ptr(), Rv,
-                                        ctypes.byref(bin_out), stream)
+def _rasterize_views_call(ctx, prm, inp, V, bg_stride, P, W, H, device, stream, out_color, radii, workspace):
+    Rv = (ctypes.c_int32 * V)()
+    bin_out = ctypes.c_void_p()
+    if workspace is None:
+        gsz, isz, bsz = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+        _lib.check(_lib.lib.gof_state_sizes_batch(P, W, H, V, 0, ctypes.byref(gsz), ctypes.byref(isz),
+                                                  ctypes.byref(bsz)), "gof_state_sizes_batch")
+        byte_opts = dict(dtype=torch.uint8, device=device)
+        geom, img = torch.empty(gsz.value, **byte_opts), torch.empty(isz.value, **byte_opts)
+        holder = {}
+
+        def _alloc(_user, nbytes):
+            holder["binning"] = torch.empty(int(nbytes), **byte_opts)
+            return holder["binning"].data_ptr()
+
+        rc = _lib.lib.gof_forward_batch(ctx, ctypes.byref(prm), ctypes.byref(inp), V, bg_stride, geom.data_ptr(),
+                                        geom.numel(), img.data_ptr(), img.numel(), None, 0, _lib.ALLOC_FN(_alloc),
+                                        None, out_color.data_ptr(), radii.data_ptr(), Rv, ctypes.byref(bin_out),
+                                        stream)
         _lib.check(rc, "rasterize_views")
-        return None, out_color, radii, workspace.geom, workspace.binning, workspace.img
+        binning = holder.get("binning", torch.empty(0, **byte_opts))
+        return [int(x) for x in Rv], out_color, radii, geom, binning, img
+    workspace._ensure(P, W, H, V)
+    rc = _lib.lib.gof_forward_batch(ctx, ctypes.byref(prm), ctypes.byref(inp), V, bg_stride,
+                                    workspace.geom.data_ptr(), workspace.geom.numel(), workspace.img.data_ptr(),
+                                    workspace.img.numel(), workspace.binning.data_ptr(), workspace.binning.numel(),
+                                    _lib.ALLOC_FN(), None, out_color.data_ptr(), radii.data_ptr(), Rv,
+                                    ctypes.byref(bin_out), stream)
+    _lib.check(rc, "rasterize_views")
+    return None, out_color, radii, workspace.geom, workspace.binning, workspace.img
 
 
 class _RasterizeViews(torch.autograd.Function):
@@ -425,7 +439,7 @@ class _RasterizeViews(torch.autograd.Function):
             rc = _lib.lib.gof_backward_batch(
                 _lib.context(device.index), ctypes.byref(prm), ctypes.byref(inp), V,
                 3 if (bgf.numel() == 3 * V and V > 1) else 0, ctx.num_rendered, _dev_ptr(radii, device, keep, torch.int32),
-                geom.data_ptr(), binning.data_ptr() if binning.numel() else None, img.data_ptr(),
+                geom.data_ptr(), binning.data_ptr() if binning.numel() else None, binning.numel(), img.data_ptr(),
                 _dev_ptr(grad_color, device, keep), ctypes.byref(grads), _lib.raw_stream(device))
             _lib.check(rc, "rasterize_views backward")
         has = lambda t: t is not None and t.numel() != 0
@@ -462,7 +476,7 @@ def state_array_batch(name: str, P: int, W: int, H: int, V: int, R: int, geom, b
     out = torch.empty(spec[1], dtype=spec[0], device=device)
     with torch.cuda.device(device):
         n = _lib.lib.gof_state_get_batch(name.encode(), P, W, H, V, R, geom.data_ptr(),
-                                         binning.data_ptr() if binning.numel() else None, img.data_ptr(),
+                                         binning.data_ptr() if binning.numel() else None, binning.numel(), img.data_ptr(),
                                          out.data_ptr() if out.numel() else None, out.numel() * out.element_size(),
                                          _lib.raw_stream(device))
     if n < 0:
@@ -485,7 +499,7 @@ def state_array(name: str, P: int, W: int, H: int, R: int, geom, binning, img):
     out = torch.empty(spec[1], dtype=spec[0], device=device)
     with torch.cuda.device(device):
         n = _lib.lib.gof_state_get(name.encode(), P, W, H, R, geom.data_ptr(),
-                                   binning.data_ptr() if binning.numel() else None, img.data_ptr(),
+                                   binning.data_ptr() if binning.numel() else None, binning.numel(), img.data_ptr(),
                                    out.data_ptr() if out.numel() else None, out.numel() * out.element_size(),
                                    _lib.raw_stream(device))
     if n < 0:

@@ -61,7 +61,14 @@ class PeerFrameGather:
     consumed channels of this rank's frames and stores them directly into EVERY rank's gather buffer (peer
     pointers of a torch symmetric-memory allocation; one multimem.st per 16 bytes when the NVSwitch multicast
     address exists), then a symmetric-memory barrier publishes them.  Replaces 3 pack copies + all_gather.
-    Needs CUDA + an initialised NCCL process group; `gather_frames` (NCCL / gloo) is the portable path."""
+    Needs CUDA + an initialised NCCL process group; `gather_frames` (NCCL / gloo) is the portable path.
+
+    The gather buffer is DOUBLE-BUFFERED: push k writes slot k % 2.  A rank can only start push k+2 (which
+    overwrites the slot of push k) after it has passed the barrier of push k+1, and every peer reaches that barrier
+    on its stream only after the work it enqueued before it -- including its reads of push k's result.  So a fast
+    rank never stores into a buffer a slower peer is still reading, provided the consumer reads the returned tensor
+    on the stream `push` was called on (or orders its reads before the next push on that stream), and the returned
+    tensor is consumed before the second-next push."""
 
     def __init__(self, num_scenes: int, V: int, H: int, W: int, device, group=None, use_multicast: bool = True):
         import torch.distributed._symmetric_memory as symm_mem
@@ -71,9 +78,13 @@ class PeerFrameGather:
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.shape = (num_scenes, V, GATHER_CHANNELS, H, W)
-        self.buf = symm_mem.empty(self.shape, dtype=torch.float32, device=self.device)
+        self.buf = symm_mem.empty((2,) + self.shape, dtype=torch.float32, device=self.device)
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
-        self.ptrs = torch.tensor([int(p) for p in self.hdl.buffer_ptrs], dtype=torch.int64, device=self.device)
+        self.slot_bytes = self.buf[0].numel() * 4
+        self.slot = 0
+        base = [int(p) for p in self.hdl.buffer_ptrs]
+        self.ptrs = [torch.tensor([p + k * self.slot_bytes for p in base], dtype=torch.int64, device=self.device)
+                     for k in range(2)]
         mc = 0
         try:
             if use_multicast and self.hdl.has_multicast_support(self.device.type, self.device.index or 0):
@@ -88,14 +99,16 @@ class PeerFrameGather:
         num_scenes, V, C, H, W = self.shape
         r = raster.reshape(-1, 9, H * W).contiguous()
         import ctypes
+        k = self.slot
+        self.slot ^= 1
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            rc = self._lib.lib.gof_pack_gather(r.data_ptr(), r.shape[0], H * W, self.ptrs.data_ptr(), self.world,
-                                               ctypes.c_void_p(self.multicast) if self.multicast else None,
+            rc = self._lib.lib.gof_pack_gather(r.data_ptr(), r.shape[0], H * W, self.ptrs[k].data_ptr(), self.world,
+                                               ctypes.c_void_p(self.multicast + k * self.slot_bytes) if self.multicast else None,
                                                first_scene * V, stream)
             self._lib.check(rc, "gof_pack_gather")
             self.hdl.barrier()
-        return self.buf
+        return self.buf[k]
 
 
 def render_sharded(make_scene, num_scenes: int, cams, cfg: dict, background: torch.Tensor, *, rank: int, world: int,

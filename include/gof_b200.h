@@ -153,7 +153,8 @@ int gof_state_sizes_batch(int32_t P, int32_t W, int32_t H, int32_t V, int64_t nu
  *                    requested speculatively (1.25x the previous num_rendered) and all kernels are
  *                    enqueued BEFORE the host waits for R, so the GPU does not idle behind the round
  *                    trip; if the guess was too small the callback is invoked a second time with the
- *                    exact size.  The blob must be passed to gof_backward at the same address.
+ *                    exact size.  The blob must be passed to gof_backward at the same address and with
+ *                    the same byte size (its layout is a function of the two).
  *   out_color      : [9,H,W], radii: [P] int32.  Both fully written.
  *   num_rendered   : host pointer; receives R in the callback mode, -1 in the sync-free mode.
  *   binning_out    : host pointer; receives the binning blob actually used. */
@@ -202,10 +203,12 @@ int gof_set_frame_sink(GofContext* ctx, void* sink, size_t sink_bytes, int32_t l
  * `geom` (or GOF_EOVERFLOW if the binning blob was too small for it). */
 int gof_num_rendered(GofContext* ctx, const void* geom, int32_t P, int32_t V, gof_stream_t stream, int32_t* num_rendered);
 
-/* Backward: replays the blend back-to-front and produces the reference's 9 gradient tensors. */
+/* Backward: replays the blend back-to-front and produces the reference's 9 gradient tensors.
+ * `binning` / `binning_bytes`: the blob the forward returned and its size in bytes (binningBuffer.numel()); the
+ * blob's internal layout is derived from exactly these two values, in forward and backward alike. */
 int gof_backward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
                  int32_t num_rendered, const int32_t* radii,
-                 const void* geom, const void* binning, const void* img,
+                 const void* geom, const void* binning, size_t binning_bytes, const void* img,
                  const float* dL_dout_color /* [9,H,W] */, const GofGrads* grads,
                  gof_stream_t stream);
 
@@ -215,7 +218,7 @@ int gof_backward(GofContext* ctx, const GofParams* prm, const GofInputs* in,
  * had been rendered one by one). */
 int gof_backward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* in, int32_t V, int32_t bg_stride,
                        int64_t num_rendered, const int32_t* radii,
-                       const void* geom, const void* binning, const void* img,
+                       const void* geom, const void* binning, size_t binning_bytes, const void* img,
                        const float* dL_dout_color /* [V,9,H,W] */, const GofGrads* grads, gof_stream_t stream);
 
 /* Stage entry: the per-Gaussian backward alone (BACKWARD::preprocess, backward.cu:957-1033):
@@ -286,12 +289,12 @@ int gof_pack_gather(const float* raster, int32_t frames, int64_t pixels, const i
  * final_T[4,H,W] f32, n_contrib[2,H,W] u32, ranges[T,2] u32, point_list[R] u32,
  * point_list_keys[R] u64.  Returns the byte size (>=0) or a negative error. */
 int64_t gof_state_get(const char* name, int32_t P, int32_t W, int32_t H, int64_t num_rendered,
-                      const void* geom, const void* binning, const void* img,
+                      const void* geom, const void* binning, size_t binning_bytes, const void* img,
                       void* dst, int64_t dst_bytes, gof_stream_t stream);
 /* Same on the state of a V-view batch: per-Gaussian arrays are [V,P,...], per-pixel [V,...,H,W],
  * ranges [V*T,2] (offsets into the batch's list), point_list / point_list_keys [R_total]. */
 int64_t gof_state_get_batch(const char* name, int32_t P, int32_t W, int32_t H, int32_t V, int64_t num_rendered,
-                            const void* geom, const void* binning, const void* img,
+                            const void* geom, const void* binning, size_t binning_bytes, const void* img,
                             void* dst, int64_t dst_bytes, gof_stream_t stream);
 
 #ifdef __cplusplus

@@ -1,7 +1,7 @@
 """2+ GPU check of the fused pack + all-gather over NVLink peer memory (sharding.PeerFrameGather) against the
 NCCL all_gather path, plus timing of both.  Run under torchrun:
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/test_peer_gather.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/peer_gather_check.py
 """
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -29,6 +29,16 @@ for mc in (False, True):
     got = pg.push(raster, first_scene=rank)
     torch.cuda.synchronize()
     ok = torch.equal(got, want)
+    # write-after-read across steps: a rank that races ahead must not overwrite frames a slower peer is still
+    # reading.  Rank 0 is slowed down by a long-running kernel between "consume step k" and "push step k+1".
+    for step in range(6):
+        scaled = raster * float(step + 2)
+        g = pg.push(scaled, first_scene=rank)
+        if rank == 0:
+            torch.cuda._sleep(20_000_000)                 # ~10 ms of device time before the consumer reads
+        snap = g.clone()                                   # the consumer's read, stream-ordered after the push
+        ok = ok and torch.equal(snap, want * float(step + 2))   # (no collective here: the ranks must be free to drift)
+    torch.cuda.synchronize()
     def t(fn, n=50):
         for _ in range(5): fn()
         torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
