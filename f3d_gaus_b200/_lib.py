@@ -87,7 +87,10 @@ SIGNATURES = {
     "gof_mark_visible": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gof_render_epilogue": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "gof_render_epilogue_batch": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    "gof_render_epilogue_backward_batch": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_float, c_void_p,
+                                                     c_void_p, c_void_p, c_void_p]),
     "gof_pack_gather": (c_int32, [c_void_p, c_int32, c_int64, c_void_p, c_int32, c_void_p, c_int64, c_void_p]),
+    "gof_backward_accumulators": (c_int64, [c_void_p, c_void_p, c_int64, c_void_p]),
     "gof_state_get": (c_int64, [c_char_p, c_int32, c_int32, c_int32, c_int64, c_void_p, c_void_p, c_size_t, c_void_p,
                                 c_void_p, c_int64, c_void_p]),
 }

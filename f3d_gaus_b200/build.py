@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libgof_b200.so")
-SOURCES = ["abi.cu", "preprocess.cu", "binning.cu", "render_fwd.cu", "render_bwd.cu", "preprocess_bwd.cu", "integrate.cu", "predictor_head.cu"]
+SOURCES = ["abi.cu", "preprocess.cu", "binning.cu", "render_fwd.cu", "render_bwd.cu", "preprocess_bwd.cu", "integrate.cu", "predictor_head.cu", "epilogue.cu"]
 HEADERS = ["gof_common.cuh", "blend_math.cuh", "conic.cuh", os.path.join("..", "..", "include", "gof_b200.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

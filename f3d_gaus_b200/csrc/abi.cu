@@ -27,6 +27,7 @@ struct GofContext {
 	int32_t* pinned = nullptr;      // host mailbox for num_rendered (callback mode)
 	float* gacc = nullptr;          // backward gradient accumulator, grown on demand
 	size_t gacc_floats = 0;
+	size_t gacc_used = 0;           // floats written by the last backward (P * V * GACC_FLOATS)
 	int64_t spec_capacity = 0;      // callback mode: binning capacity to allocate speculatively (1.25 x the last R)
 	cudaEvent_t handoff = nullptr;  // completion of the mailbox copy
 	float* sink = nullptr;          // frame sink of the NEXT forward call (device-visible address), gof_set_frame_sink
@@ -445,6 +446,7 @@ int gof_backward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* i
 	const size_t need = (size_t)P * V * GACC_FLOATS;
 	int rc;
 	if ((rc = ensure_gacc(ctx, need, s)) != GOF_OK) return rc;
+	ctx->gacc_used = need;
 	std::vector<cudaEvent_t> marks;
 	GOF_PROF_MARK(ctx, marks, s);
 	GOF_CUDA_CHECK(cudaMemsetAsync(ctx->gacc, 0, need * sizeof(float), s));
@@ -506,7 +508,18 @@ int gof_preprocess_backward(GofContext* ctx, const GofParams* prm, const GofInpu
 	return launch_preprocess_bwd(*prm, *in, 1, g, radii, ctx->gacc, *gr, s);
 }
 
-// ---- test accessor ---------------------------------------------------------------------------
+// ---- test accessors --------------------------------------------------------------------------
+int64_t gof_backward_accumulators(GofContext* ctx, void* dst, int64_t dst_bytes, gof_stream_t stream)
+{
+	if (!ctx) { set_error("gof_backward_accumulators: NULL context"); return GOF_EINVAL; }
+	const int64_t bytes = (int64_t)(ctx->gacc_used * sizeof(float));
+	if (dst && bytes) {
+		if (bytes > dst_bytes) { set_error("gof_backward_accumulators: dst too small (%lld < %lld)", (long long)dst_bytes, (long long)bytes); return GOF_ENOMEM; }
+		GOF_CUDA_CHECK(cudaMemcpyAsync(dst, ctx->gacc, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+	}
+	return bytes;
+}
+
 int64_t gof_state_get_batch(const char* name, int32_t P, int32_t W, int32_t H, int32_t V, int64_t R,
                             const void* geom, const void* binning, size_t binning_bytes, const void* img,
                             void* dst, int64_t dst_bytes, gof_stream_t stream)
@@ -603,79 +616,6 @@ int gof_pack_gather(const float* raster, int32_t frames, int64_t pixels, const i
 	return GOF_OK;
 }
 
-// ---- fused L2 epilogue -----------------------------------------------------------------------
-// One thread per pixel; see gof_b200.h.  c2w = inverse of the (column-vector) world->view
-// matrix A|t with A[r][c] = vm[4c+r], t[r] = vm[12+r]  (src/gaussian_renderer/__init__.py:881-909).
-__global__ void epilogue_kernel(const float* __restrict__ out_color_all, const float* __restrict__ vm_all, int W, int H,
-                                float fx, float fy, float* __restrict__ normal_world_all, float* __restrict__ depth_normal_all)
-{
-	const size_t NN = (size_t)W * H;
-	const float* out_color = out_color_all + (size_t)blockIdx.z * OUT_CH * NN;
-	const float* vm = vm_all + 16 * blockIdx.z;
-	float* normal_world = normal_world_all ? normal_world_all + (size_t)blockIdx.z * 3 * NN : nullptr;
-	float* depth_normal = depth_normal_all ? depth_normal_all + (size_t)blockIdx.z * 3 * NN : nullptr;
-	__shared__ float s_Ai[9], s_o[3];
-	if (threadIdx.x == 0) {
-		float A[3][3];
-		for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) A[r][c] = vm[4 * c + r];
-		const float t[3] = { vm[12], vm[13], vm[14] };
-		const float c00 = A[1][1] * A[2][2] - A[1][2] * A[2][1];
-		const float c01 = A[1][2] * A[2][0] - A[1][0] * A[2][2];
-		const float c02 = A[1][0] * A[2][1] - A[1][1] * A[2][0];
-		const float det = A[0][0] * c00 + A[0][1] * c01 + A[0][2] * c02;
-		const float id = 1.0f / det;
-		float Ai[3][3];
-		Ai[0][0] = c00 * id; Ai[1][0] = c01 * id; Ai[2][0] = c02 * id;
-		Ai[0][1] = (A[0][2] * A[2][1] - A[0][1] * A[2][2]) * id;
-		Ai[1][1] = (A[0][0] * A[2][2] - A[0][2] * A[2][0]) * id;
-		Ai[2][1] = (A[0][1] * A[2][0] - A[0][0] * A[2][1]) * id;
-		Ai[0][2] = (A[0][1] * A[1][2] - A[0][2] * A[1][1]) * id;
-		Ai[1][2] = (A[0][2] * A[1][0] - A[0][0] * A[1][2]) * id;
-		Ai[2][2] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) * id;
-		for (int r = 0; r < 3; r++) {
-			for (int c = 0; c < 3; c++) s_Ai[3 * r + c] = Ai[r][c];
-			s_o[r] = -(Ai[r][0] * t[0] + Ai[r][1] * t[1] + Ai[r][2] * t[2]);
-		}
-	}
-	__syncthreads();
-	const int x = blockIdx.x * blockDim.x + threadIdx.x;
-	const int y = blockIdx.y;
-	if (x >= W || y >= H) return;
-	const size_t N = (size_t)W * H;
-	const size_t pid = (size_t)y * W + x;
-
-	if (normal_world) {
-		float n0 = out_color[3 * N + pid], n1 = out_color[4 * N + pid], n2 = out_color[5 * N + pid];
-		const float nrm = fmaxf(sqrtf(n0 * n0 + n1 * n1 + n2 * n2), 1e-12f);
-		n0 /= nrm; n1 /= nrm; n2 /= nrm;
-		normal_world[0 * N + pid] = s_Ai[0] * n0 + s_Ai[1] * n1 + s_Ai[2] * n2;
-		normal_world[1 * N + pid] = s_Ai[3] * n0 + s_Ai[4] * n1 + s_Ai[5] * n2;
-		normal_world[2 * N + pid] = s_Ai[6] * n0 + s_Ai[7] * n1 + s_Ai[8] * n2;
-	}
-	if (depth_normal) {
-		float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-		if (x >= 1 && x < W - 1 && y >= 1 && y < H - 1) {
-			auto point = [&](int px, int py, float* p) {
-				const float d = out_color[CH_DEPTH * N + (size_t)py * W + px];
-				const float cx = (px - W / 2.f) / fx, cy = (py - H / 2.f) / fy;
-				for (int r = 0; r < 3; r++) p[r] = d * (s_Ai[3 * r] * cx + s_Ai[3 * r + 1] * cy + s_Ai[3 * r + 2]) + s_o[r];
-			};
-			float pu[3], pd[3], pl[3], pr[3];
-			point(x, y + 1, pd); point(x, y - 1, pu); point(x + 1, y, pr); point(x - 1, y, pl);
-			const float dx[3] = { pd[0] - pu[0], pd[1] - pu[1], pd[2] - pu[2] };   // along image rows (y)
-			const float dy[3] = { pr[0] - pl[0], pr[1] - pl[1], pr[2] - pl[2] };   // along image columns (x)
-			const float c0 = dx[1] * dy[2] - dx[2] * dy[1];
-			const float c1 = dx[2] * dy[0] - dx[0] * dy[2];
-			const float c2 = dx[0] * dy[1] - dx[1] * dy[0];
-			const float nrm = fmaxf(sqrtf(c0 * c0 + c1 * c1 + c2 * c2), 1e-12f);
-			o0 = c0 / nrm; o1 = c1 / nrm; o2 = c2 / nrm;
-		}
-		depth_normal[0 * N + pid] = o0;
-		depth_normal[1 * N + pid] = o1;
-		depth_normal[2 * N + pid] = o2;
-	}
-}
-
 int gof_predictor_head(const GofHeadParams* prm, const float* net, const float* depth, const float* const_offset,
                        const float* ray_x, const float* ray_y, const float* view_to_world, const float* quat,
                        const float* sh_transform, float* xyz, float* opacity, float* scaling, float* rotation,
@@ -698,24 +638,6 @@ int gof_predictor_head(const GofHeadParams* prm, const float* net, const float* 
 	}
 	return launch_predictor_head(*prm, net, depth, const_offset, ray_x, ray_y, view_to_world, quat, sh_transform, xyz, opacity,
 	                             scaling, rotation, features_dc, features_rest, (cudaStream_t)stream);
-}
-
-int gof_render_epilogue(const float* out_color, const float* viewmatrix, int32_t W, int32_t H,
-                        float fovx, float fovy, float* normal_world, float* depth_normal, gof_stream_t stream)
-{
-	return gof_render_epilogue_batch(out_color, viewmatrix, 1, W, H, fovx, fovy, normal_world, depth_normal, stream);
-}
-
-int gof_render_epilogue_batch(const float* out_color, const float* viewmatrix, int32_t V, int32_t W, int32_t H,
-                              float fovx, float fovy, float* normal_world, float* depth_normal, gof_stream_t stream)
-{
-	if (!out_color || !viewmatrix || W <= 0 || H <= 0 || V <= 0) { set_error("gof_render_epilogue: bad argument"); return GOF_EINVAL; }
-	const float fx = W / (2.f * tanf(fovx / 2.f));
-	const float fy = H / (2.f * tanf(fovy / 2.f));
-	dim3 grid((W + 127) / 128, H, V);
-	epilogue_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(out_color, viewmatrix, W, H, fx, fy, normal_world, depth_normal);
-	GOF_CUDA_CHECK(cudaGetLastError());
-	return GOF_OK;
 }
 
 }  // extern "C"

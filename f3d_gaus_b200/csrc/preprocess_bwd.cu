@@ -25,28 +25,6 @@ __device__ const float kSH_C3[] = {-0.5900435899266435f, 2.890611442640554f, -0.
                                    -0.5900435899266435f};
 
 struct V3 { float x, y, z; };
-struct M3 { float c[3][3]; };   // column-major: c[col][row]
-
-__device__ __forceinline__ M3 m3_mul(const M3& a, const M3& b)
-{
-	M3 r;
-#pragma unroll
-	for (int i = 0; i < 3; i++)
-#pragma unroll
-		for (int j = 0; j < 3; j++)
-			r.c[i][j] = a.c[0][j] * b.c[i][0] + a.c[1][j] * b.c[i][1] + a.c[2][j] * b.c[i][2];
-	return r;
-}
-__device__ __forceinline__ M3 m3_t(const M3& a)
-{
-	M3 r;
-#pragma unroll
-	for (int i = 0; i < 3; i++)
-#pragma unroll
-		for (int j = 0; j < 3; j++) r.c[i][j] = a.c[j][i];
-	return r;
-}
-
 // d(normalize(v))/dv applied to dv (auxiliary.h:150-161)
 __device__ __forceinline__ V3 dnormvdv(V3 v, V3 dv)
 {
@@ -60,111 +38,140 @@ __device__ __forceinline__ V3 dnormvdv(V3 v, V3 dv)
 }
 
 // Backward of the 10-float quadric w.r.t. mean / scale / rotation (backward.cu:381-587).
-__device__ void quadric_backward(const V3 scale, const V3 mean, const float4 rot, const float* vm,
-                                 const float* dq, V3& dL_dmean, V3& dL_dscale, float4& dL_drot)
+//
+// Evaluated in DOUBLE from the float32 inputs.  The map is catastrophically ill-conditioned at F3D-Gaus scales:
+// dL/dSinv_k = Rt_k^T dSigma Rt_k + t2_k (dB . Rt_k) + dC t2_k^2 is, pair by pair, Sinv-derivative of a perfect
+// square (t2_k + t* Rt_k.r)^2 ~ (3 sigma)^2 assembled from terms of size t2_k^2 ~ 60 -- a cancellation of ~1e5..1e6 --
+// and the reference, which evaluates it in float32 (with double only for Sinv), is 3e-2 away from the exact value of
+// its own formula.  This kernel is a 15 us HBM-bound per-Gaussian pass, so double arithmetic is free here and
+// removes the rounding error of the map altogether: what remains is the float32 noise already present in the
+// accumulated dL/dview2gaussian it is applied to (tests: e_ours <= e_ref against the float64 oracle).
+struct D3 { double x, y, z; };
+struct DM3 { double c[3][3]; };   // column-major: c[col][row]
+
+__device__ __forceinline__ DM3 dm3_mul(const DM3& a, const DM3& b)
 {
-	const float r = rot.x, x = rot.y, y = rot.z, z = rot.w;
-	M3 R;
-	R.c[0][0] = 1.f - 2.f * (y * y + z * z); R.c[0][1] = 2.f * (x * y - r * z);       R.c[0][2] = 2.f * (x * z + r * y);
-	R.c[1][0] = 2.f * (x * y + r * z);       R.c[1][1] = 1.f - 2.f * (x * x + z * z); R.c[1][2] = 2.f * (y * z - r * x);
-	R.c[2][0] = 2.f * (x * z - r * y);       R.c[2][1] = 2.f * (y * z + r * x);       R.c[2][2] = 1.f - 2.f * (x * x + y * y);
+	DM3 r;
+#pragma unroll
+	for (int i = 0; i < 3; i++)
+#pragma unroll
+		for (int j = 0; j < 3; j++)
+			r.c[i][j] = a.c[0][j] * b.c[i][0] + a.c[1][j] * b.c[i][1] + a.c[2][j] * b.c[i][2];
+	return r;
+}
+__device__ __forceinline__ DM3 dm3_t(const DM3& a)
+{
+	DM3 r;
+#pragma unroll
+	for (int i = 0; i < 3; i++)
+#pragma unroll
+		for (int j = 0; j < 3; j++) r.c[i][j] = a.c[j][i];
+	return r;
+}
+
+__device__ void quadric_backward(const V3 scale, const V3 mean, const float4 rot, const float* vm,
+                                 const float* dq, D3& dL_dmean, D3& dL_dscale, double* dL_drot)
+{
+	const double r = rot.x, x = rot.y, y = rot.z, z = rot.w;
+	DM3 R;
+	R.c[0][0] = 1. - 2. * (y * y + z * z); R.c[0][1] = 2. * (x * y - r * z);      R.c[0][2] = 2. * (x * z + r * y);
+	R.c[1][0] = 2. * (x * y + r * z);      R.c[1][1] = 1. - 2. * (x * x + z * z); R.c[1][2] = 2. * (y * z - r * x);
+	R.c[2][0] = 2. * (x * z - r * y);      R.c[2][1] = 2. * (y * z + r * x);      R.c[2][2] = 1. - 2. * (x * x + y * y);
 
 	// G2V = W2V * G2W with G2W = [R^T-layout | mean]; only the 3x4 part is needed.
 	// G2W column c (c<3) = (R[0][c], R[1][c], R[2][c], 0), column 3 = (mean, 1).
-	float G2V[4][3];
+	double G2V[4][3];
 #pragma unroll
 	for (int c = 0; c < 3; c++)
 #pragma unroll
 		for (int j = 0; j < 3; j++)
-			G2V[c][j] = vm[0 + j] * R.c[0][c] + vm[4 + j] * R.c[1][c] + vm[8 + j] * R.c[2][c] + vm[12 + j] * 0.0f;
+			G2V[c][j] = (double)vm[0 + j] * R.c[0][c] + (double)vm[4 + j] * R.c[1][c] + (double)vm[8 + j] * R.c[2][c];
 #pragma unroll
 	for (int j = 0; j < 3; j++)
-		G2V[3][j] = vm[0 + j] * mean.x + vm[4 + j] * mean.y + vm[8 + j] * mean.z + vm[12 + j];
+		G2V[3][j] = (double)vm[0 + j] * mean.x + (double)vm[4 + j] * mean.y + (double)vm[8 + j] * mean.z + (double)vm[12 + j];
 
-	M3 Rt;   // Rt[c][r] = G2V[r][c]
+	DM3 Rt;   // Rt[c][r] = G2V[r][c]
 #pragma unroll
 	for (int c = 0; c < 3; c++)
 #pragma unroll
 		for (int rr = 0; rr < 3; rr++) Rt.c[c][rr] = G2V[rr][c];
-	const V3 t = { G2V[3][0], G2V[3][1], G2V[3][2] };
-	const V3 t2 = { -(Rt.c[0][0] * t.x + Rt.c[1][0] * t.y + Rt.c[2][0] * t.z),
-	                -(Rt.c[0][1] * t.x + Rt.c[1][1] * t.y + Rt.c[2][1] * t.z),
-	                -(Rt.c[0][2] * t.x + Rt.c[1][2] * t.y + Rt.c[2][2] * t.z) };
+	const double ta[3] = { G2V[3][0], G2V[3][1], G2V[3][2] };
+	double t2a[3];
+#pragma unroll
+	for (int rr = 0; rr < 3; rr++) t2a[rr] = -(Rt.c[0][rr] * ta[0] + Rt.c[1][rr] * ta[1] + Rt.c[2][rr] * ta[2]);
 
-	const double Sinv[3] = { 1.0f / ((double)scale.x * scale.x + 1e-7), 1.0f / ((double)scale.y * scale.y + 1e-7),
-	                         1.0f / ((double)scale.z * scale.z + 1e-7) };
-	M3 SR;
+	const double sc[3] = { scale.x, scale.y, scale.z };
+	double Sinv[3];
+#pragma unroll
+	for (int k = 0; k < 3; k++) Sinv[k] = 1.0 / (sc[k] * sc[k] + 1e-7);
+	DM3 SR;
 #pragma unroll
 	for (int c = 0; c < 3; c++)
 #pragma unroll
 		for (int rr = 0; rr < 3; rr++) SR.c[c][rr] = Sinv[rr] * Rt.c[c][rr];
 
-	M3 dSig;
-	dSig.c[0][0] = dq[0];        dSig.c[0][1] = 0.5f * dq[1]; dSig.c[0][2] = 0.5f * dq[2];
-	dSig.c[1][0] = 0.5f * dq[1]; dSig.c[1][1] = dq[3];        dSig.c[1][2] = 0.5f * dq[4];
-	dSig.c[2][0] = 0.5f * dq[2]; dSig.c[2][1] = 0.5f * dq[4]; dSig.c[2][2] = dq[5];
-	const float dB[3] = { dq[6], dq[7], dq[8] };
-	const float dC = dq[9];
-	const float t2a[3] = { t2.x, t2.y, t2.z };
+	DM3 dSig;
+	dSig.c[0][0] = dq[0];        dSig.c[0][1] = 0.5 * dq[1]; dSig.c[0][2] = 0.5 * dq[2];
+	dSig.c[1][0] = 0.5 * dq[1];  dSig.c[1][1] = dq[3];       dSig.c[1][2] = 0.5 * dq[4];
+	dSig.c[2][0] = 0.5 * dq[2];  dSig.c[2][1] = 0.5 * dq[4]; dSig.c[2][2] = dq[5];
+	const double dB[3] = { dq[6], dq[7], dq[8] };
+	const double dC = dq[9];
 
 	// dL/dSR = Rt * dSigma + outer(t2, dB)   (outer: column i = t2 * dB[i])
-	M3 dSR = m3_mul(Rt, dSig);
+	DM3 dSR = dm3_mul(Rt, dSig);
 #pragma unroll
 	for (int c = 0; c < 3; c++)
 #pragma unroll
 		for (int rr = 0; rr < 3; rr++) dSR.c[c][rr] += t2a[rr] * dB[c];
 	// dL/dRt = (dSigma * SR^T)^T + diag(Sinv) applied row-wise to dSR
-	M3 dRt = m3_t(m3_mul(dSig, m3_t(SR)));
+	DM3 dRt = dm3_t(dm3_mul(dSig, dm3_t(SR)));
 #pragma unroll
 	for (int c = 0; c < 3; c++)
 #pragma unroll
 		for (int rr = 0; rr < 3; rr++) dRt.c[c][rr] += Sinv[rr] * dSR.c[c][rr];
 
-	float dSinv[3], dt2[3];
+	double dSinv[3], dt2[3];
 #pragma unroll
 	for (int rr = 0; rr < 3; rr++) {
-		dSinv[rr] = dSR.c[0][rr] * Rt.c[0][rr] + dSR.c[1][rr] * Rt.c[1][rr] + dSR.c[2][rr] * Rt.c[2][rr];
+		dSinv[rr] = dSR.c[0][rr] * Rt.c[0][rr] + dSR.c[1][rr] * Rt.c[1][rr] + dSR.c[2][rr] * Rt.c[2][rr] + dC * t2a[rr] * t2a[rr];
 		dt2[rr] = 2 * t2a[rr] * Sinv[rr] * dC + dB[0] * SR.c[0][rr] + dB[1] * SR.c[1][rr] + dB[2] * SR.c[2][rr];
 	}
-#pragma unroll
-	for (int rr = 0; rr < 3; rr++) dSinv[rr] += dC * t2a[rr] * t2a[rr];
 
-	dL_dscale.x = -2 / scale.x * Sinv[0] * dSinv[0];
-	dL_dscale.y = -2 / scale.y * Sinv[1] * dSinv[1];
-	dL_dscale.z = -2 / scale.z * Sinv[2] * dSinv[2];
+	dL_dscale.x = -2 / sc[0] * Sinv[0] * dSinv[0];
+	dL_dscale.y = -2 / sc[1] * Sinv[1] * dSinv[1];
+	dL_dscale.z = -2 / sc[2] * Sinv[2] * dSinv[2];
 
 	// Back through V2G = [G2V_R^T | -G2V_R^T t] to G2V, then through G2V = W2V * G2W.
-	const float ta[3] = { t.x, t.y, t.z };
-	M3 dG2V_R = m3_t(dRt);
+	DM3 dG2V_R = dm3_t(dRt);
 #pragma unroll
 	for (int c = 0; c < 3; c++)
 #pragma unroll
 		for (int rr = 0; rr < 3; rr++) dG2V_R.c[c][rr] += -dt2[c] * ta[rr];
 	// dL/dG2V_t = (-dt2) as a row vector times G2V_R^T (= Rt)
-	float dG2V_t[3];
+	double dG2V_t[3];
 #pragma unroll
 	for (int c = 0; c < 3; c++)
 		dG2V_t[c] = Rt.c[c][0] * -dt2[0] + Rt.c[c][1] * -dt2[1] + Rt.c[c][2] * -dt2[2];
 
 	// dL/dG2W = W2V^T * dL/dG2V (4x4, last row of dG2V is 0): element [c][r] = sum_k W2V[r][k] dG2V[c][k]
-	float dG2W[4][3];
+	double dG2W[4][3];
 #pragma unroll
 	for (int c = 0; c < 3; c++)
 #pragma unroll
 		for (int rr = 0; rr < 3; rr++)
-			dG2W[c][rr] = vm[4 * rr + 0] * dG2V_R.c[c][0] + vm[4 * rr + 1] * dG2V_R.c[c][1] + vm[4 * rr + 2] * dG2V_R.c[c][2];
+			dG2W[c][rr] = (double)vm[4 * rr + 0] * dG2V_R.c[c][0] + (double)vm[4 * rr + 1] * dG2V_R.c[c][1] + (double)vm[4 * rr + 2] * dG2V_R.c[c][2];
 #pragma unroll
 	for (int rr = 0; rr < 3; rr++)
-		dG2W[3][rr] = vm[4 * rr + 0] * dG2V_t[0] + vm[4 * rr + 1] * dG2V_t[1] + vm[4 * rr + 2] * dG2V_t[2];
+		dG2W[3][rr] = (double)vm[4 * rr + 0] * dG2V_t[0] + (double)vm[4 * rr + 1] * dG2V_t[1] + (double)vm[4 * rr + 2] * dG2V_t[2];
 
 	dL_dmean = { dG2W[3][0], dG2W[3][1], dG2W[3][2] };
 
 	// quaternion gradient from dL/dMt = the 3x3 block of dL/dG2W (backward.cu:575-586)
 #define MT(a, b) dG2W[a][b]
-	dL_drot.x = 2 * z * (MT(0, 1) - MT(1, 0)) + 2 * y * (MT(2, 0) - MT(0, 2)) + 2 * x * (MT(1, 2) - MT(2, 1));
-	dL_drot.y = 2 * y * (MT(1, 0) + MT(0, 1)) + 2 * z * (MT(2, 0) + MT(0, 2)) + 2 * r * (MT(1, 2) - MT(2, 1)) - 4 * x * (MT(2, 2) + MT(1, 1));
-	dL_drot.z = 2 * x * (MT(1, 0) + MT(0, 1)) + 2 * r * (MT(2, 0) - MT(0, 2)) + 2 * z * (MT(1, 2) + MT(2, 1)) - 4 * y * (MT(2, 2) + MT(0, 0));
-	dL_drot.w = 2 * r * (MT(0, 1) - MT(1, 0)) + 2 * x * (MT(2, 0) + MT(0, 2)) + 2 * y * (MT(1, 2) + MT(2, 1)) - 4 * z * (MT(1, 1) + MT(0, 0));
+	dL_drot[0] = 2 * z * (MT(0, 1) - MT(1, 0)) + 2 * y * (MT(2, 0) - MT(0, 2)) + 2 * x * (MT(1, 2) - MT(2, 1));
+	dL_drot[1] = 2 * y * (MT(1, 0) + MT(0, 1)) + 2 * z * (MT(2, 0) + MT(0, 2)) + 2 * r * (MT(1, 2) - MT(2, 1)) - 4 * x * (MT(2, 2) + MT(1, 1));
+	dL_drot[2] = 2 * x * (MT(1, 0) + MT(0, 1)) + 2 * r * (MT(2, 0) - MT(0, 2)) + 2 * z * (MT(1, 2) + MT(2, 1)) - 4 * y * (MT(2, 2) + MT(0, 0));
+	dL_drot[3] = 2 * r * (MT(0, 1) - MT(1, 0)) + 2 * x * (MT(2, 0) + MT(0, 2)) + 2 * y * (MT(1, 2) + MT(2, 1)) - 4 * z * (MT(1, 1) + MT(0, 0));
 #undef MT
 }
 
@@ -259,8 +266,9 @@ preprocess_bwd_kernel(int P, int V, int D, int M, const float* __restrict__ mean
 	if (dsh) for (int k = 0; k < 3 * M; k++) dsh[k] = 0.0f;
 
 	float sq[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 }, scol[3] = { 0, 0, 0 }, sop = 0.f, sm2[3] = { 0, 0, 0 };
-	V3 dmean = { 0.f, 0.f, 0.f }, dscale = { 0.f, 0.f, 0.f };
-	float4 drot = { 0.f, 0.f, 0.f, 0.f };
+	// mean / scale / rotation gradients are summed over the views in double (each view's term is exact to ~1e-16)
+	D3 dmean = { 0., 0., 0. }, dscale = { 0., 0., 0. };
+	double drot[4] = { 0., 0., 0., 0. };
 	for (int v = 0; v < V; v++) {
 		const float4* ga = reinterpret_cast<const float4*>(gacc_all + ((size_t)v * P + idx) * GACC_FLOATS);
 		const float4 g0 = ga[0], g1 = ga[1], g2 = ga[2], g3 = ga[3], g4 = ga[4];
@@ -274,12 +282,12 @@ preprocess_bwd_kernel(int P, int V, int D, int M, const float* __restrict__ mean
 		const bool visible = radii_all[(size_t)v * P + idx] > 0;
 		if (!visible) continue;
 		if (has_geom) {
-			V3 dm, ds;
-			float4 dr;
+			D3 dm, ds;
+			double dr[4];
 			quadric_backward(scale, mean, rot, viewmatrices + 16 * v, dq, dm, ds, dr);
 			dmean.x += dm.x; dmean.y += dm.y; dmean.z += dm.z;
 			dscale.x += ds.x; dscale.y += ds.y; dscale.z += ds.z;
-			drot.x += dr.x; drot.y += dr.y; drot.z += dr.z; drot.w += dr.w;
+			drot[0] += dr[0]; drot[1] += dr[1]; drot[2] += dr[2]; drot[3] += dr[3];
 		}
 		if (dsh && shs != nullptr) {
 			const V3 cam = { campos_all[3 * v], campos_all[3 * v + 1], campos_all[3 * v + 2] };
@@ -299,16 +307,16 @@ preprocess_bwd_kernel(int P, int V, int D, int M, const float* __restrict__ mean
 	dL_dmeans2D[3 * (size_t)idx + 2] = sm2[2];
 #pragma unroll
 	for (int k = 0; k < 6; k++) dL_dcov3D[(size_t)idx * 6 + k] = 0.0f;
-	dL_dmeans3D[3 * (size_t)idx + 0] = dmean.x;
-	dL_dmeans3D[3 * (size_t)idx + 1] = dmean.y;
-	dL_dmeans3D[3 * (size_t)idx + 2] = dmean.z;
-	dL_dscales[3 * (size_t)idx + 0] = dscale.x;
-	dL_dscales[3 * (size_t)idx + 1] = dscale.y;
-	dL_dscales[3 * (size_t)idx + 2] = dscale.z;
-	dL_drot[4 * (size_t)idx + 0] = drot.x;
-	dL_drot[4 * (size_t)idx + 1] = drot.y;
-	dL_drot[4 * (size_t)idx + 2] = drot.z;
-	dL_drot[4 * (size_t)idx + 3] = drot.w;
+	dL_dmeans3D[3 * (size_t)idx + 0] = (float)dmean.x;
+	dL_dmeans3D[3 * (size_t)idx + 1] = (float)dmean.y;
+	dL_dmeans3D[3 * (size_t)idx + 2] = (float)dmean.z;
+	dL_dscales[3 * (size_t)idx + 0] = (float)dscale.x;
+	dL_dscales[3 * (size_t)idx + 1] = (float)dscale.y;
+	dL_dscales[3 * (size_t)idx + 2] = (float)dscale.z;
+	dL_drot[4 * (size_t)idx + 0] = (float)drot[0];
+	dL_drot[4 * (size_t)idx + 1] = (float)drot[1];
+	dL_drot[4 * (size_t)idx + 2] = (float)drot[2];
+	dL_drot[4 * (size_t)idx + 3] = (float)drot[3];
 }
 
 }  // namespace

@@ -484,6 +484,20 @@ def state_array_batch(name: str, P: int, W: int, H: int, V: int, R: int, geom, b
     return out
 
 
+def backward_accumulators(device, V: int, P: int):
+    """Test accessor (gof_backward_accumulators): [V,P,20] per-view gradient accumulators of the last backward."""
+    device = torch.device(device)
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    out = torch.empty((V, P, 20), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        n = _lib.lib.gof_backward_accumulators(_lib.context(device.index), out.data_ptr(), out.numel() * 4,
+                                               _lib.raw_stream(device))
+    if n != out.numel() * 4:
+        raise RuntimeError(f"gof_backward_accumulators: expected {out.numel() * 4} bytes, got {n}: {_lib.last_error()}")
+    return out
+
+
 def state_array(name: str, P: int, W: int, H: int, R: int, geom, binning, img):
     """Test accessor: decode one array of the opaque forward state (gof_state_get)."""
     device = geom.device

@@ -8,9 +8,9 @@
   render                          the vanilla signature (src/gaussian-splatting/gaussian_renderer/__init__.py:18-100)
 
 Same arguments, same output keys.  Differences are internal: the rasterizer is libgof_b200,
-the per-call `subpixel_offset` allocation is dropped (no kernel reads it), and when no autograd
-graph is needed the ~20 small torch kernels of the post-processing (normalise, 4x4 inverse,
-back-projection, cross product) are replaced by one fused epilogue kernel (gof_render_epilogue).
+the per-call `subpixel_offset` allocation is dropped (no kernel reads it), and the ~20 small torch
+kernels of the post-processing (normalise, 4x4 inverse, back-projection, cross product) are one fused
+epilogue kernel (gof_render_epilogue) with a hand-written backward for the training path.
 """
 from __future__ import annotations
 
@@ -32,54 +32,85 @@ def focal2fov(focal, pixels):
     return 2 * math.atan(pixels / (2 * focal))
 
 
-def depths_to_points(world_view_transform, image_width, image_height, FoVx, FoVy, depthmap):
-    """Back-project a depth map to world points (torch ops; differentiable)."""
-    dev = depthmap.device
-    c2w = (world_view_transform.T).inverse()
-    W, H = image_width, image_height
-    fx = W / (2 * math.tan(FoVx / 2.))
-    fy = H / (2 * math.tan(FoVy / 2.))
-    intrins = torch.tensor([[fx, 0., W / 2.], [0., fy, H / 2.], [0., 0., 1.0]], dtype=torch.float32, device=dev)
-    grid_x, grid_y = torch.meshgrid(torch.arange(W, device=dev).float(), torch.arange(H, device=dev).float(),
-                                    indexing='xy')
-    points = torch.stack([grid_x, grid_y, torch.ones_like(grid_x)], dim=-1).reshape(-1, 3)
-    rays_d = points @ intrins.inverse().T @ c2w[:3, :3].T
-    rays_o = c2w[:3, 3]
-    return depthmap.reshape(-1, 1) * rays_d + rays_o
+def _epilogue_forward(raster, vm, V, W, H, FovX, FovY, want_normal=True, want_depth_normal=True):
+    dev = raster.device
+    normal_world = torch.empty((V, 3, H, W), dtype=torch.float32, device=dev) if want_normal else None
+    depth_normal = torch.empty((V, 3, H, W), dtype=torch.float32, device=dev) if want_depth_normal else None
+    with torch.cuda.device(dev):
+        rc = _lib.lib.gof_render_epilogue_batch(raster.data_ptr(), vm.data_ptr(), V, W, H, ctypes.c_float(FovX),
+                                                ctypes.c_float(FovY),
+                                                normal_world.data_ptr() if want_normal else None,
+                                                depth_normal.data_ptr() if want_depth_normal else None,
+                                                _lib.raw_stream(dev))
+    _lib.check(rc, "gof_render_epilogue_batch")
+    return normal_world, depth_normal
 
 
-def depth_to_normal(world_view_transform, image_width, image_height, FoVx, FoVy, depth):
-    """Normals from finite differences of the back-projected depth; border pixels are 0."""
-    points = depths_to_points(world_view_transform, image_width, image_height, FoVx, FoVy, depth)
-    points = points.reshape(*depth.shape[1:], 3)
-    output = torch.zeros_like(points)
-    dx = points[2:, 1:-1] - points[:-2, 1:-1]
-    dy = points[1:-1, 2:] - points[1:-1, :-2]
-    output[1:-1, 1:-1, :] = torch.nn.functional.normalize(torch.cross(dx, dy, dim=-1), dim=-1)
-    return output
+class _FusedEpilogue(torch.autograd.Function):
+    """(normal_world, depth_normal) = epilogue(out_color) with a hand-written backward (csrc/epilogue.cu): the
+    training path of render_predicted_more_v2_gof without the reference's ~20 torch kernels and 4x4 inverse() per
+    frame (src/gaussian_renderer/__init__.py:881-909,1043-1053).  out_color: [V,9,H,W], vm: [V,16]."""
 
+    @staticmethod
+    def forward(ctx, raster, vm, W, H, FovX, FovY):
+        raster = raster.contiguous()
+        ctx.save_for_backward(raster, vm)
+        ctx.dims = (int(raster.shape[0]), W, H, FovX, FovY)
+        return _epilogue_forward(raster, vm, raster.shape[0], W, H, FovX, FovY)
 
-def _postprocess_torch(rendered_image, world_view_transform, W, H, FovX, FovY):
-    render_normal = torch.nn.functional.normalize(rendered_image[3:6], p=2, dim=0)
-    c2w = (world_view_transform.squeeze().T).inverse()
-    normal_world = (c2w[:3, :3] @ render_normal.reshape(3, -1)).reshape(3, *render_normal.shape[1:])
-    depth_normal = depth_to_normal(world_view_transform.squeeze(), W, H, FovX, FovY, rendered_image[6:7])
-    return normal_world, depth_normal.permute(2, 0, 1)
+    @staticmethod
+    def backward(ctx, g_normal_world, g_depth_normal):
+        raster, vm = ctx.saved_tensors
+        V, W, H, FovX, FovY = ctx.dims
+        dev = raster.device
+        grad = torch.empty_like(raster)           # every element is written by the kernel
+        keep = [t.contiguous() if t is not None else None for t in (g_normal_world, g_depth_normal)]
+        with torch.cuda.device(dev):
+            rc = _lib.lib.gof_render_epilogue_backward_batch(
+                raster.data_ptr(), vm.data_ptr(), V, W, H, ctypes.c_float(FovX), ctypes.c_float(FovY),
+                keep[0].data_ptr() if keep[0] is not None else None,
+                keep[1].data_ptr() if keep[1] is not None else None, grad.data_ptr(), _lib.raw_stream(dev))
+        _lib.check(rc, "gof_render_epilogue_backward_batch")
+        return grad, None, None, None, None, None
 
 
 def fused_epilogue(rendered_image, world_view_transform, W, H, FovX, FovY):
-    """normal_world[3,H,W], depth_normal[3,H,W] from out_color[9,H,W] in one kernel."""
-    dev = rendered_image.device
-    img = rendered_image.contiguous()
-    vm = world_view_transform.reshape(-1).contiguous()
-    normal_world = torch.empty((3, H, W), dtype=torch.float32, device=dev)
-    depth_normal = torch.empty((3, H, W), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
-        rc = _lib.lib.gof_render_epilogue(img.data_ptr(), vm.data_ptr(), W, H, ctypes.c_float(FovX),
-                                          ctypes.c_float(FovY), normal_world.data_ptr(), depth_normal.data_ptr(),
-                                          _lib.raw_stream(dev))
-    _lib.check(rc, "gof_render_epilogue")
-    return normal_world, depth_normal
+    """normal_world[3,H,W], depth_normal[3,H,W] from out_color[9,H,W] in one kernel; differentiable w.r.t.
+    `rendered_image` (the normal channels 3..5 and the median depth 6) when it carries a graph."""
+    vm = world_view_transform.reshape(1, 16).contiguous()
+    img = rendered_image.unsqueeze(0)
+    if torch.is_grad_enabled() and rendered_image.requires_grad:
+        normal_world, depth_normal = _FusedEpilogue.apply(img, vm, W, H, FovX, FovY)
+    else:
+        normal_world, depth_normal = _epilogue_forward(img.contiguous(), vm, 1, W, H, FovX, FovY)
+    return normal_world[0], depth_normal[0]
+
+
+def depth_to_normal(world_view_transform, image_width, image_height, FoVx, FoVy, depth):
+    """Reference helper name (:898-909): normals [H,W,3] from finite differences of the back-projected depth
+    [1,H,W], zero on the border.  Served by the fused epilogue kernel (no 4x4 inverse, no meshgrid)."""
+    H, W = int(image_height), int(image_width)
+    raster = torch.zeros((1, _lib.OUTPUT_CHANNELS, H, W), dtype=torch.float32, device=depth.device)
+    raster[0, 6] = depth.reshape(H, W)
+    vm = world_view_transform.reshape(1, 16).contiguous()
+    if torch.is_grad_enabled() and depth.requires_grad:
+        _, dn = _FusedEpilogue.apply(raster, vm, W, H, FoVx, FoVy)
+    else:
+        _, dn = _epilogue_forward(raster, vm, 1, W, H, FoVx, FoVy, want_normal=False)
+    return dn[0].permute(1, 2, 0)
+
+
+def depths_to_points(world_view_transform, image_width, image_height, FoVx, FoVy, depthmap):
+    """Reference helper name (:881-896): world points [H*W,3] of a depth map [1,H,W] (pixel (x,y) -> camera ray
+    ((x-W/2)/fx, (y-H/2)/fy, 1) * depth, moved to the world frame)."""
+    W, H = int(image_width), int(image_height)
+    dev = depthmap.device
+    view_to_world = world_view_transform.reshape(4, 4).inverse()          # row-vector convention: p_w = [p_v,1] @ V2W
+    cx = (torch.arange(W, device=dev, dtype=torch.float32) - W / 2.) / (W / (2 * math.tan(FoVx / 2.)))
+    cy = (torch.arange(H, device=dev, dtype=torch.float32) - H / 2.) / (H / (2 * math.tan(FoVy / 2.)))
+    d = depthmap.reshape(H, W)
+    cam = torch.stack([cx[None, :] * d, cy[:, None] * d, d], dim=-1).reshape(-1, 3)
+    return cam @ view_to_world[:3, :3] + view_to_world[3, :3]
 
 
 def _subpixel_offset(H, W, device):
@@ -135,12 +166,8 @@ def render_predicted_more_v2_gof(pc: dict, bs, world_view_transform, full_proj_t
                                        colors_precomp=colors_precomp, opacities=opacity, scales=scales,
                                        rotations=rotations, cov3D_precomp=None, view2gaussian_precomp=None)
 
-    if rendered_image.requires_grad:
-        normal_world, depth_normal = _postprocess_torch(rendered_image, world_view_transform, image_width,
-                                                        image_height, FovX, FovY)
-    else:
-        normal_world, depth_normal = fused_epilogue(rendered_image, world_view_transform, image_width,
-                                                    image_height, FovX, FovY)
+    normal_world, depth_normal = fused_epilogue(rendered_image, world_view_transform, image_width, image_height,
+                                                FovX, FovY)
 
     return {"render": rendered_image[:3, :, :],
             "rendered_normal": normal_world,
@@ -220,16 +247,8 @@ def render_views(pc: dict, bs, world_view_transforms, full_proj_transforms, came
                "rendered_alpha": raster[:, 7:8], "distortion_map": raster[:, 8:9], "radii": radii,
                "visibility_filter": radii > 0, "num_rendered": R}
         if epilogue:
-            normal_world = torch.empty((V, 3, H, W), dtype=torch.float32, device=device)
-            depth_normal = torch.empty((V, 3, H, W), dtype=torch.float32, device=device)
             vm = world_view_transforms.reshape(V, 16).contiguous()
-            with torch.cuda.device(device):
-                rc = _lib.lib.gof_render_epilogue_batch(raster.data_ptr(), vm.data_ptr(), V, W, H, ctypes.c_float(Fov),
-                                                        ctypes.c_float(Fov), normal_world.data_ptr(),
-                                                        depth_normal.data_ptr(),
-                                                        _lib.raw_stream(device))
-            _lib.check(rc, "gof_render_epilogue_batch")
-            out["rendered_normal"], out["depth_normal"] = normal_world, depth_normal
+            out["rendered_normal"], out["depth_normal"] = _epilogue_forward(raster, vm, V, W, H, Fov, Fov)
     return out
 
 

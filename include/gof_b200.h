@@ -19,6 +19,7 @@
  *                                                                  RAST/cuda_rasterizer/rasterizer_impl.cu:188-243
  *   gof_render_epilogue  <- the torch post-processing of render_predicted_more_v2_gof
  *                                                                  src/gaussian_renderer/__init__.py:881-909,1043-1053
+ *   gof_render_epilogue_backward_batch <- torch.autograd through those same ops
  *   gof_set_frame_sink   <- the .cpu() of rgb / depth / alpha after every frame       visualize.py:304-306,396-398
  *   gof_predictor_head   <- GaussianSplatPredictor_gtunet.forward after the UNet      src/gaussian_predictor.py:954-1008
  *   gof_pack_gather      <- (no counterpart; the multi-GPU exchange step: pack + all-gather over NVLink peer memory)
@@ -274,6 +275,14 @@ int gof_render_epilogue_batch(const float* out_color, const float* viewmatrix, i
                               float fovx, float fovy, float* normal_world, float* depth_normal,
                               gof_stream_t stream);
 
+/* Backward of the fused epilogue (what autograd does through the reference's torch ops, in one kernel and without
+ * atomics): from dL/dnormal_world [V,3,H,W] and dL/ddepth_normal [V,3,H,W] (either may be NULL = zero) produce
+ * dL/dout_color [V,9,H,W]: channels 3..5 (through the normalisation and rotation) and 6 (median depth, through the
+ * finite differences of the back-projected points); the other channels are written as zeros. */
+int gof_render_epilogue_backward_batch(const float* out_color, const float* viewmatrix, int32_t V, int32_t W, int32_t H,
+                                       float fovx, float fovy, const float* dL_dnormal_world, const float* dL_ddepth_normal,
+                                       float* dL_dout_color, gof_stream_t stream);
+
 /* Fused pack + all-gather of rendered frames over NVLink peer memory (the scene-sharded runner's one exchange
  * step; no reference counterpart -- the reference is single-GPU).  raster: this rank's [frames,9,H*W] output;
  * peer_ptrs_dev: DEVICE array of `world` pointers to every rank's gather buffer [total_frames,5,H*W] (a symmetric
@@ -282,6 +291,12 @@ int gof_render_epilogue_batch(const float* out_color, const float* viewmatrix, i
  * local frame into all ranks' buffers; the caller issues the symmetric-memory barrier that publishes them. */
 int gof_pack_gather(const float* raster, int32_t frames, int64_t pixels, const int64_t* peer_ptrs_dev, int32_t world,
                     void* multicast_ptr, int64_t dst_frame0, gof_stream_t stream);
+
+/* Test accessor: the per-(view, Gaussian) gradient accumulators of the LAST gof_backward[_batch] call on `ctx`,
+ * [V,P,20] float32 = {dL/dview2gaussian[10], dL/dcolor[3], dL/dopacity, dL/dmean2D (x, y, |x|+|y|), pad[3]} -- what
+ * the backward blend handed to the per-Gaussian backward, before the views are summed.  Copies them to `dst` (device
+ * pointer) and returns the byte size, or a negative error; dst == NULL only returns the size. */
+int64_t gof_backward_accumulators(GofContext* ctx, void* dst, int64_t dst_bytes, gof_stream_t stream);
 
 /* Test accessor: copy one named array of the opaque state into dst (device pointer).
  * Names: depths[P] f32, means2D[P,2] f32, conic_opacity[P,4] f32, view2gaussian[P,10] f32,

@@ -160,7 +160,7 @@ def test_batched_backward_equals_sum_of_per_view_backwards(kind):
     accumulates when the reference renders the views one call at a time)."""
     from f3d_gaus_b200 import cameras, synthetic
     from f3d_gaus_b200.diff_gof_rasterization import (GaussianRasterizationSettings_GOF, GaussianRasterizer_GOF,
-                                                     rasterize_views_autograd)
+                                                     backward_accumulators, rasterize_views_autograd)
     import math
     dev = "cuda"
     if kind == "unit":
@@ -187,44 +187,60 @@ def test_batched_backward_equals_sum_of_per_view_backwards(kind):
     g = torch.Generator().manual_seed(3)
     dL = torch.randn(V, 9, res, res, generator=g).to(dev)
 
-    def grads_of(fn):
-        for t in list(leaves.values()) + [shs]:
-            t.grad = None
-        m2d = torch.zeros_like(leaves["xyz"], requires_grad=True)
-        color = fn(m2d)
-        (color * dL).sum().backward()
-        out = {k: v.grad.clone() for k, v in leaves.items()}
-        out["shs"] = shs.grad.clone()
-        out["means2D"] = m2d.grad.clone()
-        return color.detach(), out
-
-    def per_view(m2d):
-        outs = []
-        for v in range(V):
-            rs = GaussianRasterizationSettings_GOF(res, res, tanfov, tanfov, 0.0, torch.zeros(1, device=dev), bg, 1.0,
-                                                   wv[v], fp[v], D, cc[v], False, False)
-            c, _ = GaussianRasterizer_GOF(rs)(leaves["xyz"], m2d, leaves["opacity"], shs=shs, scales=leaves["scaling"],
-                                              rotations=leaves["rotation"])
-            outs.append(c)
-        return torch.stack(outs)
-
-    def batched(m2d):
-        c, _ = rasterize_views_autograd(leaves["xyz"], m2d, leaves["opacity"], shs=shs, scales=leaves["scaling"],
-                                        rotations=leaves["rotation"], bg=bg, viewmatrices=wv, projmatrices=fp, campos=cc,
-                                        tanfovx=tanfov, tanfovy=tanfov, image_height=res, image_width=res, sh_degree=D)
-        return c
-
-    c1, g1 = grads_of(per_view)
-    c2, g2 = grads_of(batched)
-    assert torch.equal(c1.view(torch.int32), c2.view(torch.int32))
+    import numpy as np
+    import oracle_cpu
+    n = lambda t: t.detach().cpu().numpy()
     rel = lambda a, b: (a.double() - b.double()).norm().item() / max(b.double().norm().item(), 1e-30)
+    P = leaves["xyz"].shape[0]
+
+    # ---- batched: one forward + one backward for the V views, through autograd ----
+    m2d = torch.zeros_like(leaves["xyz"], requires_grad=True)
+    c2, _ = rasterize_views_autograd(leaves["xyz"], m2d, leaves["opacity"], shs=shs, scales=leaves["scaling"],
+                                     rotations=leaves["rotation"], bg=bg, viewmatrices=wv, projmatrices=fp, campos=cc,
+                                     tanfovx=tanfov, tanfovy=tanfov, image_height=res, image_width=res, sh_degree=D)
+    (c2 * dL).sum().backward()
+    g2 = {"xyz": leaves["xyz"].grad, "scaling": leaves["scaling"].grad, "rotation": leaves["rotation"].grad,
+          "opacity": leaves["opacity"].grad, "shs": shs.grad, "means2D": m2d.grad}
+    acc = backward_accumulators(leaves["xyz"].device, V, P)     # [V,P,20]: what the batched K10 consumed, per view
+
+    # ---- per view: V reference-shaped forward + backward calls, gradients summed as autograd would ----
+    names = {"xyz": "dL_dmeans3D", "scaling": "dL_dscales", "rotation": "dL_drotations", "opacity": "dL_dopacity",
+             "shs": "dL_dsh", "means2D": "dL_dmeans2D"}
+    quad = ("xyz", "scaling", "rotation")
+    g1 = {k: 0.0 for k in names}
+    E_pv = {k: 0.0 for k in quad}
+    E_b = {k: 0.0 for k in quad}
+    for v in range(V):
+        c = {"W": res, "H": res, "D": D, "tanfovx": tanfov, "tanfovy": tanfov, "kernel_size": 0.0, "scale_modifier": 1.0,
+             "bg": bg, "means3D": leaves["xyz"].detach(), "opacities": leaves["opacity"].detach(),
+             "scales": leaves["scaling"].detach(), "rotations": leaves["rotation"].detach(), "shs": shs.detach(),
+             "viewmatrix": wv[v].contiguous(), "projmatrix": fp[v].contiguous(), "campos": cc[v].contiguous()}
+        o = refgpu.OursRun()
+        f = o.forward(c, decode_state=True)
+        assert torch.equal(f["out_color"].view(torch.int32), c2[v].detach().view(torch.int32)), f"view {v}"
+        gv = o.backward(c, dL[v])
+        for k, kk in names.items():
+            g1[k] = g1[k] + gv[kk]
+        # both sets of per-view blend gradients through the float64 oracle of the per-Gaussian map
+        cn = oracle_cpu.case_to_numpy(c)
+        for dst, dq, dcol in ((E_pv, gv["dL_dview2gaussian"], gv["dL_dcolors"]), (E_b, acc[v, :, 0:10], acc[v, :, 10:13])):
+            ex = oracle_cpu.preprocess_backward(cn, n(f["radii"]), n(f["clamped"]), n(dq.contiguous()), n(dcol.contiguous()), f64=True)
+            for k in quad:
+                dst[k] = dst[k] + ex[names[k]]
+
     for k in ("opacity", "shs", "means2D"):
-        assert rel(g2[k], g1[k]) <= 1e-5, (k, rel(g2[k], g1[k]))
-    # quadric gradients: float atomics are unordered and the views are summed in a different order; the map amplifies
-    # that noise by ~(t/s)^2 (~4e3 on the unit cloud, ~6e5 at F3D-Gaus scales)
-    tol = 2e-2 if kind == "unit" else 0.5
-    for k in ("xyz", "scaling", "rotation"):
-        assert rel(g2[k], g1[k]) <= tol, (k, rel(g2[k], g1[k]))
+        assert rel(g2[k].reshape(g1[k].shape), g1[k]) <= 1e-5, (k, rel(g2[k].reshape(g1[k].shape), g1[k]))
+    # Quadric gradients (xyz, scaling, rotation).  K10 is the exact (double) map of the float32 blend gradients it is
+    # handed, per view; the two paths hand it blend gradients that differ by the order of their float atomics (~1e-7),
+    # and the map amplifies that by ~(t/s)^2 (~4e3 on the unit cloud, ~6e5 at F3D-Gaus scales).  So the bound is
+    # DERIVED, not chosen: each path must reproduce the float64 map of ITS OWN per-view blend gradients within the bar,
+    # and the two may differ by what the exact propagation of the two inputs gives.
+    for k in quad:
+        exact_b, exact_pv = torch.from_numpy(np.asarray(E_b[k])), torch.from_numpy(np.asarray(E_pv[k]))
+        assert rel(g2[k].cpu(), exact_b) <= 1e-4, (k, "batched", rel(g2[k].cpu(), exact_b))
+        assert rel(g1[k].cpu(), exact_pv) <= 1e-4, (k, "per view", rel(g1[k].cpu(), exact_pv))
+        carried = rel(exact_b, exact_pv)
+        assert rel(g2[k], g1[k]) <= 1e-3 + 1.1 * carried, (k, rel(g2[k], g1[k]), carried)
 
 
 @pytest.mark.parametrize("exact", [False, True])

@@ -111,9 +111,20 @@ def grad_close(name, a, b, rtol=1e-3):
     assert rel <= rtol, f"{name}: relative L2 error {rel:.3e}"
 
 
-BWD_CASES = ["f3d_s64_r256_view2", "f3d_s256_r256_canon", "f3d_s256_r256_view2", "unit_p4096_200x136",
-             "unit_p20000_sh3_bg", "f3d_colors_ks_mod", "single_gaussian"] + \
-            ["golden_" + n for n in cases.GOLDEN_CASES]
+def _aggregated_196k(d):
+    """BASELINE configs[3] size: three f3d-like sets expressed in one world frame, 196 608 Gaussians,
+    rendered at 256x256 from orbit view 3."""
+    from f3d_gaus_b200 import cameras, synthetic
+    pc = synthetic.concat_sets([synthetic.f3d_like(s, 256) for s in (0, 1, 2)])
+    cams = cameras.orbit_cameras(8)
+    return cases.make_case(pc, cams.world_view[3], cams.full_proj[3], cams.centers[3], W=256, H=256, fov_deg=13.164, device=d)
+
+
+FWD_CASES["f3d_agg196k_r256_view3"] = _aggregated_196k
+
+BWD_CASES = ["f3d_s64_r256_view2", "f3d_s256_r256_canon", "f3d_s256_r256_view2", "f3d_s256_r512_view2",
+             "f3d_agg196k_r256_view3", "unit_p4096_200x136", "unit_p20000_sh3_bg", "f3d_colors_ks_mod",
+             "single_gaussian"] + ["golden_" + n for n in cases.GOLDEN_CASES]
 
 
 # Outputs of the backward BLEND (K9) are well-conditioned sums: 1e-3 relative, element-wise.
@@ -171,16 +182,22 @@ def test_backward(name):
     for k in QUADRIC_GRADS:
         exact = torch.from_numpy(ex[k])
         e_ref, e_ours = rel_l2(ref[k].cpu(), exact), rel_l2(stage[k].cpu(), exact)
-        # (the absolute floor covers tiny, well-conditioned cases where the reference happens to round exactly)
-        assert e_ours <= 2 * e_ref + 3e-3, f"{k}: ours {e_ours:.3e} vs reference {e_ref:.3e} from the float64 value"
-        # (2) end to end: within the bar, or indistinguishable from the reference's own float32 noise (run-to-run
-        #     atomics order, its rounding distance from the float64 value) plus the exactly propagated difference
-        #     of the blend gradients
+        # (2) the stage on identical inputs: K10 evaluates the map in double, so it must be at least as close to the
+        #     float64 value as the reference's float32 evaluation is, and within the north-star bar in absolute terms
+        assert e_ours <= e_ref + 1e-6, f"{k}: ours {e_ours:.3e} vs reference {e_ref:.3e} from the float64 value"
+        assert e_ours <= 1e-3, f"{k}: ours {e_ours:.3e} from the float64 value"
+        # (3) end to end.  ours = exact(dq_ours) (+1e-7), ref = exact(dq_ref) + err_ref with |err_ref| = e_ref |exact|:
+        #     |ours - ref| <= carried + e_ref, where `carried` is the in-tolerance (~1e-7) difference of the two blend
+        #     gradients propagated exactly through the ill-conditioned map, and the reference's run-to-run spread
+        #     (unordered float atomics) bounds how well `ref` is defined at all
         noise = max(rel_l2(refs[1][k], ref[k]), e_ref)
         carried = rel_l2(torch.from_numpy(ex_o[k]), exact)
         e = rel_l2(ours[k], ref[k])
-        assert e <= 1e-3 + 8 * noise + 2 * carried, \
+        assert e <= 1e-3 + 1.1 * (noise + carried), \
             f"{k}: end-to-end rel L2 {e:.3e} vs reference float32 noise {noise:.3e}, carried {carried:.3e}"
+        # (4) and against the exact map of OUR blend gradients the end-to-end result is within the bar outright
+        e_self = rel_l2(ours[k].cpu(), torch.from_numpy(ex_o[k]))
+        assert e_self <= 1e-3, f"{k}: ours end to end {e_self:.3e} from the float64 map of its own blend gradients"
     if c.get("shs") is not None:
         grad_close("dL_dsh(stage)", gsh, ref["dL_dsh"])
 
@@ -229,3 +246,45 @@ def test_background_only_where_empty():
     assert torch.allclose(o["out_color"][0], torch.full_like(o["out_color"][0], 0.25))
     assert torch.allclose(o["out_color"][2], torch.full_like(o["out_color"][2], 0.75))
     assert float(o["out_color"][3:].abs().sum()) == 0.0
+
+
+@needs_ref
+def test_mark_visible_bit_exact():
+    """gof_mark_visible against Rasterizer::markVisible (rasterizer_impl.cu:54-66,174-186 -> in_frustum,
+    auxiliary.h:177-202): the near-plane test p_view.z <= 0.2 only, bit for bit -- including view depths exactly at the
+    threshold and one ulp on either side, NaN and infinite coordinates."""
+    import numpy as np
+    from f3d_gaus_b200.diff_gof_rasterization import _C
+    lib = refgpu.ref_lib()
+
+    def both(xyz, vm, pm):
+        ours = _C.mark_visible(xyz, vm, pm)
+        theirs = torch.zeros(xyz.shape[0], dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        lib.ref_mark_visible(xyz.shape[0], xyz.data_ptr(), vm.data_ptr(), pm.data_ptr(), theirs.data_ptr())
+        torch.cuda.synchronize()
+        assert ours.dtype == torch.bool
+        assert torch.equal(ours, theirs.bool()), f"{int((ours != theirs.bool()).sum())} of {xyz.shape[0]} differ"
+        return ours
+
+    # identity camera: p_view.z == z exactly; thresholds around float(0.2)
+    t = np.float32(0.2)
+    zs = np.array([t, np.nextafter(t, np.float32(0)), np.nextafter(t, np.float32(1)), 0.0, -0.0, -1.0, 1e-30, 0.19999, 0.20001,
+                   np.inf, -np.inf, np.nan, 7.5], dtype=np.float32)
+    xyz = torch.zeros((len(zs), 3))
+    xyz[:, 2] = torch.from_numpy(zs)
+    eye = torch.eye(4, device="cuda")
+    vis = both(xyz.cuda().contiguous(), eye, eye)
+    assert vis.tolist() == [False, False, True, False, False, False, False, False, True, True, False, True, True]
+    # oblique cameras: dense samples in a thin slab around the near plane (the float32 sum decides), plus the f3d cloud
+    for name in ("f3d_s256_r256_view2", "unit_p20000_sh3_bg"):
+        c = FWD_CASES[name]("cuda")
+        g = torch.Generator().manual_seed(3)
+        P = 200000
+        vm = c["viewmatrix"]
+        cam = torch.randn(P, 3, generator=g)
+        cam[:, 2] = 0.2 + (torch.rand(P, generator=g) - 0.5) * 4e-6           # view depth within +-2e-6 of the plane
+        world = (torch.cat([cam, torch.ones(P, 1)], dim=1).cuda() @ vm.inverse())[:, :3].contiguous()
+        vis = both(world, vm, c["projmatrix"])
+        assert 0.2 < float(vis.float().mean()) < 0.8                          # the slab really straddles the threshold
+        both(c["means3D"], vm, c["projmatrix"])
