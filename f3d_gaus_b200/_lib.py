@@ -78,6 +78,7 @@ SIGNATURES = {
     "gof_predictor_head": (c_int32, [POINTER(GofHeadParams)] + [c_void_p] * 15),
     "gof_set_frame_sink": (c_int32, [c_void_p, c_void_p, c_size_t, c_int32]),
     "gof_num_rendered": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, POINTER(c_int32)]),
+    "gof_num_rendered_async": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "gof_backward": (c_int32, [c_void_p, POINTER(GofParams), POINTER(GofInputs), c_int32, c_void_p,
                                c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, POINTER(GofGrads), c_void_p]),
     "gof_backward_batch": (c_int32, [c_void_p, POINTER(GofParams), POINTER(GofInputs), c_int32, c_int32, c_int64, c_void_p,

@@ -4,6 +4,7 @@
 #include "gof_common.cuh"
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -11,6 +12,17 @@
 namespace gof {
 
 static thread_local char g_err[512] = "";
+
+int pdl_mask()
+{
+	static const int mask = [] {
+		const char* off = getenv("GOF_NO_PDL");
+		if (off && off[0] && off[0] != '0') return 0;
+		const char* m = getenv("GOF_PDL_MASK");
+		return m && m[0] ? atoi(m) : (PDL_SCAN | PDL_SCATTER | PDL_SORT | PDL_PRE_BWD);
+	}();
+	return mask;
+}
 
 void set_error(const char* fmt, ...)
 {
@@ -408,6 +420,14 @@ int gof_num_rendered(GofContext* ctx, const void* geom, int32_t P, int32_t V, go
 	GOF_CUDA_CHECK(cudaStreamSynchronize(s));
 	for (int v = 0; v < V; v++) num_rendered[v] = ctx->pinned[MAILBOX_HEAD + v];
 	if (ctx->pinned[1]) { set_error("num_rendered=%d exceeded the binning capacity", ctx->pinned[0]); return GOF_EOVERFLOW; }
+	return GOF_OK;
+}
+
+int gof_num_rendered_async(const void* geom, int32_t P, int32_t V, int32_t* host_dst, gof_stream_t stream)
+{
+	if (!geom || !host_dst || P <= 0 || V <= 0 || V > GOF_MAX_VIEWS) { set_error("gof_num_rendered_async: bad argument"); return GOF_EINVAL; }
+	GeomState g = GeomState::carve(align_base(geom), (size_t)P, (size_t)V);
+	GOF_CUDA_CHECK(cudaMemcpyAsync(host_dst, g.mailbox, (MAILBOX_HEAD + V) * sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
 	return GOF_OK;
 }
 

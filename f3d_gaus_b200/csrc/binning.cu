@@ -92,6 +92,8 @@ tile_scan_kernel(int VT, int T, int V, const uint32_t* __restrict__ counts, uint
 	__shared__ uint32_t s_part[SCAN_THREADS];
 	__shared__ uint32_t s_max[SCAN_THREADS / 32];
 	__shared__ uint32_t s_bucket[64], s_bmax;
+	pdl_trigger();
+	pdl_wait();                    // the tile counts come from the preprocess
 	const int tid = threadIdx.x;
 	const int per = (VT + SCAN_THREADS - 1) / SCAN_THREADS;
 	const int lo = min(VT, tid * per), hi = min(VT, lo + per);
@@ -168,6 +170,8 @@ scatter_kernel(int P, int T, dim3 grid, const uint32_t* __restrict__ tiles_touch
                const int32_t* __restrict__ mailbox)
 {
 	__shared__ uint32_t s_cur[SCATTER_TILES];
+	pdl_trigger();
+	pdl_wait();                    // mailbox / cursors come from the tile scan
 	if (mailbox[1]) return;   // binning capacity exceeded (sync-free mode): outputs are invalid, write nothing
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	const int view = blockIdx.y;
@@ -323,6 +327,8 @@ tile_sort_gather_kernel(int P, int T, dim3 grid, int W, int H, float focal_x, fl
                         const uint32_t* __restrict__ tile_order)
 {
 	__shared__ uint64_t s_e[SORT_CAP];
+	pdl_trigger();
+	pdl_wait();                    // bucket entries come from the scatter
 	if (mailbox[1]) return;
 	const int gt = (int)tile_order[blockIdx.x];   // global tile index (view * T + tile), largest buckets first
 	const uint2 range = ranges[gt];
@@ -422,16 +428,15 @@ extract_offsets_kernel(int P, const uint32_t* __restrict__ tiles_touched, uint32
 
 int launch_tile_scan(const Frame& f, const GeomState& g, const ImgState& im, int64_t capacity, cudaStream_t s)
 {
-	tile_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(f.V * f.T, f.T, f.V, im.tile_counts, im.ranges, im.tile_cursor, g.mailbox,
-	                                            (long long)capacity, im.tile_order);
-	GOF_CUDA_CHECK(cudaGetLastError());
+	GOF_CUDA_CHECK(launch_chained(PDL_SCAN, tile_scan_kernel, dim3(1), dim3(SCAN_THREADS), 0, s, f.V * f.T, f.T, f.V, im.tile_counts, im.ranges,
+	                              im.tile_cursor, g.mailbox, (long long)capacity, im.tile_order));
 	return GOF_OK;
 }
 
 int launch_tile_scan_raw(int T, const uint32_t* counts, uint2* ranges, uint32_t* cursor, int32_t* mailbox, cudaStream_t s)
 {
-	tile_scan_kernel<<<1, SCAN_THREADS, 0, s>>>(T, T, 1, counts, ranges, cursor, mailbox, (long long)1 << 40, nullptr);
-	GOF_CUDA_CHECK(cudaGetLastError());
+	GOF_CUDA_CHECK(launch_chained(PDL_SCAN, tile_scan_kernel, dim3(1), dim3(SCAN_THREADS), 0, s, T, T, 1, counts, ranges, cursor, mailbox,
+	                              (long long)1 << 40, (uint32_t*)nullptr));
 	return GOF_OK;
 }
 
@@ -440,12 +445,11 @@ int launch_binning(const Frame& f, const GeomState& g, const ImgState& im, const
 {
 	if (capacity <= 0) return GOF_OK;
 	dim3 blocks((f.P + 255) / 256, f.V);
-	scatter_kernel<<<blocks, 256, 0, s>>>(f.P, f.T, f.grid, g.tiles_touched, g.rect, g.depths, im.tile_cursor, b.entries,
-	                                      g.mailbox);
-	GOF_CUDA_CHECK(cudaGetLastError());
-	tile_sort_gather_kernel<<<f.V * f.T, SORT_THREADS, 0, s>>>(f.P, f.T, f.grid, f.W, f.H, f.focal_x, f.focal_y, ray_pad, im.ranges,
-	                                                           b.entries, g.rec, b.point_list, b.slab, b.block_mask, g.mailbox, im.tile_order);
-	GOF_CUDA_CHECK(cudaGetLastError());
+	GOF_CUDA_CHECK(launch_chained(PDL_SCATTER, scatter_kernel, blocks, dim3(256), 0, s, f.P, f.T, f.grid, g.tiles_touched, g.rect, g.depths,
+	                              im.tile_cursor, b.entries, g.mailbox));
+	GOF_CUDA_CHECK(launch_chained(PDL_SORT, tile_sort_gather_kernel, dim3(f.V * f.T), dim3(SORT_THREADS), 0, s, f.P, f.T, f.grid, f.W, f.H,
+	                              f.focal_x, f.focal_y, ray_pad, im.ranges, b.entries, g.rec, b.point_list, b.slab, b.block_mask,
+	                              g.mailbox, im.tile_order));
 	return GOF_OK;
 }
 

@@ -42,7 +42,7 @@ constexpr int SLAB_BYTES = 80;
 constexpr size_t ALIGN = 256;
 __host__ __device__ inline size_t align_up(size_t x, size_t a = ALIGN) { return (x + a - 1) / a * a; }
 
-constexpr int MAILBOX_HEAD = 4;   // mailbox ints: {R_total, overflow, max tile count, -, R_view[0..V-1]}
+constexpr int MAILBOX_HEAD = GOF_MAILBOX_HEAD;   // mailbox ints: {R_total, overflow, max tile count, -, R_view[0..V-1]}
 
 // ---- opaque state layouts (our own; the reference's are rasterizer_impl.cu:188-243) -------
 // All per-Gaussian arrays are [V, P] (view-major); V = 1 for the single-frame entry points.
@@ -87,6 +87,38 @@ void set_error(const char* fmt, ...);
 			return GOF_ECUDA;                                                            \
 		}                                                                                \
 	} while (0)
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------
+// The stages of a frame are a chain of dependent kernels on one stream.  Each stage is launched with the
+// programmatic-stream-serialization attribute: its CTAs may be scheduled as soon as every CTA of the previous
+// stage has executed pdl_trigger() (first thing it does) and SM resources free up, and they block in pdl_wait()
+// (first thing THEY do, before touching any global memory) until the previous stage has completed and flushed.
+// What overlaps is the launch latency and CTA ramp-up of stage k+1 with the tail of stage k -- 2-4 us per edge,
+// which matters for the single-frame call (five ~5-25 us stages in front of the blend).  The blend itself is launched
+// WITHOUT it: its CTAs would be placed while the sort's still occupy the SMs, and for a single frame (256 CTAs on 148
+// SMs) that placement is less even than a launch into the drained GPU (measured: 5% slower per frame).
+// GOF_PDL_MASK selects the edges (PdlEdge bits), GOF_NO_PDL=1 disables all.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+enum PdlEdge { PDL_SCAN = 1, PDL_SCATTER = 2, PDL_SORT = 4, PDL_BLEND = 8, PDL_PRE_BWD = 16 };
+int pdl_mask();                 // edges on which PDL is used: GOF_PDL_MASK (default: every edge but the blend's), 0 with GOF_NO_PDL=1
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chained(int edge, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args)
+{
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = grid;
+	cfg.blockDim = block;
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = s;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = (pdl_mask() & edge) ? 1 : 0;
+	return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // Camera-dependent scalars shared by the stages.
 struct Frame {

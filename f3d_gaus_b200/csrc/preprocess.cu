@@ -324,6 +324,7 @@ preprocess_kernel(int P, int D, int M,
 	// Tile histogram of this block's duplicates: counted in shared memory, flushed with one global
 	// atomic per touched tile (grids above HIST_TILES tiles count straight into global memory).
 	__shared__ uint32_t s_hist[HIST_TILES];
+	pdl_trigger();                 // the tile scan may be scheduled behind this grid (it waits for our completion)
 	const int T = grid.x * grid.y;
 	const bool use_hist = T <= HIST_TILES;
 	if (use_hist) for (int i = threadIdx.x; i < T; i += PRE_THREADS) s_hist[i] = 0;

@@ -250,6 +250,8 @@ preprocess_bwd_kernel(int P, int V, int D, int M, const float* __restrict__ mean
                       float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh,
                       float* __restrict__ dL_dscales, float* __restrict__ dL_drot, float* __restrict__ dL_dv2g)
 {
+	pdl_trigger();
+	pdl_wait();                    // the accumulators come from the backward blend
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	if (idx >= P) return;
 
@@ -326,11 +328,10 @@ int launch_preprocess_bwd(const GofParams& prm, const GofInputs& in, int V, cons
                           cudaStream_t s)
 {
 	const int P = prm.P;
-	preprocess_bwd_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, V, prm.D, prm.M, in.means3D, radii, in.shs, g.clamped,
-		in.scales, in.rotations, in.viewmatrix, in.campos, gacc, grads.dL_dmeans2D, grads.dL_dcolors,
+	GOF_CUDA_CHECK(launch_chained(PDL_PRE_BWD, preprocess_bwd_kernel, dim3((P + 255) / 256), dim3(256), 0, s, P, V, prm.D, prm.M, in.means3D, radii,
+		in.shs, g.clamped, in.scales, in.rotations, in.viewmatrix, in.campos, gacc, grads.dL_dmeans2D, grads.dL_dcolors,
 		grads.dL_dopacity, grads.dL_dmeans3D, grads.dL_dcov3D, grads.dL_dsh, grads.dL_dscales,
-		grads.dL_drotations, grads.dL_dview2gaussian);
-	GOF_CUDA_CHECK(cudaGetLastError());
+		grads.dL_drotations, grads.dL_dview2gaussian));
 	return GOF_OK;
 }
 

@@ -52,11 +52,13 @@ __device__ __forceinline__ void red_global_v4(float* addr, float4 v)
 #define GOF_BWD_IEEE_RCP 0        // 1: the correctly rounded float reciprocal / sqrt sequences (A/B switch)
 #endif
 __device__ __forceinline__ float rcp_f32(float x) { return GOF_BWD_IEEE_RCP ? __frcp_rn(x) : rcp_approx(x); }
+#if GOF_BWD_IEEE_RCP || !GOF_BWD_F32_QUADRIC
 __device__ __forceinline__ double rcp_refined(float x)
 {
 	const double r = (double)rcp_f32(x);
 	return fma(r, fma(-(double)x, r, 1.0), r);
 }
+#endif
 
 __global__ void __launch_bounds__(BWD_THREADS, GOF_BWD_MIN_CTAS)
 render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int tiles_per_view, int tiles_x,
@@ -75,6 +77,7 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 
 	const int tid = threadIdx.x;
 	const int warp = tid >> 5, lane = tid & 31;
+	pdl_trigger();                 // the per-Gaussian backward may be scheduled behind this grid
 	// CTAs are launched longest-list-first: blockIdx.x -> (view, tile) through tile_order (render_fwd.cu)
 	const uint32_t gt = tile_order[blockIdx.x];
 	const int view = (int)(gt / (uint32_t)tiles_per_view);

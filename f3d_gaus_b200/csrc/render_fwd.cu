@@ -41,6 +41,12 @@ namespace {
 #ifndef GOF_FWD_CHUNK
 #define GOF_FWD_CHUNK 128
 #endif
+#ifndef GOF_FWD_SCAN64
+#define GOF_FWD_SCAN64 1          // pass 2 pops survivors from a word + three-word shift register (A/B switch; 0: word index + refill cascade)
+#endif
+#ifndef GOF_FWD_FOLD_W
+#define GOF_FWD_FOLD_W 1          // fast blend: normals / distortion accumulate with w = alpha*T formed once
+#endif
 constexpr int CHUNK = GOF_FWD_CHUNK;       // records per pipeline stage (10 KB at 128)
 constexpr int STAGES = GOF_FWD_STAGES;
 constexpr int NW = CHUNK / 32;             // 32-record words per chunk
@@ -84,17 +90,30 @@ __device__ __forceinline__ bool blend_pair(PixState& s, const PairGeom& g, float
 	const float A1 = __fsub_rn(1.0f, T);
 	const float m2 = __fmul_rn(m, m);
 	const float err = __fmaf_rn(-s.dist1, __fadd_rn(m, m), __fmaf_rn(A1, m2, s.dist2));
-	s.distortion = __fmaf_rn(T, __fmul_rn(alpha, err), s.distortion);
-	s.dist1 = __fmaf_rn(T, __fmul_rn(alpha, m), s.dist1);
-	s.dist2 = __fmaf_rn(T, __fmul_rn(alpha, m2), s.dist2);
+	if (EXACT || !GOF_FWD_FOLD_W) {
+		s.distortion = __fmaf_rn(T, __fmul_rn(alpha, err), s.distortion);
+		s.dist1 = __fmaf_rn(T, __fmul_rn(alpha, m), s.dist1);
+		s.dist2 = __fmaf_rn(T, __fmul_rn(alpha, m2), s.dist2);
+	} else {
+		// the relaxed channels (normals, distortion) share one weight w = alpha*T (one rounding instead of two)
+		const float w = __fmul_rn(alpha, T);
+		s.distortion = __fmaf_rn(w, err, s.distortion);
+		s.dist1 = __fmaf_rn(w, m, s.dist1);
+		s.dist2 = __fmaf_rn(w, m2, s.dist2);
+		s.C[3] = __fmaf_rn(-w, nn0, s.C[3]);
+		s.C[4] = __fmaf_rn(-w, nn1, s.C[4]);
+		s.C[5] = __fmaf_rn(-w, nn2, s.C[5]);
+	}
 
 	s.C[0] = __fmaf_rn(T, __fmul_rn(alpha, d.x), s.C[0]);
 	s.C[1] = __fmaf_rn(T, __fmul_rn(alpha, d.y), s.C[1]);
 	s.C[2] = __fmaf_rn(T, __fmul_rn(alpha, d.z), s.C[2]);
-	// view-space normal is -n/|n|
-	s.C[3] = __fmaf_rn(-T, __fmul_rn(alpha, nn0), s.C[3]);
-	s.C[4] = __fmaf_rn(-T, __fmul_rn(alpha, nn1), s.C[4]);
-	s.C[5] = __fmaf_rn(-T, __fmul_rn(alpha, nn2), s.C[5]);
+	if (EXACT || !GOF_FWD_FOLD_W) {
+		// view-space normal is -n/|n|
+		s.C[3] = __fmaf_rn(-T, __fmul_rn(alpha, nn0), s.C[3]);
+		s.C[4] = __fmaf_rn(-T, __fmul_rn(alpha, nn1), s.C[4]);
+		s.C[5] = __fmaf_rn(-T, __fmul_rn(alpha, nn2), s.C[5]);
+	}
 	if (T > 0.5f) {           // median depth: last Gaussian seen while T > 0.5
 		s.C[6] = t;
 		s.max_contributor = contributor;
@@ -125,6 +144,8 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 
 	const int tid = threadIdx.x;
 	const int warp = tid >> 5, lane = tid & 31;
+	pdl_trigger();
+	pdl_wait();                    // ranges / slab / block masks come from the binning stages
 	// CTAs are launched longest-list-first: blockIdx.x -> (view, tile) through tile_order
 	const uint32_t gt = tile_order[blockIdx.x];
 	const int view = (int)(gt / (uint32_t)T);
@@ -241,6 +262,25 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 			// `cur` = the word being consumed, `wsel` its index; m[1..] stay loop-invariant.  Two survivors are
 			// taken per trip: their exact evaluations (double division, exp) are independent dependency chains
 			// that interleave, the two blends then run in list order.
+#if GOF_FWD_SCAN64
+			static_assert(NW == 4, "the survivor walk is written for 128-record chunks");
+			// `cur` = the word being consumed, the others wait in a three-word shift register
+			uint32_t cur = m[0], w1 = m[1], w2 = m[2], w3 = m[3], jbase = 0;
+			auto next = [&](uint32_t& j) -> bool {      // pop the lane's next survivor (list order); false when none is left
+				while (cur == 0) {
+					if ((w1 | w2 | w3) == 0) return false;
+					cur = w1; w1 = w2; w2 = w3; w3 = 0; jbase += 32;
+				}
+				j = jbase + (uint32_t)__ffs((int)cur) - 1u;
+				cur &= cur - 1u;
+				return true;
+			};
+			for (;;) {
+				uint32_t ja, jb;
+				if (!next(ja)) break;
+				const bool hb = next(jb);
+				if (!hb) jb = ja;
+#else
 			uint32_t cur = m[0], wsel = 0;
 			auto refill = [&]() -> bool {      // make `cur` non-empty; false when the lane has no survivors left
 				if (cur != 0) return true;
@@ -256,6 +296,7 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 				const bool hb = refill();
 				uint32_t jb = ja;
 				if (hb) { jb = 32u * wsel + (uint32_t)__ffs((int)cur) - 1u; cur &= cur - 1u; }
+#endif
 				const uint32_t ra = rec + ja * SLAB_BYTES, rb = rec + jb * SLAB_BYTES;
 				const float4 a1 = lds128(ra + 16), a2 = lds128(ra + 32), a3 = lds128(ra + 48), a4 = lds128(ra + 64);
 				const float4 b1 = lds128(rb + 16), b2 = lds128(rb + 32), b3 = lds128(rb + 48), b4 = lds128(rb + 64);
@@ -352,8 +393,9 @@ int launch_render_fwd(const GofParams& prm, const Frame& f, const GeomState& g, 
 	auto launch = [&](auto kernel) {
 		// per device and per function; cheap enough to set on every launch (one process may drive several GPUs)
 		if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return;
-		kernel<<<grid, FWD_THREADS, smem, s>>>(im.ranges, im.tile_order, f.T, (int)f.grid.x, b.slab, prm.W, prm.H, f.focal_x, f.focal_y,
-		                                       background, bg_stride, im.final_T, im.n_contrib, out_color, g.mailbox, b.block_mask, sink, sink_hwc);
+		launch_chained(PDL_BLEND, kernel, grid, dim3(FWD_THREADS), smem, s, im.ranges, im.tile_order, f.T, (int)f.grid.x, b.slab, prm.W, prm.H,
+		               f.focal_x, f.focal_y, background, bg_stride, im.final_T, im.n_contrib, out_color, g.mailbox, b.block_mask, sink,
+		               sink_hwc);
 	};
 	const bool exact = (prm.flags & GOF_FLAG_EXACT_BLEND) != 0;
 	if (sink) { if (exact) launch(render_fwd_kernel<true, true>); else launch(render_fwd_kernel<false, true>); }

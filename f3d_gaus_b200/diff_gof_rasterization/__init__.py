@@ -268,6 +268,7 @@ class BatchWorkspace:
         self.geom = self.img = self.binning = None
         self.key = None
         self.capacity_hint = 0
+        self.mailbox_host = None
 
     def _ensure(self, P, W, H, V):
         gsz, isz, bsz = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
@@ -282,6 +283,28 @@ class BatchWorkspace:
             self.key = (P, W, H, V)
         if self.binning is None or self.binning.numel() < bsz.value:
             self.binning = torch.empty(bsz.value, **opts)
+
+    def finish_async(self):
+        """Non-blocking `finish`: enqueue the mailbox copy on the current stream (gof_num_rendered_async); read the
+        result with `finish_poll()` once an event recorded behind this call has completed."""
+        P, W, H, V = self.key
+        if self.mailbox_host is None or self.mailbox_host.numel() != 4 + V:
+            self.mailbox_host = torch.zeros(4 + V, dtype=torch.int32).pin_memory()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib.gof_num_rendered_async(self.geom.data_ptr(), P, V, self.mailbox_host.data_ptr(),
+                                                       _lib.raw_stream(self.device)), "gof_num_rendered_async")
+
+    def finish_poll(self):
+        """Per-view R of the batch `finish_async` was enqueued behind, or None on overflow (the workspace is grown)."""
+        m = self.mailbox_host.tolist()
+        R = m[4:]
+        if m[1]:
+            self.capacity_hint = int(1.5 * m[0]) + 1024
+            self.binning = None
+            return None
+        if 1.25 * sum(R) > self.capacity_hint:
+            self.capacity_hint = int(1.5 * sum(R)) + 1024
+        return R
 
     def finish(self):
         P, W, H, V = self.key

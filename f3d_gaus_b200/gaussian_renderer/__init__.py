@@ -4,6 +4,7 @@
   depths_to_points / depth_to_normal (:881-909)
   render_predicted_more_v2_gof_in (:1070-1228) point integration for mesh extraction (rasterizer.integrate)
   HostFrameSink                   render_views + pipelined D2H of rgb/depth/alpha (the loops' `.cpu()` return path)
+  SceneStreamer                   the multi-scene loop as a 2-slot pipeline: H2D of scene k+1 | render k | frames of k-1 to host
   render_views                    all V views of a scene in one batched pass (what the reference's render loops do frame by frame)
   render                          the vanilla signature (src/gaussian-splatting/gaussian_renderer/__init__.py:18-100)
 
@@ -324,6 +325,106 @@ class HostFrameSink:
                 return None
             out += r
         return out
+
+
+class SceneStreamer:
+    """Pipelined multi-scene render loop to HOST memory -- the streaming form of the reference's
+    `for batch: for scene: for view: render(...).cpu()` loops (visualize.py:221,293-306,387-402).
+
+    `slots` scenes are in flight: while scene k renders, the H2D copy of scene k+1 runs on a copy stream and the
+    frames of scene k-1 drain to pinned host memory (stored by the blend kernel itself, `zero_copy`, or packed on the
+    device and copied by the DMA engine on a third stream).  Nothing synchronises the host except `collect()`, which
+    waits on ONE event: that of the oldest outstanding scene.  The binning-overflow check of a scene rides on the same
+    event (BatchWorkspace.finish_async), so it does not stall the scenes behind it; an overflowed scene is re-rendered
+    inside `collect()` after its workspace has grown.
+
+        st = SceneStreamer(V, H, W, device, cams, bg, cfg)
+        for k, scene in enumerate(scenes):                 # scene: staging.PinnedScene (one pinned slab)
+            if st.pending == st.slots:
+                frames, R = st.collect()                   # [V,5,H,W] pinned host view of scene k - slots: consume / copy it
+            st.submit(scene)
+        while st.pending: frames, R = st.collect()
+
+    The host view returned by `collect()` is reused by the submit after the next `slots - 1` ones."""
+
+    def __init__(self, V: int, H: int, W: int, device, world_view_transforms, full_proj_transforms, camera_centers,
+                 bg_color, cfg, slots: int = 2, zero_copy: bool = True, channels_last: bool = True):
+        self.V, self.H, self.W = V, H, W
+        self.device = torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.cams = (world_view_transforms.reshape(V, 4, 4), full_proj_transforms.reshape(V, 4, 4), camera_centers.reshape(V, 3))
+        self.bg, self.cfg = bg_color, cfg
+        self.slots = max(1, int(slots))
+        self.zero_copy = bool(zero_copy)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.d2h_stream = None if self.zero_copy else torch.cuda.Stream(device=self.device)
+        self.slot = []
+        for _ in range(self.slots):
+            if self.zero_copy and channels_last:
+                host = torch.empty((V, H, W, 5), dtype=torch.float32).pin_memory().permute(0, 3, 1, 2)
+            else:
+                host = torch.empty((V, 5, H, W), dtype=torch.float32).pin_memory()
+            self.slot.append({"host": host, "slab": None, "ws": BatchWorkspace(self.device), "scene": None, "pc": None,
+                              "staging": None if self.zero_copy else torch.empty((V, 5, H, W), dtype=torch.float32, device=self.device),
+                              "raster": torch.empty((V, 9, H, W), dtype=torch.float32, device=self.device),
+                              "h2d": torch.cuda.Event(), "done": torch.cuda.Event()})
+        self.head = 0          # next slot to submit into
+        self.pending = 0       # scenes submitted and not yet collected
+
+    def _render(self, s):
+        wv, fp, cc = self.cams
+        o = render_views(s["pc"], 0, wv, fp, cc, self.bg, self.cfg, workspace=s["ws"], epilogue=False, out_color=s["raster"],
+                         sink=s["host"] if self.zero_copy else None)
+        s["ws"].finish_async()                     # the mailbox copy rides behind the render on the compute stream
+        main = torch.cuda.current_stream(self.device)
+        if self.zero_copy:
+            s["done"].record(main)
+            return
+        r = o["raster"]
+        st = s["staging"]
+        st[:, 0:3].copy_(r[:, 0:3])
+        st[:, 3:4].copy_(r[:, 6:7])
+        st[:, 4:5].copy_(r[:, 7:8])
+        packed = torch.cuda.Event()
+        packed.record(main)
+        self.d2h_stream.wait_event(packed)
+        with torch.cuda.stream(self.d2h_stream):
+            s["host"].copy_(st, non_blocking=True)
+            s["done"].record(self.d2h_stream)
+
+    def submit(self, scene):
+        """Enqueue scene (a staging.PinnedScene): H2D on the copy stream, render on the current stream.  Never blocks
+        the host; raises if all slots are in flight (call collect() first)."""
+        if self.pending == self.slots:
+            raise RuntimeError("SceneStreamer: all slots in flight; collect() before submitting more")
+        s = self.slot[self.head]
+        self.head = (self.head + 1) % self.slots
+        self.pending += 1
+        nbytes = scene.host_slab.numel()
+        if s["slab"] is None or s["slab"].numel() < nbytes:
+            s["slab"] = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        main = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.copy_stream):
+            s["pc"] = scene.upload(s["slab"])
+            s["h2d"].record(self.copy_stream)
+        s["scene"] = scene
+        main.wait_event(s["h2d"])
+        self._render(s)
+
+    def collect(self):
+        """Wait for the OLDEST outstanding scene; returns (frames [V,5,H,W] in pinned host memory, per-view num_rendered)."""
+        if self.pending == 0:
+            raise RuntimeError("SceneStreamer: nothing to collect")
+        s = self.slot[(self.head - self.pending) % self.slots]
+        s["done"].synchronize()
+        R = s["ws"].finish_poll()
+        while R is None:                           # binning blob too small: it has been grown, render this scene again
+            self._render(s)
+            s["done"].synchronize()
+            R = s["ws"].finish_poll()
+        self.pending -= 1
+        return s["host"], R
 
 
 def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None,

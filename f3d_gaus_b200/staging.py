@@ -20,12 +20,22 @@ class PinnedScene:
         self.nbytes = sum(n for _, n, _ in layout.values())
         self.host_slab = torch.empty(max(at, 256), dtype=torch.uint8).pin_memory()
         self.dev_slab = torch.empty(max(at, 256), dtype=torch.uint8, device=self.device)
-        view = lambda slab, o, n, shape: slab[o:o + n].view(torch.float32).view(shape)
-        self.host = {k: view(self.host_slab, *l) for k, l in layout.items()}
-        self.dev = {k: view(self.dev_slab, *l) for k, l in layout.items()}
+        self.layout = layout
+        self.host = self.views(self.host_slab)
+        self.dev = self.views(self.dev_slab)
         for k, v in pc.items():
             self.host[k].copy_(v.to(dtype=torch.float32))
 
-    def upload(self) -> dict:
-        self.dev_slab.copy_(self.host_slab, non_blocking=True)
-        return self.dev
+    def views(self, slab: torch.Tensor) -> dict:
+        """The per-key tensor views of a slab (host or device) that has this scene's layout."""
+        return {k: slab[o:o + n].view(torch.float32).view(shape) for k, (o, n, shape) in self.layout.items()}
+
+    def upload(self, dst_slab: torch.Tensor | None = None) -> dict:
+        """One async H2D copy on the current stream into the scene's own device slab, or into `dst_slab` (a device
+        byte tensor of at least the slab size: streaming loops keep one per pipeline slot)."""
+        if dst_slab is None:
+            self.dev_slab.copy_(self.host_slab, non_blocking=True)
+            return self.dev
+        dst = dst_slab[:self.host_slab.numel()]
+        dst.copy_(self.host_slab, non_blocking=True)
+        return self.views(dst)

@@ -204,6 +204,14 @@ int gof_set_frame_sink(GofContext* ctx, void* sink, size_t sink_bytes, int32_t l
  * `geom` (or GOF_EOVERFLOW if the binning blob was too small for it). */
 int gof_num_rendered(GofContext* ctx, const void* geom, int32_t P, int32_t V, gof_stream_t stream, int32_t* num_rendered);
 
+/* Same without blocking: enqueues on `stream` a copy of the batch's mailbox into `host_dst`, 4 + V int32 of PINNED host
+ * memory: {R_total, overflow flag, longest tile list, 0, R_view[0..V-1]}.  Valid once the work enqueued on `stream` up
+ * to this call has completed (record an event behind it); overflow != 0 means the binning blob was too small and every
+ * output of the batch holds NaN.  This is what lets a streaming loop (gaussian_renderer.SceneStreamer) check batch k
+ * while batch k+1 is already running. */
+#define GOF_MAILBOX_HEAD 4
+int gof_num_rendered_async(const void* geom, int32_t P, int32_t V, int32_t* host_dst, gof_stream_t stream);
+
 /* Backward: replays the blend back-to-front and produces the reference's 9 gradient tensors.
  * `binning` / `binning_bytes`: the blob the forward returned and its size in bytes (binningBuffer.numel()); the
  * blob's internal layout is derived from exactly these two values, in forward and backward alike. */

@@ -326,3 +326,42 @@ def test_pinned_scene_single_upload():
         assert d[k].shape == v.shape and d[k].data_ptr() % 256 == 0 and torch.equal(d[k].cpu(), v), k
     scene.host["opacity"].mul_(0.5)                      # the pinned views are writable in place
     assert torch.equal(scene.upload()["opacity"].cpu(), pc_cpu["opacity"] * 0.5)
+
+
+@pytest.mark.parametrize("zero_copy", [True, False])
+def test_scene_streamer_pipeline(zero_copy):
+    """SceneStreamer: several scenes in flight (H2D of k+1 | render k | frames of k-1 to host); every collected frame
+    block is bit-identical to render_views of that scene, in submission order, including a scene whose first render
+    overflows the (deliberately undersized) binning blob and is re-rendered inside collect()."""
+    from f3d_gaus_b200 import cameras, synthetic
+    from f3d_gaus_b200.gaussian_renderer import PinnedScene, SceneStreamer, render_views
+    dev = torch.device("cuda", torch.cuda.current_device())
+    res = 128
+    cams = cameras.orbit_cameras(8)
+    wv, fp, cc = cams.world_view.to(dev), cams.full_proj.to(dev), cams.centers.to(dev)
+    cfg = synthetic.cfg_for(res)
+    bg = torch.tensor([0.2, 0.1, 0.3], device=dev)
+    scenes = [PinnedScene(synthetic.f3d_like(seed, 96), dev) for seed in range(5)]
+    want = []
+    for sc in scenes:
+        o = render_views({k: v.to(dev) for k, v in sc.host.items()}, 0, wv, fp, cc, bg, cfg, epilogue=False)
+        want.append((torch.cat([o["render"], o["rendered_depth"], o["rendered_alpha"]], dim=1).cpu(), o["num_rendered"]))
+    st = SceneStreamer(8, res, res, dev, wv, fp, cc, bg, cfg, slots=2, zero_copy=zero_copy)
+    for s in st.slot:
+        s["ws"].capacity_hint = 2000            # far too small: the first render of each slot overflows
+    got = []
+    for sc in scenes:
+        if st.pending == st.slots:
+            frames, R = st.collect()
+            got.append((frames.clone(), R))
+        st.submit(sc)
+    with pytest.raises(RuntimeError):
+        st.submit(scenes[0]); st.submit(scenes[0]); st.submit(scenes[0])
+    while st.pending:
+        frames, R = st.collect()
+        got.append((frames.clone(), R))
+    got = got[:len(scenes)]
+    assert len(got) == len(scenes)
+    for k, ((f, R), (wf, wR)) in enumerate(zip(got, want)):
+        assert R == wR, k
+        assert torch.equal(f, wf), k
