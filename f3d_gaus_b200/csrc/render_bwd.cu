@@ -301,11 +301,20 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 					dL_dn[1] += dL_dA * ry;
 					dL_dn[2] += dL_dA;
 
+#ifdef GOF_BWD_DIAG_ONE_RED
+					// DIAGNOSTIC build only (tools/build_variant.sh): one reduction per pair instead of five, everything
+					// still computed -- separates the arithmetic from the L2-reduction issue rate.  Results are WRONG.
+					red_global_v4(dst + 0, make_float4(dL_dn[0] * rx + dL_dn[1] + dL_dn[2] * ry + (float)(dL_dB * 2) + gcol[2],
+					                                   dL_dn[0] * ry + dL_dn[1] * rx + dL_dn[2] + (float)dL_dC + G * dL_dalpha,
+					                                   dL_dn[0] + dL_dn[2] * rx + (float)(dL_dB * 2 * rx) + gcol[0] + gmx,
+					                                   dL_dn[1] * ry + (float)(dL_dB * 2 * ry) + gcol[1] + gmy + fabsf(gmx) + fabsf(gmy)));
+#else
 					red_global_v4(dst + 0, make_float4(dL_dn[0] * rx, dL_dn[0] * ry + dL_dn[1] * rx, dL_dn[0] + dL_dn[2] * rx, dL_dn[1] * ry));
 					red_global_v4(dst + 4, make_float4(dL_dn[1] + dL_dn[2] * ry, dL_dn[2], (float)(dL_dB * 2 * rx), (float)(dL_dB * 2 * ry)));
 					red_global_v4(dst + 8, make_float4((float)(dL_dB * 2), (float)dL_dC, gcol[0], gcol[1]));
 					red_global_v4(dst + 12, make_float4(gcol[2], G * dL_dalpha, gmx, gmy));
 					atomicAdd(dst + 16, fabsf(gmx) + fabsf(gmy));
+#endif
 				}
 			}
 		}

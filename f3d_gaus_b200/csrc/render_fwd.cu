@@ -33,16 +33,13 @@ namespace gof {
 namespace {
 
 #ifndef GOF_FWD_STAGES
-#define GOF_FWD_STAGES 4
+#define GOF_FWD_STAGES 4          // power of two (ring addressing by list position); a warp reads two chunks and sweeps a third
 #endif
 #ifndef GOF_FWD_MIN_CTAS
 #define GOF_FWD_MIN_CTAS 3
 #endif
 #ifndef GOF_FWD_CHUNK
 #define GOF_FWD_CHUNK 128
-#endif
-#ifndef GOF_FWD_SCAN64
-#define GOF_FWD_SCAN64 1          // pass 2 pops survivors from a word + three-word shift register (A/B switch; 0: word index + refill cascade)
 #endif
 #ifndef GOF_FWD_FOLD_W
 #define GOF_FWD_FOLD_W 1          // fast blend: normals / distortion accumulate with w = alpha*T formed once
@@ -125,8 +122,43 @@ __device__ __forceinline__ bool blend_pair(PixState& s, const PairGeom& g, float
 }
 
 constexpr int CONSUMER_WARPS = TILE_PIX / 32;          // 8
-constexpr int FWD_THREADS = TILE_PIX + 32;             // + 1 producer warp
-constexpr int REC_F4 = SLAB_FLOATS / 4;                // float4 per slab record (6)
+constexpr int FWD_THREADS = TILE_PIX;                  // every warp blends; there is no dedicated producer warp
+
+// Survivors of one lane (= pixel) in TWO consecutive 128-record chunks, ca and ca+1: eight 32-record words.  The words
+// live in shared memory, one private column per thread (word w of the tile list -> row w % 8, so the chunk that enters
+// the window overwrites the rows of the chunk that left it); registers hold only the word being consumed (`cur`, the
+// bits not popped yet) and its index in the list (`p`).  Invariant ("normalised"): cur != 0 unless nothing is queued.
+constexpr int QUEUE_ROWS = 2 * NW;
+struct LaneQueue {
+	uint32_t cur, p;
+	uint32_t col;                                   // shared-window address of this thread's column (row 0)
+	__device__ __forceinline__ uint32_t row(uint32_t w) const { return col + (w % QUEUE_ROWS) * (FWD_THREADS * 4); }
+	__device__ __forceinline__ void store_chunk(int c, const uint32_t (&m)[NW]) const
+	{
+#pragma unroll
+		for (int k = 0; k < NW; k++)
+			asm volatile("st.shared.u32 [%0], %1;" ::"r"(row((uint32_t)c * NW + k)), "r"(m[k]) : "memory");
+	}
+	// skip exhausted words; p_end = words queued so far (warp-uniform)
+	__device__ __forceinline__ void normalise(uint32_t p_end)
+	{
+		while (cur == 0 && p + 1 < p_end) {
+			p++;
+			asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cur) : "r"(row(p)) : "memory");
+		}
+	}
+	// true if the next survivor lies in a word below `limit` (= it belongs to the window's first chunk)
+	__device__ __forceinline__ bool pending_below(uint32_t limit) const { return cur != 0 && p < limit; }
+	// pop the next survivor in list order: its position in the tile list; false when nothing is queued
+	__device__ __forceinline__ bool pop(uint32_t& j, uint32_t p_end)
+	{
+		if (cur == 0) return false;
+		j = (p << 5) + (uint32_t)__ffs((int)cur) - 1u;
+		cur &= cur - 1u;
+		normalise(p_end);
+		return true;
+	}
+};
 
 template <bool EXACT, bool SINK>
 __global__ void __launch_bounds__(FWD_THREADS, GOF_FWD_MIN_CTAS)
@@ -136,11 +168,12 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
                   float* __restrict__ final_T_all, uint32_t* __restrict__ n_contrib_all, float* __restrict__ out_color_all,
                   const int32_t* __restrict__ mailbox, const uint8_t* __restrict__ block_mask, float* __restrict__ sink_all, int sink_hwc)
 {
+	static_assert(NW == 4, "the survivor queues are written for 128-record chunks");
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	float4 (*s_rec)[CHUNK * REC_F4] = reinterpret_cast<float4 (*)[CHUNK * REC_F4]>(smem_raw);
 	uint64_t* s_full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * CHUNK * SLAB_BYTES);
-	uint64_t* s_empty = s_full + STAGES;
-	float* s_out = reinterpret_cast<float*>(s_empty + STAGES);      // [SINK_CH * 256] tile of the frame sink
+	uint32_t* s_released = reinterpret_cast<uint32_t*>(s_full + STAGES);      // per stage: warps that have let go of it (monotonic)
+	uint32_t* s_queue = reinterpret_cast<uint32_t*>(s_full + 2 * STAGES);     // [QUEUE_ROWS][256] survivor words (LaneQueue)
+	float* s_out = reinterpret_cast<float*>(s_queue + QUEUE_ROWS * FWD_THREADS);   // [SINK_CH * 256] tile of the frame sink
 
 	const int tid = threadIdx.x;
 	const int warp = tid >> 5, lane = tid & 31;
@@ -162,29 +195,36 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 	const int nchunks = (n + CHUNK - 1) / CHUNK;
 	const float* tile_slab = slab + (size_t)range.x * SLAB_FLOATS;
 
+	// The tile's slab is streamed through a STAGES-deep ring by TMA bulk copies.  There is no producer warp (it would
+	// hold a ninth warp's registers for one busy lane): the first STAGES chunks are requested here, and the warp that is
+	// the LAST to let go of a stage requests the chunk that reuses it (release_stage).
+	auto request_chunk = [&](int c) {
+		const int s = c % STAGES;
+		const uint32_t bytes = (uint32_t)min(CHUNK, n - c * CHUNK) * SLAB_BYTES;
+		mbar_arrive_expect_tx(&s_full[s], bytes);
+		tma_bulk_g2s(smem_raw + (size_t)s * (CHUNK * SLAB_BYTES), tile_slab + (size_t)c * CHUNK * SLAB_FLOATS, bytes, &s_full[s]);
+	};
 	if (tid == 0) {
 #pragma unroll
-		for (int s = 0; s < STAGES; s++) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], CONSUMER_WARPS); }
+		for (int s = 0; s < STAGES; s++) { mbar_init(&s_full[s], 1); s_released[s] = 0; }
 		mbar_fence_init();
+		for (int c = 0; c < min(STAGES, nchunks); c++) request_chunk(c);
 	}
 	__syncthreads();
-
-	if (warp == CONSUMER_WARPS) {
-		// ---------------- producer warp: one elected lane streams the slab ----------------------
+	auto release_stage = [&](int c) {              // this warp will not read chunk c's stage again
+		__syncwarp();
 		if (lane == 0) {
-			for (int c = 0; c < nchunks; c++) {
-				const int s = c % STAGES;
-				if (c >= STAGES) mbar_wait_backoff(&s_empty[s], (uint32_t)(((c / STAGES) - 1) & 1));
-				const int cnt = min(CHUNK, n - c * CHUNK);
-				const uint32_t bytes = (uint32_t)cnt * SLAB_BYTES;
-				mbar_arrive_expect_tx(&s_full[s], bytes);
-				tma_bulk_g2s(&s_rec[s][0], tile_slab + (size_t)c * CHUNK * SLAB_FLOATS, bytes, &s_full[s]);
+			__threadfence_block();
+			const uint32_t before = atomicAdd(&s_released[c % STAGES], 1u);
+			if ((before % CONSUMER_WARPS) == CONSUMER_WARPS - 1 && c + STAGES < nchunks) {
+				__threadfence_block();
+				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the warps' reads of the stage precede the bulk write
+				request_chunk(c + STAGES);
 			}
 		}
-		return;
-	}
+	};
 
-	// -------------------- consumer warps: 8x4 pixel block each --------------------------------
+	// -------------------- every warp: an 8x4 pixel block ----------------------------------------
 	const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);   // tile-local pixel
 	const uint32_t px = tile_x * TILE_X + lx;
 	const uint32_t py = tile_y * TILE_Y + ly;
@@ -192,7 +232,6 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 	const uint32_t pix_id = W * py + px;
 	const float rx = pixel_ray(px, W, focal_x);
 	const float ry = pixel_ray(py, H, focal_y);
-	const float fx = (float)lx, fy = (float)ly;
 
 	PixState st;
 	st.T = 1.0f;
@@ -206,7 +245,11 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 
 	const uint32_t rec_base = smem_u32(smem_raw);
 	const uint8_t* tile_bm = block_mask + range.x;
-	for (int c = 0; c < nchunks; c++) {
+
+	// ---- pass 1 of chunk c: conic sweep over the chunk's records that can touch this warp's 8x4 block (bit `warp` of
+	// the record's block mask, ~1/3 of them); coefficients are warp-broadcast shared-memory reads.  Leaves the lane's
+	// survivors among the chunk's 128 records in q.
+	auto conic_sweep = [&](int c, uint32_t (&m)[NW]) {
 		const int s = c % STAGES;
 		const int cnt = min(CHUNK, n - c * CHUNK);
 		// this lane's share of the chunk's block masks (records lane, 32+lane, 64+lane, 96+lane): read from
@@ -215,20 +258,17 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 #pragma unroll
 		for (int k = 0; k < NW; k++) bm[k] = 0;
 		if (!warp_done) {
-			const uint8_t* q = tile_bm + c * CHUNK + lane;
+			const uint8_t* p = tile_bm + c * CHUNK + lane;
 #pragma unroll
 			for (int k = 0; k < NW; k++)
-				if (32 * k + lane < cnt) bm[k] = __ldg(q + 32 * k);
+				if (32 * k + lane < cnt) bm[k] = __ldg(p + 32 * k);
 		}
 		mbar_wait(&s_full[s], (uint32_t)((c / STAGES) & 1));
-		if (!warp_done) {
-			const uint32_t rec = rec_base + (uint32_t)s * (CHUNK * SLAB_BYTES);   // shared-window address of the stage
-			const uint32_t base = (uint32_t)c * CHUNK;
-			// ---- pass 1: conic sweep over the chunk's records that can touch this warp's 8x4 block (bit `warp`
-			// of the record's block mask, ~1/3 of them); coefficients are warp-broadcast shared-memory reads.
-			uint32_t m[NW];                            // survivors among records [32k, 32k+32)
 #pragma unroll
-			for (int k = 0; k < NW; k++) m[k] = 0;
+		for (int k = 0; k < NW; k++) m[k] = 0;       // survivors among records [32k, 32k+32)
+		if (!warp_done) {
+			const float fx = (float)lx, fy = (float)ly;
+			const uint32_t rec = rec_base + (uint32_t)s * (CHUNK * SLAB_BYTES);   // shared-window address of the stage
 #pragma unroll 1
 			for (int w = 0; w < NW; w++) {
 				const int valid = cnt - 32 * w;
@@ -257,61 +297,64 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 #pragma unroll
 				for (int k = 0; k < NW; k++) m[k] = 0;
 			}
-			// ---- pass 2: each pixel blends its own survivors, in list order.  ONE loop over the whole
-			// chunk: the warp iterates max-over-lanes(survivors in the chunk) / 2 times.
-			// `cur` = the word being consumed, `wsel` its index; m[1..] stay loop-invariant.  Two survivors are
-			// taken per trip: their exact evaluations (double division, exp) are independent dependency chains
-			// that interleave, the two blends then run in list order.
-#if GOF_FWD_SCAN64
-			static_assert(NW == 4, "the survivor walk is written for 128-record chunks");
-			// `cur` = the word being consumed, the others wait in a three-word shift register
-			uint32_t cur = m[0], w1 = m[1], w2 = m[2], w3 = m[3], jbase = 0;
-			auto next = [&](uint32_t& j) -> bool {      // pop the lane's next survivor (list order); false when none is left
-				while (cur == 0) {
-					if ((w1 | w2 | w3) == 0) return false;
-					cur = w1; w1 = w2; w2 = w3; w3 = 0; jbase += 32;
-				}
-				j = jbase + (uint32_t)__ffs((int)cur) - 1u;
-				cur &= cur - 1u;
-				return true;
-			};
-			for (;;) {
-				uint32_t ja, jb;
-				if (!next(ja)) break;
-				const bool hb = next(jb);
-				if (!hb) jb = ja;
-#else
-			uint32_t cur = m[0], wsel = 0;
-			auto refill = [&]() -> bool {      // make `cur` non-empty; false when the lane has no survivors left
-				if (cur != 0) return true;
-#pragma unroll
-				for (int k = 1; k < NW; k++)
-					if (wsel < (uint32_t)k && m[k] != 0) { cur = m[k]; wsel = k; return true; }
-				return false;
-			};
-			for (;;) {
-				if (!refill()) break;
-				const uint32_t ja = 32u * wsel + (uint32_t)__ffs((int)cur) - 1u;
-				cur &= cur - 1u;
-				const bool hb = refill();
-				uint32_t jb = ja;
-				if (hb) { jb = 32u * wsel + (uint32_t)__ffs((int)cur) - 1u; cur &= cur - 1u; }
-#endif
-				const uint32_t ra = rec + ja * SLAB_BYTES, rb = rec + jb * SLAB_BYTES;
-				const float4 a1 = lds128(ra + 16), a2 = lds128(ra + 32), a3 = lds128(ra + 48), a4 = lds128(ra + 64);
-				const float4 b1 = lds128(rb + 16), b2 = lds128(rb + 32), b3 = lds128(rb + 48), b4 = lds128(rb + 64);
-				const PairGeom ga = pair_geom(a1, a2, a3, rx, ry);
-				const PairGeom gb = pair_geom(b1, b2, b3, rx, ry);
-				float ta, alpha_a, tb, alpha_b;
-				const bool oka = pair_alpha_eval(ga, a4.x, a1.z, ta, alpha_a);
-				const bool okb = pair_alpha_eval(gb, b4.x, b1.z, tb, alpha_b) && hb;
-				if (oka && blend_pair<EXACT>(st, ga, ta, alpha_a, make_float4(a4.y, a4.z, a4.w, 0.0f), base + ja + 1)) { done = true; break; }
-				if (okb && blend_pair<EXACT>(st, gb, tb, alpha_b, make_float4(b4.y, b4.z, b4.w, 0.0f), base + jb + 1)) { done = true; break; }
-			}
-			warp_done = __all_sync(0xffffffffu, done);
 		}
-		__syncwarp();
-		if (lane == 0) mbar_arrive(&s_empty[s]);   // this warp is finished with stage s
+	};
+
+	// ---- pass 2: each pixel blends its own survivors, in list order (float32 quadric, exact FP64 ray minimum, expf,
+	// blend), two per trip so that the two evaluations' dependency chains interleave.
+	// The lanes of a warp are NOT synchronised at chunk boundaries.  A lane queues the survivors of TWO chunks: ca (the
+	// oldest chunk some lane of the warp still needs) and ca+1.  A pixel with few survivors in chunk ca moves on to
+	// those of ca+1 while its heavier neighbours are still in ca; the warp advances (lets go of the stage of ca, sweeps
+	// chunk ca+2 into the queue) when no lane has anything left in ca.  Per-pixel survivor counts per chunk fluctuate
+	// around a spatially smooth load: in per-chunk lock-step 14 of 32 lanes were active in this loop; the one-chunk
+	// lookahead absorbs the fluctuation (oracle model: 19 of 32; the persistent part of the imbalance and saturated
+	// pixels cap it at 21).
+	LaneQueue q;
+	q.cur = 0;
+	q.p = 0;
+	q.col = smem_u32(s_queue) + (uint32_t)tid * 4u;
+	{
+		uint32_t m[NW];
+		if (nchunks > 0) { conic_sweep(0, m); q.store_chunk(0, m); q.cur = m[0]; }
+		if (nchunks > 1) { conic_sweep(1, m); q.store_chunk(1, m); }
+		q.normalise((uint32_t)min(nchunks, 2) * NW);
+	}
+	// the ring holds STAGES * CHUNK consecutive list positions: record j sits at rec_base + 80 (j mod 512)
+	static_assert((STAGES & (STAGES - 1)) == 0, "ring addressing by list position needs a power-of-two ring");
+	constexpr uint32_t RING_MASK = STAGES * CHUNK - 1;
+	for (int ca = 0; ca < nchunks; ca++) {
+		const uint32_t p_end = (uint32_t)min(nchunks, ca + 2) * NW;
+		const uint32_t p_b = (uint32_t)(ca + 1) * NW;              // first word of chunk ca+1
+		while (__any_sync(0xffffffffu, q.pending_below(p_b))) {
+			uint32_t ja, jb;
+			if (!q.pop(ja, p_end)) continue;                       // nothing queued: wait for the warp to advance
+			const bool hb = q.pop(jb, p_end);
+			if (!hb) jb = ja;
+			const uint32_t ra = rec_base + (ja & RING_MASK) * SLAB_BYTES;
+			const uint32_t rb = rec_base + (jb & RING_MASK) * SLAB_BYTES;
+			const float4 a1 = lds128(ra + 16), a2 = lds128(ra + 32), a3 = lds128(ra + 48), a4 = lds128(ra + 64);
+			const float4 b1 = lds128(rb + 16), b2 = lds128(rb + 32), b3 = lds128(rb + 48), b4 = lds128(rb + 64);
+			const PairGeom ga = pair_geom(a1, a2, a3, rx, ry);
+			const PairGeom gb = pair_geom(b1, b2, b3, rx, ry);
+			float ta, alpha_a, tb, alpha_b;
+			const bool oka = pair_alpha_eval(ga, a4.x, a1.z, ta, alpha_a);
+			const bool okb = pair_alpha_eval(gb, b4.x, b1.z, tb, alpha_b) && hb;
+			// contributor ids are 1-based list positions (forward.cu:494-496)
+			if ((oka && blend_pair<EXACT>(st, ga, ta, alpha_a, make_float4(a4.y, a4.z, a4.w, 0.0f), ja + 1u)) ||
+			    (okb && blend_pair<EXACT>(st, gb, tb, alpha_b, make_float4(b4.y, b4.z, b4.w, 0.0f), jb + 1u))) {
+				done = true;                                        // the pixel is saturated: it has no survivors any more
+				q.cur = 0;
+				q.p = 0xffffff00u;                                  // beyond every p_end: normalise() never reloads
+			}
+		}
+		release_stage(ca);
+		warp_done = __all_sync(0xffffffffu, done);
+		if (ca + 2 < nchunks) {
+			uint32_t m[NW];
+			conic_sweep(ca + 2, m);
+			q.store_chunk(ca + 2, m);
+			q.normalise((uint32_t)(ca + 3) * NW);                  // a lane that had run dry picks up the new words
+		}
 	}
 
 	if (overflow) {
@@ -389,7 +432,8 @@ int launch_render_fwd(const GofParams& prm, const Frame& f, const GeomState& g, 
                       const float* background, int bg_stride, float* out_color, float* sink, int sink_hwc, cudaStream_t s)
 {
 	const dim3 grid((unsigned)(f.T * f.V), 1, 1);
-	const size_t smem = (size_t)STAGES * CHUNK * SLAB_BYTES + 2 * STAGES * sizeof(uint64_t) + (sink ? (size_t)SINK_CH * TILE_PIX * sizeof(float) : 0);
+	const size_t smem = (size_t)STAGES * CHUNK * SLAB_BYTES + 2 * STAGES * sizeof(uint64_t) + (size_t)QUEUE_ROWS * FWD_THREADS * 4 +
+	                    (sink ? (size_t)SINK_CH * TILE_PIX * sizeof(float) : 0);   // ring | full barriers | release counters | queues | sink tile
 	auto launch = [&](auto kernel) {
 		// per device and per function; cheap enough to set on every launch (one process may drive several GPUs)
 		if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return;

@@ -294,14 +294,11 @@ class HostFrameSink:
             if lo >= hi:
                 break
             o = render_views(pc, bs, wv[lo:hi], fp[lo:hi], cc[lo:hi], bg_color, cfg, workspace=self.workspaces[ci],
-                             epilogue=False, sink=self.host[lo:hi] if self.zero_copy else None, **kw)
+                             epilogue=False, sink=self.host[lo:hi] if self.zero_copy else self.staging[lo:hi], **kw)
             self.last_raster = o["raster"]            # [v,9,H,W] of the last pass (the whole batch when chunks == 1)
             if self.zero_copy:
                 continue
-            st = self.staging[lo:hi]
-            st[:, 0:3].copy_(o["render"])
-            st[:, 3:4].copy_(o["rendered_depth"])
-            st[:, 4:5].copy_(o["rendered_alpha"])
+            st = self.staging[lo:hi]                  # packed by the blend kernel (device sink)
             ready = torch.cuda.Event()
             ready.record(main)
             self.copy_stream.wait_event(ready)
@@ -332,8 +329,9 @@ class SceneStreamer:
     `for batch: for scene: for view: render(...).cpu()` loops (visualize.py:221,293-306,387-402).
 
     `slots` scenes are in flight: while scene k renders, the H2D copy of scene k+1 runs on a copy stream and the
-    frames of scene k-1 drain to pinned host memory (stored by the blend kernel itself, `zero_copy`, or packed on the
-    device and copied by the DMA engine on a third stream).  Nothing synchronises the host except `collect()`, which
+    frames of scene k-1 drain to pinned host memory (stored there by the blend kernel itself, `zero_copy`, or stored
+    by it into a packed device block that the DMA engine copies on a third stream -- the better choice when many GPUs
+    share one host: DMA bursts use the host's write path more efficiently than the kernel's 320-byte posted writes).  Nothing synchronises the host except `collect()`, which
     waits on ONE event: that of the oldest outstanding scene.  The binning-overflow check of a scene rides on the same
     event (BatchWorkspace.finish_async), so it does not stall the scenes behind it; an overflowed scene is re-rendered
     inside `collect()` after its workspace has grown.
@@ -368,29 +366,25 @@ class SceneStreamer:
             self.slot.append({"host": host, "slab": None, "ws": BatchWorkspace(self.device), "scene": None, "pc": None,
                               "staging": None if self.zero_copy else torch.empty((V, 5, H, W), dtype=torch.float32, device=self.device),
                               "raster": torch.empty((V, 9, H, W), dtype=torch.float32, device=self.device),
-                              "h2d": torch.cuda.Event(), "done": torch.cuda.Event()})
+                              "h2d": torch.cuda.Event(), "done": torch.cuda.Event(), "packed": torch.cuda.Event()})
         self.head = 0          # next slot to submit into
         self.pending = 0       # scenes submitted and not yet collected
 
     def _render(self, s):
         wv, fp, cc = self.cams
-        o = render_views(s["pc"], 0, wv, fp, cc, self.bg, self.cfg, workspace=s["ws"], epilogue=False, out_color=s["raster"],
-                         sink=s["host"] if self.zero_copy else None)
+        # the blend kernel packs rgb / depth / alpha itself: into the pinned host buffer (zero_copy) or into a device
+        # staging block that the DMA engine then moves on its own stream -- no pack kernels either way
+        render_views(s["pc"], 0, wv, fp, cc, self.bg, self.cfg, workspace=s["ws"], epilogue=False, out_color=s["raster"],
+                     sink=s["host"] if self.zero_copy else s["staging"])
         s["ws"].finish_async()                     # the mailbox copy rides behind the render on the compute stream
         main = torch.cuda.current_stream(self.device)
         if self.zero_copy:
             s["done"].record(main)
             return
-        r = o["raster"]
-        st = s["staging"]
-        st[:, 0:3].copy_(r[:, 0:3])
-        st[:, 3:4].copy_(r[:, 6:7])
-        st[:, 4:5].copy_(r[:, 7:8])
-        packed = torch.cuda.Event()
-        packed.record(main)
-        self.d2h_stream.wait_event(packed)
+        s["packed"].record(main)
+        self.d2h_stream.wait_event(s["packed"])
         with torch.cuda.stream(self.d2h_stream):
-            s["host"].copy_(st, non_blocking=True)
+            s["host"].copy_(s["staging"], non_blocking=True)
             s["done"].record(self.d2h_stream)
 
     def submit(self, scene):

@@ -11,7 +11,7 @@ for spec in "$@"; do
 import json,sys
 try:
     d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1]); r=d["roofline"]
-    print(sys.argv[2], "value",round(d["value"]),"e2e",round(d["e2e"]["value"]),"per_view",round(d["per_view_api"]["value"]),round(d["per_view_api"]["e2e"]),
+    print(sys.argv[2], "value",round(d["value"]),"e2e",round(d["e2e"]["value"]),"serial",round(d["e2e_serial"]["value"]),"per_view",round(d["per_view_api"]["value"]),round(d["per_view_api"]["e2e"]),
           "stages_us",{k:round(v*1e3,1) for k,v in r["stage_ms_per_step"].items()})
 except Exception as e:
     print(sys.argv[2], "FAILED", e); print(open(sys.argv[1].replace(".json",".err")).read()[-800:])
