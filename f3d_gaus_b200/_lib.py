@@ -13,11 +13,17 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GOF_B200_LIB") or os.path.join(_HERE, "libgof_b200.so")   # override: kernel-variant experiments
 
 FLAG_EXACT_BLEND = 1
+FLAG_SAVE_CONTRIB = 2
 
 
-def default_flags() -> int:
-    """Blend arithmetic mode: bit-exact contributing path iff GOF_EXACT_BLEND=1 (see gof_b200.h)."""
-    return FLAG_EXACT_BLEND if os.environ.get("GOF_EXACT_BLEND", "0") not in ("0", "", "false") else 0
+def default_flags(*differentiated) -> int:
+    """Blend arithmetic mode: bit-exact contributing path iff GOF_EXACT_BLEND=1; FLAG_SAVE_CONTRIB when one of the
+    tensors passed requires grad, i.e. a backward may follow this forward (see gof_b200.h; GOF_SAVE_CONTRIB=0/1 forces it)."""
+    flags = FLAG_EXACT_BLEND if os.environ.get("GOF_EXACT_BLEND", "0") not in ("0", "", "false") else 0
+    force = os.environ.get("GOF_SAVE_CONTRIB", "")
+    if force == "1" or (force != "0" and any(t is not None and getattr(t, "requires_grad", False) for t in differentiated)):
+        flags |= FLAG_SAVE_CONTRIB
+    return flags
 
 
 GOF_OK = 0

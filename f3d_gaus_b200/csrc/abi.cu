@@ -154,7 +154,7 @@ int gof_state_sizes_batch(int32_t P, int32_t W, int32_t H, int32_t V, int64_t nu
 	const size_t T = (size_t)((W + TILE_X - 1) / TILE_X) * ((H + TILE_Y - 1) / TILE_Y);
 	if (geom_bytes) *geom_bytes = GeomState::carve(nullptr, (size_t)P, (size_t)V).total;
 	if (img_bytes) *img_bytes = ImgState::carve(nullptr, (size_t)W * H, T, (size_t)V).total;
-	if (binning_bytes) *binning_bytes = BinState::carve(nullptr, (size_t)num_rendered).total;
+	if (binning_bytes) *binning_bytes = BinState::carve(nullptr, (size_t)num_rendered, T * (size_t)V).total;
 	return GOF_OK;
 }
 
@@ -167,25 +167,26 @@ int gof_state_sizes(int32_t P, int32_t W, int32_t H, int64_t num_rendered,
 static char* align_base(const void* p) { return reinterpret_cast<char*>(align_up(reinterpret_cast<size_t>(p))); }
 
 // Largest R whose binning layout fits in `bytes` (host arithmetic only).
-static int64_t binning_capacity(size_t bytes)
+static int64_t binning_capacity(size_t bytes, size_t VT)
 {
 	int64_t lo = 0, hi = (int64_t)1 << 31;
 	while (lo + 1 < hi) {
 		const int64_t mid = (lo + hi) / 2;
-		if (BinState::carve(nullptr, (size_t)mid).total <= bytes) lo = mid; else hi = mid;
+		if (BinState::carve(nullptr, (size_t)mid, VT).total <= bytes) lo = mid; else hi = mid;
 	}
 	return lo;
 }
 
-// The binning blob's layout is a pure function of (address, byte size): the capacity it is carved for is the
-// largest R that fits.  Forward, backward and the test accessor all derive it this way, so a blob that was
+// The binning blob's layout is a pure function of (address, byte size, tiles in the batch): the capacity it is carved
+// for is the largest R that fits.  Forward, backward and the test accessor all derive it this way, so a blob that was
 // allocated speculatively (capacity > num_rendered) is decoded identically by every later call that is handed
 // the same tensor -- no per-process side table, nothing to go stale between a forward and its backward.
-static int64_t blob_capacity(const void* blob, size_t bytes)
+static int64_t blob_capacity(const void* blob, size_t bytes, size_t VT)
 {
 	if (!blob) return 0;
 	const size_t skew = (size_t)(align_base(blob) - (const char*)blob);
-	return bytes > skew ? binning_capacity(bytes - skew) : 0;
+	if (bytes <= skew || BinState::carve(nullptr, 0, VT).total > bytes - skew) return 0;
+	return binning_capacity(bytes - skew, VT);
 }
 
 int gof_set_frame_sink(GofContext* ctx, void* sink, size_t sink_bytes, int32_t layout)
@@ -264,6 +265,8 @@ int gof_forward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* in
 	}
 
 	const Frame f = make_frame(prm, V);
+	const size_t VT = (size_t)f.T * (size_t)V;
+	const int save_contrib = (prm->flags & GOF_FLAG_SAVE_CONTRIB) ? 1 : 0;
 	GeomState g = GeomState::carve(align_base(geom), (size_t)P, (size_t)V);
 	ImgState im = ImgState::carve(align_base(img), N, (size_t)f.T, (size_t)V);
 	if (!geom || g.total > geom_bytes) { set_error("gof_forward: geom blob too small (%zu < %zu)", geom_bytes, g.total); return GOF_ENOMEM; }
@@ -280,11 +283,11 @@ int gof_forward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* in
 	BinState b;
 	if (binning != nullptr) {
 		// sync-free mode: capacity is whatever fits in the caller's blob; R stays on the device
-		capacity = blob_capacity(binning, binning_bytes);
-		if ((rc = launch_tile_scan(f, g, im, capacity, s)) != GOF_OK) return rc;
+		capacity = blob_capacity(binning, binning_bytes, VT);
+		if ((rc = launch_tile_scan(f, g, im, capacity, s, save_contrib)) != GOF_OK) return rc;
 		GOF_STAGE_CHECK(prm, s);
 		GOF_PROF_MARK(ctx, marks, s);
-		b = BinState::carve(align_base(binning), (size_t)capacity);
+		b = BinState::carve(align_base(binning), (size_t)capacity, VT);
 		if (num_rendered) for (int v = 0; v < V; v++) num_rendered[v] = -1;
 	} else {
 		if (!alloc) { set_error("gof_forward: neither a binning blob nor an allocation callback"); return GOF_EINVAL; }
@@ -294,17 +297,17 @@ int gof_forward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* in
 			// Speculative hand-off: allocate the binning blob for 1.25x the previous call's num_rendered and enqueue
 			// EVERYTHING before waiting for R, so the GPU never idles behind the host round trip of the reference's
 			// protocol (rasterizer_impl.cu:336-340).  The host still returns R as soon as the scan has finished.
-			const size_t need = BinState::carve(nullptr, (size_t)ctx->spec_capacity).total;
+			const size_t need = BinState::carve(nullptr, (size_t)ctx->spec_capacity, VT).total;
 			void* blob = alloc(alloc_user, need);
 			if (!blob) { set_error("gof_forward: binning allocation callback returned NULL for %zu bytes", need); return GOF_ENOMEM; }
-			capacity = blob_capacity(blob, need);          // the layout every later call derives from (blob, need)
-			b = BinState::carve(align_base(blob), (size_t)capacity);
-			if ((rc = launch_tile_scan(f, g, im, capacity, s)) != GOF_OK) return rc;
+			capacity = blob_capacity(blob, need, VT);      // the layout every later call derives from (blob, need)
+			b = BinState::carve(align_base(blob), (size_t)capacity, VT);
+			if ((rc = launch_tile_scan(f, g, im, capacity, s, save_contrib)) != GOF_OK) return rc;
 			GOF_PROF_MARK(ctx, marks, s);
 			GOF_CUDA_CHECK(cudaMemcpyAsync(ctx->pinned, g.mailbox, (MAILBOX_HEAD + V) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
 			GOF_CUDA_CHECK(cudaEventRecord(ctx->handoff, s));
 			GOF_PROF_MARK(ctx, marks, s);
-			if ((rc = launch_binning(f, g, im, b, capacity, s)) != GOF_OK) return rc;
+			if ((rc = launch_binning(f, g, im, b, capacity, s, 0.0f, save_contrib)) != GOF_OK) return rc;
 			GOF_PROF_MARK(ctx, marks, s);
 			if ((rc = launch_render_fwd(*prm, f, g, im, b, in->background, bg_stride, out_color, sink, sink_hwc, s)) != GOF_OK) return rc;
 			GOF_PROF_MARK(ctx, marks, s);
@@ -322,7 +325,7 @@ int gof_forward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* in
 			done = false;
 		}
 		if (!done) {
-			if ((rc = launch_tile_scan(f, g, im, (int64_t)1 << 40, s)) != GOF_OK) return rc;
+			if ((rc = launch_tile_scan(f, g, im, (int64_t)1 << 40, s, save_contrib)) != GOF_OK) return rc;
 			GOF_STAGE_CHECK(prm, s);
 			GOF_PROF_MARK(ctx, marks, s);
 			GOF_CUDA_CHECK(cudaMemcpyAsync(ctx->pinned, g.mailbox, (MAILBOX_HEAD + V) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -330,17 +333,17 @@ int gof_forward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* in
 			const int64_t R = ctx->pinned[0];
 			ctx->spec_capacity = R + R / 4 + 4096;
 			if (num_rendered) for (int v = 0; v < V; v++) num_rendered[v] = ctx->pinned[MAILBOX_HEAD + v];
-			const size_t need = BinState::carve(nullptr, (size_t)R).total;
+			const size_t need = BinState::carve(nullptr, (size_t)R, VT).total;
 			void* blob = alloc(alloc_user, need);
 			if (!blob) { set_error("gof_forward: binning allocation callback returned NULL for %zu bytes", need); return GOF_ENOMEM; }
 			if (binning_out) *binning_out = blob;
-			capacity = blob_capacity(blob, need);
-			b = BinState::carve(align_base(blob), (size_t)capacity);
+			capacity = blob_capacity(blob, need, VT);
+			b = BinState::carve(align_base(blob), (size_t)capacity, VT);
 		}
 	}
 
 	GOF_PROF_MARK(ctx, marks, s);   // after the num_rendered hand-off
-	if ((rc = launch_binning(f, g, im, b, capacity, s)) != GOF_OK) return rc;
+	if ((rc = launch_binning(f, g, im, b, capacity, s, 0.0f, save_contrib)) != GOF_OK) return rc;
 	GOF_STAGE_CHECK(prm, s);
 	GOF_PROF_MARK(ctx, marks, s);
 	if ((rc = launch_render_fwd(*prm, f, g, im, b, in->background, bg_stride, out_color, sink, sink_hwc, s)) != GOF_OK) return rc;
@@ -398,11 +401,11 @@ int gof_integrate(GofContext* ctx, const GofParams* prm, const GofInputs* in, in
 	const int64_t R = ctx->pinned[0];
 	const size_t max_count = (size_t)ctx->pinned[2];
 	if (num_rendered) *num_rendered = (int32_t)R;
-	const size_t bin_bytes = BinState::carve(nullptr, (size_t)R).total;
+	const size_t bin_bytes = BinState::carve(nullptr, (size_t)R, (size_t)f.T).total;
 	const size_t scr_bytes = IntegrateScratch::carve(nullptr, (size_t)PN, (size_t)f.T, max_count).total;
 	char* blob = (char*)alloc(alloc_user, bin_bytes + scr_bytes + 2 * ALIGN);
 	if (!blob) { set_error("gof_integrate: allocation callback returned NULL for %zu bytes", bin_bytes + scr_bytes); return GOF_ENOMEM; }
-	BinState b = BinState::carve(align_base(blob), (size_t)R);
+	BinState b = BinState::carve(align_base(blob), (size_t)R, (size_t)f.T);
 	IntegrateScratch sc = IntegrateScratch::carve(align_base(align_base(blob) + bin_bytes), (size_t)PN, (size_t)f.T, max_count);
 	if ((rc = launch_binning(f, g, im, b, R, s, 0.5f)) != GOF_OK) return rc;
 	GOF_STAGE_CHECK(prm, s);
@@ -455,12 +458,12 @@ int gof_backward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* i
 	BinState b{};
 	if (num_rendered > 0) {
 		if (!binning) { set_error("gof_backward: binning blob is NULL but num_rendered=%lld", (long long)num_rendered); return GOF_EINVAL; }
-		const int64_t cap = blob_capacity(binning, binning_bytes);
+		const int64_t cap = blob_capacity(binning, binning_bytes, (size_t)f.T * (size_t)V);
 		if (cap < num_rendered) {
 			set_error("gof_backward: binning blob of %zu bytes holds %lld duplicates, num_rendered=%lld", binning_bytes, (long long)cap, (long long)num_rendered);
 			return GOF_ENOMEM;
 		}
-		b = BinState::carve(align_base(binning), (size_t)cap);
+		b = BinState::carve(align_base(binning), (size_t)cap, (size_t)f.T * (size_t)V);
 	}
 
 	const size_t need = (size_t)P * V * GACC_FLOATS;
@@ -553,9 +556,9 @@ int64_t gof_state_get_batch(const char* name, int32_t P, int32_t W, int32_t H, i
 	const size_t N = (size_t)W * H, n = (size_t)P * V, VT = (size_t)V * f.T;
 	GeomState g = GeomState::carve(align_base(geom), (size_t)P, (size_t)V);
 	ImgState im = ImgState::carve(align_base(img), N, (size_t)f.T, (size_t)V);
-	const int64_t cap = blob_capacity(binning, binning_bytes);
+	const int64_t cap = blob_capacity(binning, binning_bytes, VT);
 	if (cap < R) { set_error("gof_state_get: binning blob of %zu bytes holds %lld duplicates, num_rendered=%lld", binning_bytes, (long long)cap, (long long)R); return GOF_ENOMEM; }
-	BinState b = BinState::carve(align_base(binning), (size_t)cap);
+	BinState b = BinState::carve(align_base(binning), (size_t)cap, VT);
 	const std::string nm(name);
 	const void* src = nullptr;
 	size_t bytes = 0;

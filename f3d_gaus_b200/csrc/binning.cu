@@ -65,7 +65,7 @@ ImgState ImgState::carve(char* base, size_t N, size_t T, size_t V)
 	return im;
 }
 
-BinState BinState::carve(char* base, size_t R)
+BinState BinState::carve(char* base, size_t R, size_t VT)
 {
 	BinState b;
 	char* p = base;
@@ -73,6 +73,8 @@ BinState BinState::carve(char* base, size_t R)
 	take(p, b.point_list, R);
 	take(p, b.slab, R * SLAB_FLOATS);
 	take(p, b.block_mask, R);
+	take(p, b.bwd_rec, R * BWD_REC_FLOATS);
+	take(p, b.contrib, contrib_slots(R, VT) * CONTRIB_SLOT_WORDS);
 	b.total = align_up((size_t)(p - base)) + ALIGN;
 	return b;
 }
@@ -87,7 +89,7 @@ constexpr int SCAN_THREADS = 1024;
 __global__ void __launch_bounds__(SCAN_THREADS)
 tile_scan_kernel(int VT, int T, int V, const uint32_t* __restrict__ counts, uint2* __restrict__ ranges,
                  uint32_t* __restrict__ cursor, int32_t* __restrict__ mailbox, long long capacity,
-                 uint32_t* __restrict__ order)
+                 uint32_t* __restrict__ order, int save_contrib)
 {
 	__shared__ uint32_t s_part[SCAN_THREADS];
 	__shared__ uint32_t s_max[SCAN_THREADS / 32];
@@ -103,11 +105,29 @@ tile_scan_kernel(int VT, int T, int V, const uint32_t* __restrict__ counts, uint
 	mx = __reduce_max_sync(0xffffffffu, mx);
 	if ((tid & 31) == 0) s_max[tid >> 5] = mx;
 	__syncthreads();
-	// Hillis-Steele inclusive scan over the 1024 partials
-	for (int off = 1; off < SCAN_THREADS; off <<= 1) {
-		const uint32_t v = (tid >= off) ? s_part[tid - off] : 0;
+	// inclusive scan over the 1024 partials: shuffle scan inside each warp, then over the 32 warp totals
+	{
+		const int lane = tid & 31, wid = tid >> 5;
+		uint32_t v = sum;
+#pragma unroll
+		for (int off = 1; off < 32; off <<= 1) {
+			const uint32_t u = __shfl_up_sync(0xffffffffu, v, off);
+			if (lane >= off) v += u;
+		}
+		__shared__ uint32_t s_wsum[SCAN_THREADS / 32];
+		if (lane == 31) s_wsum[wid] = v;
 		__syncthreads();
-		s_part[tid] += v;
+		if (wid == 0) {
+			uint32_t t = s_wsum[lane];
+#pragma unroll
+			for (int off = 1; off < 32; off <<= 1) {
+				const uint32_t u = __shfl_up_sync(0xffffffffu, t, off);
+				if (lane >= off) t += u;
+			}
+			s_wsum[lane] = t;
+		}
+		__syncthreads();
+		s_part[tid] = v + (wid ? s_wsum[wid - 1] : 0u);
 		__syncthreads();
 	}
 	uint32_t run = s_part[tid] - sum;   // exclusive prefix of this thread's chunk
@@ -149,7 +169,7 @@ tile_scan_kernel(int VT, int T, int V, const uint32_t* __restrict__ counts, uint
 		mailbox[0] = (int32_t)total;
 		mailbox[1] = ((long long)total > capacity) ? 1 : 0;
 		mailbox[2] = (int32_t)m;
-		mailbox[3] = 0;
+		mailbox[3] = save_contrib;
 		int32_t prev = 0;
 		for (int v = 0; v < V; v++) {   // per-view R from the inclusive prefixes written above
 			const int32_t inc = mailbox[MAILBOX_HEAD + v];
@@ -324,7 +344,8 @@ tile_sort_gather_kernel(int P, int T, dim3 grid, int W, int H, float focal_x, fl
                         const uint2* __restrict__ ranges, uint64_t* __restrict__ entries,
                         const float* __restrict__ rec_all, uint32_t* __restrict__ point_list,
                         float* __restrict__ slab, uint8_t* __restrict__ block_mask, const int32_t* __restrict__ mailbox,
-                        const uint32_t* __restrict__ tile_order)
+                        const uint32_t* __restrict__ tile_order, float* __restrict__ bwd_rec,
+                        const float2* __restrict__ means2D_all, const float4* __restrict__ conic_opacity_all)
 {
 	__shared__ uint64_t s_e[SORT_CAP];
 	pdl_trigger();
@@ -378,6 +399,14 @@ tile_sort_gather_kernel(int P, int T, dim3 grid, int W, int H, float focal_x, fl
 		dst[2] = make_float4(q0.y, q0.z, q0.w, q1.x);          // Sxy Sxz Syy Syz
 		dst[3] = make_float4(q1.y, q1.z, q1.w, q2.x);          // Szz Bx By Bz
 		dst[4] = make_float4(q2.y, q3.x, q3.y, q3.z);          // C r g b
+		if (bwd_rec != nullptr) {
+			// what the backward blend needs per pair besides the slab record (backward.cu:897-909): 2-D mean, 2-D conic, id
+			const float2 xy = __ldg(&means2D_all[(size_t)view * P + id]);
+			const float4 co = __ldg(&conic_opacity_all[(size_t)view * P + id]);
+			float4* bd = reinterpret_cast<float4*>(bwd_rec + (size_t)(range.x + i) * BWD_REC_FLOATS);
+			bd[0] = make_float4(xy.x, xy.y, co.x, co.y);
+			bd[1] = make_float4(co.z, __uint_as_float(id), 0.0f, 0.0f);
+		}
 	}
 }
 
@@ -426,22 +455,22 @@ extract_offsets_kernel(int P, const uint32_t* __restrict__ tiles_touched, uint32
 
 }  // namespace
 
-int launch_tile_scan(const Frame& f, const GeomState& g, const ImgState& im, int64_t capacity, cudaStream_t s)
+int launch_tile_scan(const Frame& f, const GeomState& g, const ImgState& im, int64_t capacity, cudaStream_t s, int save_contrib)
 {
 	GOF_CUDA_CHECK(launch_chained(PDL_SCAN, tile_scan_kernel, dim3(1), dim3(SCAN_THREADS), 0, s, f.V * f.T, f.T, f.V, im.tile_counts, im.ranges,
-	                              im.tile_cursor, g.mailbox, (long long)capacity, im.tile_order));
+	                              im.tile_cursor, g.mailbox, (long long)capacity, im.tile_order, save_contrib));
 	return GOF_OK;
 }
 
 int launch_tile_scan_raw(int T, const uint32_t* counts, uint2* ranges, uint32_t* cursor, int32_t* mailbox, cudaStream_t s)
 {
 	GOF_CUDA_CHECK(launch_chained(PDL_SCAN, tile_scan_kernel, dim3(1), dim3(SCAN_THREADS), 0, s, T, T, 1, counts, ranges, cursor, mailbox,
-	                              (long long)1 << 40, (uint32_t*)nullptr));
+	                              (long long)1 << 40, (uint32_t*)nullptr, 0));
 	return GOF_OK;
 }
 
 int launch_binning(const Frame& f, const GeomState& g, const ImgState& im, const BinState& b, int64_t capacity,
-                   cudaStream_t s, float ray_pad)
+                   cudaStream_t s, float ray_pad, int for_backward)
 {
 	if (capacity <= 0) return GOF_OK;
 	dim3 blocks((f.P + 255) / 256, f.V);
@@ -449,7 +478,7 @@ int launch_binning(const Frame& f, const GeomState& g, const ImgState& im, const
 	                              im.tile_cursor, b.entries, g.mailbox));
 	GOF_CUDA_CHECK(launch_chained(PDL_SORT, tile_sort_gather_kernel, dim3(f.V * f.T), dim3(SORT_THREADS), 0, s, f.P, f.T, f.grid, f.W, f.H,
 	                              f.focal_x, f.focal_y, ray_pad, im.ranges, b.entries, g.rec, b.point_list, b.slab, b.block_mask,
-	                              g.mailbox, im.tile_order));
+	                              g.mailbox, im.tile_order, for_backward ? b.bwd_rec : (float*)nullptr, g.means2D, g.conic_opacity));
 	return GOF_OK;
 }
 

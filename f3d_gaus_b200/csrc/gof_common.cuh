@@ -42,7 +42,7 @@ constexpr int SLAB_BYTES = 80;
 constexpr size_t ALIGN = 256;
 __host__ __device__ inline size_t align_up(size_t x, size_t a = ALIGN) { return (x + a - 1) / a * a; }
 
-constexpr int MAILBOX_HEAD = GOF_MAILBOX_HEAD;   // mailbox ints: {R_total, overflow, max tile count, -, R_view[0..V-1]}
+constexpr int MAILBOX_HEAD = GOF_MAILBOX_HEAD;   // mailbox ints: {R_total, overflow, max tile count, contributor masks saved, R_view[0..V-1]}
 
 // ---- opaque state layouts (our own; the reference's are rasterizer_impl.cu:188-243) -------
 // All per-Gaussian arrays are [V, P] (view-major); V = 1 for the single-frame entry points.
@@ -73,9 +73,17 @@ struct BinState {
 	uint32_t* point_list;      // [R]  sorted Gaussian indices (the reference's point_list)
 	float* slab;               // [R,20] tile-ordered slab records
 	uint8_t* block_mask;       // [R]  bit b: the record can pass the conic test in 8x4 pixel block b of its tile
+	float* bwd_rec;            // [R,8]  tile-ordered backward record {mean2D.xy, conic.xyz, Gaussian id, -, -}: what the backward
+	                           //  blend needs per pair besides the slab, so that it streams instead of gathering (training forwards)
+	uint32_t* contrib;         // [slots][4][256]  per pixel: which records of the tile list it BLENDED (training forwards
+	                           //  only, GOF_FLAG_SAVE_CONTRIB); slot of chunk c of tile gt = (ranges[gt].x >> 7) + gt + c
 	size_t total;
-	static BinState carve(char* base, size_t R);
+	static size_t contrib_slots(size_t R, size_t VT) { return (R >> 7) + VT + 1; }
+	static BinState carve(char* base, size_t R, size_t VT);
 };
+constexpr int CONTRIB_SLOT_WORDS = 4 * TILE_PIX;   // 4 KB per 128-record chunk of a tile
+constexpr int BWD_REC_FLOATS = 8;
+constexpr int BWD_REC_BYTES = 32;
 
 // ---- error plumbing ---------------------------------------------------------------------
 void set_error(const char* fmt, ...);
@@ -131,10 +139,12 @@ struct Frame {
 // ---- stage launchers (one .cu each) ---------------------------------------------------------
 int launch_preprocess(const GofParams& prm, const GofInputs& in, const Frame& f, const GeomState& g,
                       const ImgState& im, int32_t* radii, cudaStream_t s);
-int launch_tile_scan(const Frame& f, const GeomState& g, const ImgState& im, int64_t capacity, cudaStream_t s);
+// save_contrib: recorded in mailbox[3] -- tells the backward that the forward left per-pixel contributor masks
+int launch_tile_scan(const Frame& f, const GeomState& g, const ImgState& im, int64_t capacity, cudaStream_t s, int save_contrib = 0);
 // ray_pad: 0 for the blend (rays through pixel centres), 0.5 for point integration (conic.cuh)
+// for_backward: also write BinState::bwd_rec (a training forward, GOF_FLAG_SAVE_CONTRIB)
 int launch_binning(const Frame& f, const GeomState& g, const ImgState& im, const BinState& b, int64_t capacity,
-                   cudaStream_t s, float ray_pad = 0.0f);
+                   cudaStream_t s, float ray_pad = 0.0f, int for_backward = 0);
 // point integration (integrate.cu)
 struct IntegrateScratch {
 	uint32_t* used_mask;      // [T][words][256]  per-pixel contributed bits over the tile's list

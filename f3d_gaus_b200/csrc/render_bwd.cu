@@ -32,11 +32,48 @@ namespace {
 #define GOF_BWD_MIN_CTAS 2
 #endif
 constexpr int CHUNK = 128;
-constexpr int STAGES = 3;
+constexpr int NW = CHUNK / 32;
+constexpr int STAGES = 4;            // power of two: the ring is addressed by list position (chunk c lives in stage c % 4)
+constexpr int QUEUE_ROWS = 2 * NW;   // survivor words of the two chunks a warp works on (see LaneQueueDown)
 constexpr int CONSUMER_WARPS = TILE_PIX / 32;
 constexpr int BWD_THREADS = TILE_PIX + 32;
-constexpr int STAGE_REC_BYTES = CHUNK * SLAB_BYTES;      // 10 KB
-constexpr size_t BWD_SMEM = (size_t)STAGES * STAGE_REC_BYTES + 2 * STAGES * sizeof(uint64_t) + 64;
+constexpr int STAGE_SLAB_BYTES = CHUNK * SLAB_BYTES;     // 10 KB of slab records ...
+constexpr int STAGE_REC_BYTES = STAGE_SLAB_BYTES + CHUNK * BWD_REC_BYTES;   // ... + 4 KB of backward records per stage
+constexpr size_t BWD_SMEM = (size_t)STAGES * STAGE_REC_BYTES + 2 * STAGES * sizeof(uint64_t) + 64 +
+                            (size_t)QUEUE_ROWS * TILE_PIX * 4;      // ring | barriers | s_max | survivor queues
+
+// Survivors of one lane (= pixel) in the two chunks its warp is working on, walked from the BACK of the tile list: eight
+// 32-record words in shared memory, one private column per thread (word w of the list -> row w % 8), the word being
+// consumed (`cur`, bits not popped yet) and its index `p` in registers.  Mirror image of render_fwd.cu's LaneQueue.
+// Invariant: cur != 0 unless nothing is queued at or above p_low.
+struct LaneQueueDown {
+	uint32_t cur, p, col;
+	__device__ __forceinline__ uint32_t row(uint32_t w) const { return col + (w % QUEUE_ROWS) * (TILE_PIX * 4); }
+	__device__ __forceinline__ void store_chunk(int c, uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) const
+	{
+		const uint32_t w = (uint32_t)c * NW;
+		asm volatile("st.shared.u32 [%0], %1;" ::"r"(row(w + 0)), "r"(m0) : "memory");
+		asm volatile("st.shared.u32 [%0], %1;" ::"r"(row(w + 1)), "r"(m1) : "memory");
+		asm volatile("st.shared.u32 [%0], %1;" ::"r"(row(w + 2)), "r"(m2) : "memory");
+		asm volatile("st.shared.u32 [%0], %1;" ::"r"(row(w + 3)), "r"(m3) : "memory");
+	}
+	__device__ __forceinline__ void normalise(uint32_t p_low)       // skip exhausted words, down to word p_low
+	{
+		while (cur == 0 && p > p_low) {
+			p--;
+			asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cur) : "r"(row(p)) : "memory");
+		}
+	}
+	__device__ __forceinline__ bool pop(uint32_t& j, uint32_t p_low) // deepest queued survivor: its position in the tile list
+	{
+		if (cur == 0) return false;
+		const uint32_t bit = 31u - (uint32_t)__clz((int)cur);
+		j = (p << 5) + bit;
+		cur &= ~(1u << bit);
+		normalise(p_low);
+		return true;
+	}
+};
 
 __device__ __forceinline__ void red_global_v4(float* addr, float4 v)
 {
@@ -66,7 +103,8 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
                   float focal_x, float focal_y, const float* __restrict__ bg_colors, int bg_stride,
                   const float2* __restrict__ means2D_all, const float4* __restrict__ conic_opacity_all,
                   const float* __restrict__ final_Ts_all, const uint32_t* __restrict__ n_contrib_all,
-                  const float* __restrict__ dL_dpixels_all, float* __restrict__ gacc_all)
+                  const float* __restrict__ dL_dpixels_all, float* __restrict__ gacc_all,
+                  const uint32_t* __restrict__ contrib, const int32_t* __restrict__ mailbox, const float* __restrict__ bwd_rec)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	// layout: [STAGES] record stages | full[STAGES] | empty[STAGES] | s_max[8]
@@ -74,6 +112,7 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 	uint64_t* s_full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * STAGE_REC_BYTES);
 	uint64_t* s_empty = s_full + STAGES;
 	uint32_t* s_max = reinterpret_cast<uint32_t*>(s_empty + STAGES);
+	uint32_t* s_queue = s_max + 16;                                  // [QUEUE_ROWS][256]
 
 	const int tid = threadIdx.x;
 	const int warp = tid >> 5, lane = tid & 31;
@@ -103,9 +142,15 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 	const int n = (int)(range.y - range.x);
 	const float* tile_slab = slab + (size_t)range.x * SLAB_FLOATS;
 	const uint32_t* tile_ids = point_list + range.x;
+	// Did the forward run with GOF_FLAG_SAVE_CONTRIB (recorded in the mailbox by the tile scan)?  Then it left (a) per-pixel
+	// contributor masks: pass 1 is a 16-byte load per pixel and chunk instead of the conic sweep, and every queued record
+	// contributes; (b) tile-ordered backward records {mean2D, conic, id}: pass 2 reads them from the ring instead of
+	// chasing point_list -> means2D / conic_opacity through L2 (two dependent round trips per pair, the top stall).
+	const bool have_masks = mailbox[3] != 0;
 
 	const uint32_t last_contributor = inside ? n_contrib[pix_id] : 0;
 	const uint32_t max_contributor = inside ? n_contrib[pix_id + N] : 0;
+	const uint32_t* tile_contrib = contrib + ((size_t)(range.x >> 7) + gt) * CONTRIB_SLOT_WORDS + (tid & (TILE_PIX - 1));
 
 	// Deepest record any pixel of this tile blended; init barriers.
 	const uint32_t wmax = __reduce_max_sync(0xffffffffu, last_contributor);
@@ -121,19 +166,23 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 	for (int k = 0; k < CONSUMER_WARPS; k++) tile_last = max(tile_last, s_max[k]);
 	const int m = min((int)tile_last, n);           // records [0, m) may contribute
 	const int nchunks = (m + CHUNK - 1) / CHUNK;     // walked from chunk nchunks-1 down to 0
-	// the i-th chunk in walk order is chunk (nchunks-1-i); it lives in stage i % STAGES
+	// the i-th chunk in walk order is chunk c = nchunks-1-i; it lives in stage c % STAGES (every run of STAGES consecutive
+	// chunks uses every stage once, so a stage's k-th use is walk index i with i / STAGES == k: the barrier parities)
 
 	if (!consumer) {
 		// ------------- producer warp: one elected lane streams the slab, deepest chunk first ---------
 		if (lane == 0) {
 			for (int i = 0; i < nchunks; i++) {
-				const int s = i % STAGES;
-				if (i >= STAGES) mbar_wait_backoff(&s_empty[s], (uint32_t)(((i / STAGES) - 1) & 1));
 				const int c = nchunks - 1 - i;
+				const int s = c % STAGES;
+				if (i >= STAGES) mbar_wait_backoff(&s_empty[s], (uint32_t)(((i / STAGES) - 1) & 1));
 				const int cnt = min(CHUNK, m - c * CHUNK);
-				const uint32_t bytes = (uint32_t)cnt * SLAB_BYTES;
-				mbar_arrive_expect_tx(&s_full[s], bytes);
+				const uint32_t bytes = (uint32_t)cnt * SLAB_BYTES, aux_bytes = have_masks ? (uint32_t)cnt * BWD_REC_BYTES : 0u;
+				mbar_arrive_expect_tx(&s_full[s], bytes + aux_bytes);
 				tma_bulk_g2s(smem_raw + (size_t)s * STAGE_REC_BYTES, tile_slab + (size_t)c * CHUNK * SLAB_FLOATS, bytes, &s_full[s]);
+				if (have_masks)      // the training forward also left tile-ordered backward records: stream them alongside
+					tma_bulk_g2s(smem_raw + (size_t)s * STAGE_REC_BYTES + STAGE_SLAB_BYTES,
+					             bwd_rec + ((size_t)range.x + (size_t)c * CHUNK) * BWD_REC_FLOATS, aux_bytes, &s_full[s]);
 			}
 		}
 		return;
@@ -142,7 +191,6 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 	// ------------- consumer warps -----------------------------------------------------------------
 	const float rx = pixel_ray(px, W, focal_x);
 	const float ry = pixel_ray(py, H, focal_y);
-	const float fx = (float)lx, fy = (float)ly;
 
 	// Per-pixel state (backward.cu:690-735).
 	const float T_final = inside ? final_Ts[pix_id] : 0;
@@ -167,49 +215,93 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 	const float ddelx_dx = 0.5 * W;
 	const float ddely_dy = 0.5 * H;
 
-	for (int i = 0; i < nchunks; i++) {
-		const int c = nchunks - 1 - i;
-		const int s = i % STAGES;
-		mbar_wait(&s_full[s], (uint32_t)((i / STAGES) & 1));
-		const int cnt = min(CHUNK, m - c * CHUNK);
-		const uint32_t rec = rec_base + s * STAGE_REC_BYTES;
+	// ---- pass 1 of chunk c: the lane's contributor candidates among the chunk's 128 records, into the queue rows.
+	// With masks: four words loaded from the forward's contributor masks (requested one chunk ahead, see request_masks);
+	// without: the conic sweep over the records this pixel can have blended (index < last_contributor).
+	uint32_t nx0 = 0, nx1 = 0, nx2 = 0, nx3 = 0;
+	auto request_masks = [&](int c) {
+		// volatile: the loads must be ISSUED here, a whole chunk ahead of their use (the compiler would otherwise be
+		// free to sink them to their use and expose the L2 latency once per chunk)
+		const uint32_t* w = tile_contrib + (size_t)c * CONTRIB_SLOT_WORDS;
+		asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(nx0) : "l"(w));
+		asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(nx1) : "l"(w + TILE_PIX));
+		asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(nx2) : "l"(w + 2 * TILE_PIX));
+		asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(nx3) : "l"(w + 3 * TILE_PIX));
+	};
+	LaneQueueDown q;
+	q.cur = 0;
+	q.p = (uint32_t)max(nchunks, 1) * NW - 1u;
+	q.col = smem_u32(s_queue) + (uint32_t)tid * 4u;
+	auto stage_of = [&](int c) { return rec_base + (uint32_t)(c % STAGES) * STAGE_REC_BYTES; };
+	auto sweep = [&](int c) {                 // chunk c must be the next one in walk order that has not been swept
+		const int i = nchunks - 1 - c;
+		uint32_t m0 = nx0, m1 = nx1, m2 = nx2, m3 = nx3;
+		if (have_masks && c > 0) request_masks(c - 1);
+		mbar_wait(&s_full[c % STAGES], (uint32_t)((i / STAGES) & 1));
 		const uint32_t base = (uint32_t)c * CHUNK;
-
-		// ---- pass 1: conic sweep; only records this pixel blended (index < last_contributor) ----
-		uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-		if (base < last_contributor) {
+		if (!have_masks) {
+			m0 = m1 = m2 = m3 = 0;
+			if (base < last_contributor) {
+				const int cnt = min(CHUNK, m - c * CHUNK);
+				const float fx = (float)lx, fy = (float)ly;
+				const uint32_t rec = stage_of(c);
 #pragma unroll 1
-			for (int w = 0; w < CHUNK / 32; w++) {
-				const int valid = min(cnt, (int)(last_contributor - base)) - 32 * w;
-				if (valid <= 0) break;
-				uint32_t bits = 0;
-				const uint32_t rw = rec + (uint32_t)w * (32 * SLAB_BYTES);
+				for (int w = 0; w < NW; w++) {
+					const int valid = min(cnt, (int)(last_contributor - base)) - 32 * w;
+					if (valid <= 0) break;
+					uint32_t bits = 0;
+					const uint32_t rw = rec + (uint32_t)w * (32 * SLAB_BYTES);
 #pragma unroll
-				for (int jj = 0; jj < 32; jj++) {
-					const float4 k0 = lds128(rw + jj * SLAB_BYTES);
-					const float2 k1 = lds64(rw + jj * SLAB_BYTES + 16);
-					if (!conic_reject(k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, fx, fy)) bits |= 1u << jj;
+					for (int jj = 0; jj < 32; jj++) {
+						const float4 k0 = lds128(rw + jj * SLAB_BYTES);
+						const float2 k1 = lds64(rw + jj * SLAB_BYTES + 16);
+						if (!conic_reject(k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, fx, fy)) bits |= 1u << jj;
+					}
+					if (valid < 32) bits &= (1u << valid) - 1u;
+					if (w == 0) m0 = bits; else if (w == 1) m1 = bits; else if (w == 2) m2 = bits; else m3 = bits;
 				}
-				if (valid < 32) bits &= (1u << valid) - 1u;
-				if (w == 0) m0 = bits; else if (w == 1) m1 = bits; else if (w == 2) m2 = bits; else m3 = bits;
 			}
 		}
-		// ---- pass 2: this pixel's survivors, back to front; m3 is the word being consumed ----------
-		uint32_t jbase = 96;
-		while ((m0 | m1 | m2 | m3) != 0) {
-			if (m3 == 0) { m3 = m2; m2 = m1; m1 = m0; m0 = 0; jbase -= 32; }
-			if (m3 != 0) {
-				const uint32_t bit = 31u - (uint32_t)__clz((int)m3);
-				m3 &= ~(1u << bit);
-				const uint32_t j = jbase + bit;
+		q.store_chunk(c, m0, m1, m2, m3);
+		return m3;
+	};
+	if (have_masks && nchunks > 0) request_masks(nchunks - 1);
+	if (nchunks > 0) q.cur = sweep(nchunks - 1);
+	if (nchunks > 1) sweep(nchunks - 2);
+	q.normalise((uint32_t)max(nchunks - 2, 0) * NW);
+
+	// ---- pass 2: each pixel walks its own contributors, back to front.  As in the forward blend the lanes of a warp are
+	// not synchronised at chunk boundaries: a lane queues the candidates of two chunks, ca (the deepest chunk some lane of
+	// the warp still needs) and ca-1, and moves on to ca-1 as soon as it has nothing left in ca; the warp advances (lets
+	// go of the stage of ca, sweeps chunk ca-2) when no lane has anything left in ca.
+	for (int ca = nchunks - 1; ca >= 0; ca--) {
+		const uint32_t p_low = (uint32_t)max(ca - 1, 0) * NW;       // lowest word queued
+		const uint32_t p_a = (uint32_t)ca * NW;                     // first word of chunk ca
+		while (__any_sync(0xffffffffu, q.cur != 0 && q.p >= p_a)) {
+			uint32_t contributor;                                   // 0-based position in the tile list
+			if (q.pop(contributor, p_low)) {
+				const uint32_t j = contributor & (CHUNK - 1);
+				const uint32_t rec = stage_of((int)(contributor >> 7));
 				const uint32_t r = rec + j * SLAB_BYTES;
 				const float4 k1 = lds128(r + 16), k2 = lds128(r + 32), k3 = lds128(r + 48), k4 = lds128(r + 64);
-				// the Gaussian's id and its 2-D mean / conic (two dependent L2 round trips) are requested before the exact
-				// evaluation so that they are in flight during its double division; nearly every survivor needs them
-				const uint32_t contributor = base + j;       // 0-based position in the tile list
-				const int gid = (int)__ldg(&tile_ids[contributor]);
-				const float2 xy = __ldg(&means2D[gid]);
-				const float4 con = __ldg(&conic_opacity[gid]);
+				// the Gaussian's id and its 2-D mean / conic: from the tile-ordered backward record in the ring when the
+				// forward left one; otherwise gathered (two dependent L2 round trips, requested before the exact evaluation
+				// so that they are in flight during its double division)
+				int gid;
+				float2 xy;
+				float4 con;
+				if (have_masks) {
+					const uint32_t ar = rec + STAGE_SLAB_BYTES + j * BWD_REC_BYTES;
+					const float4 x0 = lds128(ar);
+					const float2 x1 = lds64(ar + 16);
+					xy = make_float2(x0.x, x0.y);
+					con = make_float4(x0.z, x0.w, x1.x, 0.0f);
+					gid = __float_as_int(x1.y);
+				} else {
+					gid = (int)__ldg(&tile_ids[contributor]);
+					xy = __ldg(&means2D[gid]);
+					con = __ldg(&conic_opacity[gid]);
+				}
 				const PairGeom g = pair_geom(k1, k2, k3, rx, ry);
 				const float w = k1.z;
 				float t, alpha, G;
@@ -319,7 +411,11 @@ render_bwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 			}
 		}
 		__syncwarp();
-		if (lane == 0) mbar_arrive(&s_empty[s]);   // this warp is finished with stage s
+		if (lane == 0) mbar_arrive(&s_empty[ca % STAGES]);   // this warp is finished with the stage of chunk ca
+		if (ca >= 2) {
+			sweep(ca - 2);
+			q.normalise((uint32_t)(ca - 2) * NW);              // a lane that had run dry picks up the new words
+		}
 	}
 }
 
@@ -332,7 +428,7 @@ int launch_render_bwd(const GofParams& prm, const Frame& f, const GeomState& g, 
 	const dim3 grid((unsigned)(f.T * f.V), 1, 1);
 	GOF_CUDA_CHECK(cudaFuncSetAttribute(render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM));
 	render_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, s>>>(im.ranges, im.tile_order, f.T, (int)f.grid.x, b.slab, b.point_list, f.P, prm.W, prm.H, f.focal_x, f.focal_y, background, bg_stride,
-	                                                     g.means2D, g.conic_opacity, im.final_T, im.n_contrib, dL_dpix, gacc);
+	                                                     g.means2D, g.conic_opacity, im.final_T, im.n_contrib, dL_dpix, gacc, b.contrib, g.mailbox, b.bwd_rec);
 	GOF_CUDA_CHECK(cudaGetLastError());
 	return GOF_OK;
 }

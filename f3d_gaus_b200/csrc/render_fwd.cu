@@ -160,20 +160,25 @@ struct LaneQueue {
 	}
 };
 
-template <bool EXACT, bool SINK>
+// MASK: also record, per pixel, which records of the tile list were blended (GOF_FLAG_SAVE_CONTRIB): one bit per list
+// position, kept for the window's two chunks in shared memory ([chunk parity][word][thread], lane-private columns) and
+// written out as whole 128-record blocks when the warp lets go of a chunk -- contrib[slot][word][thread], coalesced.
+template <bool EXACT, bool SINK, bool MASK>
 __global__ void __launch_bounds__(FWD_THREADS, GOF_FWD_MIN_CTAS)
 render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int T, int tiles_x,
                   const float* __restrict__ slab, int W, int H,
                   float focal_x, float focal_y, const float* __restrict__ bg_colors, int bg_stride,
                   float* __restrict__ final_T_all, uint32_t* __restrict__ n_contrib_all, float* __restrict__ out_color_all,
-                  const int32_t* __restrict__ mailbox, const uint8_t* __restrict__ block_mask, float* __restrict__ sink_all, int sink_hwc)
+                  const int32_t* __restrict__ mailbox, const uint8_t* __restrict__ block_mask, float* __restrict__ sink_all, int sink_hwc,
+                  uint32_t* __restrict__ contrib)
 {
 	static_assert(NW == 4, "the survivor queues are written for 128-record chunks");
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	uint64_t* s_full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * CHUNK * SLAB_BYTES);
 	uint32_t* s_released = reinterpret_cast<uint32_t*>(s_full + STAGES);      // per stage: warps that have let go of it (monotonic)
 	uint32_t* s_queue = reinterpret_cast<uint32_t*>(s_full + 2 * STAGES);     // [QUEUE_ROWS][256] survivor words (LaneQueue)
-	float* s_out = reinterpret_cast<float*>(s_queue + QUEUE_ROWS * FWD_THREADS);   // [SINK_CH * 256] tile of the frame sink
+	uint32_t* s_blended = s_queue + QUEUE_ROWS * FWD_THREADS;                 // MASK: [QUEUE_ROWS][256] blended bits, same layout
+	float* s_out = reinterpret_cast<float*>(s_blended + (MASK ? QUEUE_ROWS * FWD_THREADS : 0));   // [SINK_CH * 256] tile of the frame sink
 
 	const int tid = threadIdx.x;
 	const int warp = tid >> 5, lane = tid & 31;
@@ -313,6 +318,31 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 	q.cur = 0;
 	q.p = 0;
 	q.col = smem_u32(s_queue) + (uint32_t)tid * 4u;
+	// MASK: this thread's column of blended bits sits QUEUE_ROWS rows behind its queue column
+	constexpr uint32_t BLENDED_OFF = QUEUE_ROWS * FWD_THREADS * 4;
+	if (MASK) {
+#pragma unroll
+		for (int w = 0; w < QUEUE_ROWS; w++) s_blended[w * FWD_THREADS + tid] = 0;
+	}
+	auto mark_blended = [&](uint32_t j) {               // list position j was blended by this pixel
+		const uint32_t a = q.row(j >> 5) + BLENDED_OFF;
+		uint32_t v;
+		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+		v |= 1u << (j & 31u);
+		asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+	};
+	// contributor-mask block of chunk c of this tile (gof_common.cuh: BinState::contrib)
+	uint32_t* const tile_contrib = MASK ? contrib + ((size_t)(range.x >> 7) + gt) * CONTRIB_SLOT_WORDS + tid : nullptr;
+	auto flush_blended = [&](int c) {                   // the warp is done with chunk c: write its four words, clear the rows
+#pragma unroll
+		for (int k = 0; k < NW; k++) {
+			const uint32_t a = q.row((uint32_t)c * NW + k) + BLENDED_OFF;
+			uint32_t v;
+			asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+			tile_contrib[(size_t)c * CONTRIB_SLOT_WORDS + k * TILE_PIX] = v;
+			asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(0u) : "memory");
+		}
+	};
 	{
 		uint32_t m[NW];
 		if (nchunks > 0) { conic_sweep(0, m); q.store_chunk(0, m); q.cur = m[0]; }
@@ -340,13 +370,22 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 			const bool oka = pair_alpha_eval(ga, a4.x, a1.z, ta, alpha_a);
 			const bool okb = pair_alpha_eval(gb, b4.x, b1.z, tb, alpha_b) && hb;
 			// contributor ids are 1-based list positions (forward.cu:494-496)
-			if ((oka && blend_pair<EXACT>(st, ga, ta, alpha_a, make_float4(a4.y, a4.z, a4.w, 0.0f), ja + 1u)) ||
-			    (okb && blend_pair<EXACT>(st, gb, tb, alpha_b, make_float4(b4.y, b4.z, b4.w, 0.0f), jb + 1u))) {
+			bool saturated = false;
+			if (oka) {
+				saturated = blend_pair<EXACT>(st, ga, ta, alpha_a, make_float4(a4.y, a4.z, a4.w, 0.0f), ja + 1u);
+				if (MASK && !saturated) mark_blended(ja);
+			}
+			if (okb && !saturated) {
+				saturated = blend_pair<EXACT>(st, gb, tb, alpha_b, make_float4(b4.y, b4.z, b4.w, 0.0f), jb + 1u);
+				if (MASK && !saturated) mark_blended(jb);
+			}
+			if (saturated) {
 				done = true;                                        // the pixel is saturated: it has no survivors any more
 				q.cur = 0;
 				q.p = 0xffffff00u;                                  // beyond every p_end: normalise() never reloads
 			}
 		}
+		if (MASK) flush_blended(ca);
 		release_stage(ca);
 		warp_done = __all_sync(0xffffffffu, done);
 		if (ca + 2 < nchunks) {
@@ -432,18 +471,24 @@ int launch_render_fwd(const GofParams& prm, const Frame& f, const GeomState& g, 
                       const float* background, int bg_stride, float* out_color, float* sink, int sink_hwc, cudaStream_t s)
 {
 	const dim3 grid((unsigned)(f.T * f.V), 1, 1);
-	const size_t smem = (size_t)STAGES * CHUNK * SLAB_BYTES + 2 * STAGES * sizeof(uint64_t) + (size_t)QUEUE_ROWS * FWD_THREADS * 4 +
-	                    (sink ? (size_t)SINK_CH * TILE_PIX * sizeof(float) : 0);   // ring | full barriers | release counters | queues | sink tile
+	const bool mask = (prm.flags & GOF_FLAG_SAVE_CONTRIB) != 0;
+	const size_t smem = (size_t)STAGES * CHUNK * SLAB_BYTES + 2 * STAGES * sizeof(uint64_t) + (size_t)QUEUE_ROWS * FWD_THREADS * 4 * (mask ? 2 : 1) +
+	                    (sink ? (size_t)SINK_CH * TILE_PIX * sizeof(float) : 0);   // ring | full barriers | release counters | queues (| blended bits) | sink tile
 	auto launch = [&](auto kernel) {
 		// per device and per function; cheap enough to set on every launch (one process may drive several GPUs)
 		if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return;
 		launch_chained(PDL_BLEND, kernel, grid, dim3(FWD_THREADS), smem, s, im.ranges, im.tile_order, f.T, (int)f.grid.x, b.slab, prm.W, prm.H,
 		               f.focal_x, f.focal_y, background, bg_stride, im.final_T, im.n_contrib, out_color, g.mailbox, b.block_mask, sink,
-		               sink_hwc);
+		               sink_hwc, b.contrib);
 	};
 	const bool exact = (prm.flags & GOF_FLAG_EXACT_BLEND) != 0;
-	if (sink) { if (exact) launch(render_fwd_kernel<true, true>); else launch(render_fwd_kernel<false, true>); }
-	else      { if (exact) launch(render_fwd_kernel<true, false>); else launch(render_fwd_kernel<false, false>); }
+	if (mask) {
+		if (sink) { if (exact) launch(render_fwd_kernel<true, true, true>); else launch(render_fwd_kernel<false, true, true>); }
+		else      { if (exact) launch(render_fwd_kernel<true, false, true>); else launch(render_fwd_kernel<false, false, true>); }
+	} else {
+		if (sink) { if (exact) launch(render_fwd_kernel<true, true, false>); else launch(render_fwd_kernel<false, true, false>); }
+		else      { if (exact) launch(render_fwd_kernel<true, false, false>); else launch(render_fwd_kernel<false, false, false>); }
+	}
 	GOF_CUDA_CHECK(cudaGetLastError());
 	return GOF_OK;
 }

@@ -114,8 +114,11 @@ class _CModule:
             gbytes, ibytes = _state_sizes(P, W, H)
             geom = torch.empty(gbytes, **byte_opts)
             img = torch.empty(ibytes, **byte_opts)
+            # (inside an autograd.Function's forward grad mode is off, but the inputs still say whether they require grad)
             prm = _lib.GofParams(P, int(degree), M, W, H, float(tan_fovx), float(tan_fovy), float(kernel_size),
-                                 float(scale_modifier), int(bool(prefiltered)), int(bool(debug)), _lib.default_flags())
+                                 float(scale_modifier), int(bool(prefiltered)), int(bool(debug)),
+                                 _lib.default_flags(means3D, colors, opacity, scales, rotations, sh, cov3D_precomp,
+                                                    view2gaussian_precomp))
             inp = _lib.GofInputs(
                 _dev_ptr(background, device, keep), _dev_ptr(means3D, device, keep), _dev_ptr(sh, device, keep),
                 _dev_ptr(colors, device, keep), _dev_ptr(opacity, device, keep), _dev_ptr(scales, device, keep),
@@ -359,7 +362,8 @@ def rasterize_views(background, means3D, colors, opacity, scales, rotations, sca
         bg = background.reshape(-1)
         bg_stride = 3 if bg.numel() == 3 * V and V > 1 else 0
         prm = _lib.GofParams(P, int(degree), M, W, H, float(tan_fovx), float(tan_fovy), float(kernel_size),
-                             float(scale_modifier), int(bool(prefiltered)), int(bool(debug)), _lib.default_flags())
+                             float(scale_modifier), int(bool(prefiltered)), int(bool(debug)),
+                             _lib.default_flags(means3D, colors, opacity, scales, rotations, sh))
         inp = _lib.GofInputs(
             _dev_ptr(bg, device, keep), _dev_ptr(means3D, device, keep), _dev_ptr(sh, device, keep),
             _dev_ptr(colors, device, keep), _dev_ptr(opacity, device, keep), _dev_ptr(scales, device, keep),

@@ -114,6 +114,26 @@ def depths_to_points(world_view_transform, image_width, image_height, FoVx, FoVy
     return cam @ view_to_world[:3, :3] + view_to_world[3, :3]
 
 
+_SH_CACHE: dict = {}
+
+
+def _packed_sh(features_dc: torch.Tensor, features_rest: torch.Tensor) -> torch.Tensor:
+    """[P,1,3] + [P,M-1,3] -> contiguous [P,M,3] (the reference's per-call torch.cat, :1006).  The render loops call the
+    renderer once per view with the SAME scene tensors, so under no_grad the packed copy is cached for as long as the
+    two inputs are unmodified (same storage, shape and in-place version counter); with autograd the cat is part of the
+    graph and is done every time."""
+    if torch.is_grad_enabled() and (features_dc.requires_grad or features_rest.requires_grad):
+        return torch.cat([features_dc, features_rest], dim=1).contiguous()
+    key = (features_dc.data_ptr(), features_rest.data_ptr(), features_dc._version, features_rest._version,
+           tuple(features_dc.shape), tuple(features_rest.shape), features_dc.device)
+    hit = _SH_CACHE.get("last")
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    shs = torch.cat([features_dc, features_rest], dim=1).contiguous()
+    _SH_CACHE["last"] = (key, shs, features_dc, features_rest)      # the inputs are kept alive: their addresses stay theirs
+    return shs
+
+
 def _subpixel_offset(H, W, device):
     # The reference allocates zeros(H,W,2) per call (:954); no kernel reads it, so share one.
     key = (H, W, str(device))
@@ -158,7 +178,7 @@ def render_predicted_more_v2_gof(pc: dict, bs, world_view_transform, full_proj_t
     scales = pc["scaling"][bs]
     rotations = pc["rotation"][bs]
     if override_color is None:
-        shs = torch.cat([pc["features_dc"][bs], pc["features_rest"][bs]], dim=1).contiguous()
+        shs = _packed_sh(pc["features_dc"][bs], pc["features_rest"][bs])
         colors_precomp = None
     else:
         shs = None

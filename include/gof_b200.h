@@ -85,6 +85,12 @@ typedef struct GofParams {
  *   float32 reciprocal arithmetic (<= 4 ulp): rgb, median depth, alpha, T and the contributor
  *   counts stay bit-identical, normals and distortion agree to ~1e-6 (north-star bar: 1e-4). */
 #define GOF_FLAG_EXACT_BLEND 1
+/* GOF_FLAG_SAVE_CONTRIB (forward): the blend also records, per pixel, WHICH records of its tile list it blended (one
+ *   bit per list position, 32 bytes per duplicate in the binning blob).  A backward on that state then walks exactly
+ *   those pairs instead of re-running the conic sweep over the whole list and re-evaluating the survivors that did
+ *   not contribute.  Set it for forwards whose result will be differentiated (the Python layer does when an input
+ *   requires grad); the backward finds out from the state itself and works either way, with identical results. */
+#define GOF_FLAG_SAVE_CONTRIB 2
 
 /* Per-Gaussian inputs + camera (argument list of Rasterizer::forward). */
 typedef struct GofInputs {

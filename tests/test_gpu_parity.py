@@ -142,10 +142,15 @@ def rel_l2(a, b):
 
 
 @needs_ref
+@pytest.mark.parametrize("pass1", ["sweep", "masks"])
 @pytest.mark.parametrize("name", BWD_CASES)
-def test_backward(name):
+def test_backward(name, pass1, monkeypatch):
+    """pass1 = how the backward blend finds each pixel's contributors: "sweep" re-runs the conic sweep over the tile
+    list (a forward without GOF_FLAG_SAVE_CONTRIB, e.g. inference state), "masks" reads the per-pixel contributor
+    masks a training forward leaves behind.  Same bars either way."""
     import oracle_cpu
     from f3d_gaus_b200.diff_gof_rasterization import preprocess_backward_stage
+    monkeypatch.setenv("GOF_SAVE_CONTRIB", "1" if pass1 == "masks" else "0")
     c = FWD_CASES[name]("cuda")
     dL = cases.grad_seed(c)
     refs = []
@@ -288,3 +293,20 @@ def test_mark_visible_bit_exact():
         vis = both(world, vm, c["projmatrix"])
         assert 0.2 < float(vis.float().mean()) < 0.8                          # the slab really straddles the threshold
         both(c["means3D"], vm, c["projmatrix"])
+
+
+@pytest.mark.parametrize("name", ["f3d_s256_r256_view2", "unit_p20000_sh3_bg", "f3d_s256_r512_view2"])
+def test_backward_masks_equal_sweep(name, monkeypatch):
+    """The two pass-1 variants of the backward blend walk the same (pixel, record) pairs with the same arithmetic: their
+    gradients differ only by the order of the float reductions; a forward with masks renders the identical image."""
+    c = FWD_CASES[name]("cuda")
+    dL = cases.grad_seed(c)
+    outs, imgs = {}, {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("GOF_SAVE_CONTRIB", mode)
+        o = refgpu.OursRun()
+        imgs[mode] = o.forward(c, decode_state=False)["out_color"]
+        outs[mode] = o.backward(c, dL)
+    assert torch.equal(imgs["0"].view(torch.int32), imgs["1"].view(torch.int32))
+    for k in BLEND_GRADS:
+        assert rel_l2(outs["1"][k], outs["0"][k]) <= 2e-6, (k, rel_l2(outs["1"][k], outs["0"][k]))
