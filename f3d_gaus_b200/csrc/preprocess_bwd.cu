@@ -240,7 +240,10 @@ __device__ V3 sh_backward(int deg, int M, const V3 pos, const V3 campos, const f
 
 // One thread per Gaussian; loops over the V views of a batch and SUMS their gradients (V = 1: the reference's
 // per-frame backward).  Per view: gacc[v], radii[v], clamped[v], viewmatrix[v], campos[v].
-__global__ void __launch_bounds__(256)
+// 128 threads per CTA: the double-precision quadric chain needs ~220 registers per thread, so a 256-thread CTA would
+// be alone on its SM; 128-thread CTAs sit two per SM and spread 65,536 Gaussians over 512 CTAs instead of 256.
+constexpr int PRE_BWD_THREADS = 128;
+__global__ void __launch_bounds__(PRE_BWD_THREADS)
 preprocess_bwd_kernel(int P, int V, int D, int M, const float* __restrict__ means3D, const int* __restrict__ radii_all,
                       const float* __restrict__ shs, const uint8_t* __restrict__ clamped_all,
                       const float* __restrict__ scales, const float* __restrict__ rotations,
@@ -328,7 +331,7 @@ int launch_preprocess_bwd(const GofParams& prm, const GofInputs& in, int V, cons
                           cudaStream_t s)
 {
 	const int P = prm.P;
-	GOF_CUDA_CHECK(launch_chained(PDL_PRE_BWD, preprocess_bwd_kernel, dim3((P + 255) / 256), dim3(256), 0, s, P, V, prm.D, prm.M, in.means3D, radii,
+	GOF_CUDA_CHECK(launch_chained(PDL_PRE_BWD, preprocess_bwd_kernel, dim3((P + PRE_BWD_THREADS - 1) / PRE_BWD_THREADS), dim3(PRE_BWD_THREADS), 0, s, P, V, prm.D, prm.M, in.means3D, radii,
 		in.shs, g.clamped, in.scales, in.rotations, in.viewmatrix, in.campos, gacc, grads.dL_dmeans2D, grads.dL_dcolors,
 		grads.dL_dopacity, grads.dL_dmeans3D, grads.dL_dcov3D, grads.dL_dsh, grads.dL_dscales,
 		grads.dL_drotations, grads.dL_dview2gaussian));

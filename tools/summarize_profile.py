@@ -2,7 +2,7 @@
 """Turn one GPU-box visit (gpurun_out/<tag>/, written by tools/gpu_round.sh) into the tracked
 summaries under profiles/:  <round>_launches.md (per-kernel share of a bench step from the ncu launch
 list), <round>_blend_ncu.md (key `ncu --set full` metrics of the blend kernels) and
-render_fwd_traffic.json (dram bytes per forward-blend launch, read by bench.py).
+kernel_traffic.json (dram bytes per launch + issue-side figures of the blend kernels, read by bench.py).
 
     python tools/summarize_profile.py gpurun_out/s3a r01
 """
@@ -57,7 +57,7 @@ def launches(src, out_md, title):
     return agg
 
 
-def full(rep, out_md, title, traffic_json=None, traffic_kernel="render_fwd"):
+def full(rep, out_md, title, traffic_json=None, traffic_kernel="render_fwd", traffic_workload="nvs256", traffic_what=""):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
@@ -81,14 +81,19 @@ def full(rep, out_md, title, traffic_json=None, traffic_kernel="render_fwd"):
             def metric(name):
                 sel = [float(r[hdr.index(name)].replace(",", "")) for r, n in zip(rows[2:], names) if traffic_kernel in n]
                 return sum(sel) / len(sel) if (name in hdr and sel) else None
+            try:
+                with open(traffic_json) as f:
+                    table = json.load(f)
+            except Exception:
+                table = {}
+            table[traffic_kernel + "_kernel"] = {
+                "dram_bytes_per_launch": sum(vals) / len(vals), "launches": len(vals), "source": os.path.relpath(rep, ROOT),
+                "issue_active_pct": metric("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "active_lanes_per_instruction": metric("smsp__thread_inst_executed_per_inst_executed.ratio"),
+                "warp_instructions": metric("smsp__inst_executed.sum"), "workload": traffic_workload,
+                "what": traffic_what}
             with open(traffic_json, "w") as f:
-                json.dump({"kernel": traffic_kernel, "dram_bytes_per_launch": sum(vals) / len(vals),
-                           "launches": len(vals), "source": os.path.relpath(rep, ROOT),
-                           "issue_active_pct": metric("smsp__issue_active.avg.pct_of_peak_sustained_active"),
-                           "active_lanes_per_instruction": metric("smsp__thread_inst_executed_per_inst_executed.ratio"),
-                           "warp_instructions": metric("smsp__inst_executed.sum"),
-                           "workload": "bench.py step: one launch blends 8 views of 65536 f3d-like Gaussians, 256x256"},
-                          f, indent=1)
+                json.dump(table, f, indent=1)
 
 
 def main():
@@ -101,13 +106,18 @@ def main():
     rep = os.path.join(src, "prof_blend.ncu-rep")
     if os.path.exists(rep):
         full(rep, os.path.join(prof, f"{tag}_blend_ncu.md"),
-             f"{tag}: ncu --set full, blend kernels (65,536 Gaussians, 256x256)",
-             os.path.join(prof, "render_fwd_traffic.json"))
-    for stem, what in (("prof_bwd", "backward blend (65,536 Gaussians, 256x256, one view)"),
-                       ("prof_head", "predictor output head (64 images of 256x256, 23 channels)")):
-        rep = os.path.join(src, stem + ".ncu-rep")
-        if os.path.exists(rep):
-            full(rep, os.path.join(prof, f"{tag}_{stem[5:]}_ncu.md"), f"{tag}: ncu --set full, {what}")
+             f"{tag}: ncu --set full, forward pipeline of one bench step (8 views of 65,536 Gaussians, 256x256)",
+             os.path.join(prof, "kernel_traffic.json"), "render_fwd", "nvs256",
+             "bench.py nvs256 step: one launch blends 8 views of 65536 f3d-like Gaussians, 256x256")
+    rep = os.path.join(src, "prof_bwd.ncu-rep")
+    if os.path.exists(rep):
+        full(rep, os.path.join(prof, f"{tag}_bwd_ncu.md"),
+             f"{tag}: ncu --set full, backward blend of one train256 step (8 views of 65,536 Gaussians, 256x256)",
+             os.path.join(prof, "kernel_traffic.json"), "render_bwd", "train256",
+             "bench.py train256 step: one launch walks back the 8 views of 65536 f3d-like Gaussians, 256x256")
+    rep = os.path.join(src, "prof_head.ncu-rep")
+    if os.path.exists(rep):
+        full(rep, os.path.join(prof, f"{tag}_head_ncu.md"), f"{tag}: ncu --set full, predictor output head (64 images of 256x256, 23 channels)")
     for name in ("bench_ours.json", "bench_reference.json", "quick_bench.log", "head_bench.json", "train_bench.json"):
         p = os.path.join(src, name)
         if os.path.exists(p):
