@@ -50,8 +50,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 VIEWS = 8
 P_SIDE = 256            # 256*256 = 65,536 Gaussians
 L2_FLUSH_BYTES = 256 << 20
-MIN_TIMED_STEPS = {"nvs256": 200, "train256": 50, "cycle3": 20, "batch512": 10}    # floor of timed steps per workload
-OTHER_STEPS = {"train256": 50, "cycle3": 20, "batch512": 10}
+MIN_TIMED_STEPS = {"nvs256": 400, "train256": 100, "cycle3": 40, "batch512": 20}    # floor of timed steps per workload
+OTHER_STEPS = {"train256": 100, "cycle3": 40, "batch512": 20}
 WORKLOADS = ("nvs256", "train256", "cycle3", "batch512")
 FOV = 13.164
 

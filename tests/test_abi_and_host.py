@@ -158,3 +158,35 @@ def test_ctypes_structs_match_the_header(tmp_path):
         cls = structs[name]
         assert ctypes.sizeof(cls) == int(size), name
         assert [getattr(cls, f).offset for f, _ in cls._fields_] == [int(o) for o in offsets], name
+
+
+def test_bench_workloads_and_formulas():
+    """bench.py imports without a GPU and names the four BASELINE configs; the algorithmic-byte formulas are SURVEY.md 8(d)'s."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_module", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert set(bench.WORKLOAD_CLASSES) == set(bench.WORKLOADS) == {"nvs256", "train256", "cycle3", "batch512"}
+    assert all(bench.MIN_TIMED_STEPS[w] >= 10 for w in bench.WORKLOADS)
+    P, R, W, H = 65536, 186000, 256, 256
+    assert bench.bytes_render_fwd(P, R, W, H) == 8 * 256 + 60 * R + 12 * P + 60 * W * H          # ~15.9 MB @ configs[1]
+    assert bench.bytes_render_bwd(P, R, W, H) == 8 * 256 + 80 * R + 60 * W * H + 68 * P
+    assert abs(bench.bytes_render_fwd(P, R, W, H) / 1e6 - 15.9) < 0.1
+    assert bench.Batch512.frames_per_step == 64 and bench.Cycle3.frames_per_step == 10
+    peak, src = bench.measured_peak_gbs()
+    assert 5000 < peak < 9000 and ("measured" in src or "fallback" in src)
+
+
+def test_save_contrib_flag_follows_requires_grad(monkeypatch):
+    """The Python layer asks the forward for contributor masks exactly when a differentiable input is passed."""
+    from f3d_gaus_b200 import _lib
+    monkeypatch.delenv("GOF_SAVE_CONTRIB", raising=False)
+    monkeypatch.delenv("GOF_EXACT_BLEND", raising=False)
+    a, b = torch.zeros(3), torch.zeros(3, requires_grad=True)
+    assert _lib.default_flags(a, None) == 0
+    assert _lib.default_flags(a, b) == _lib.FLAG_SAVE_CONTRIB
+    monkeypatch.setenv("GOF_SAVE_CONTRIB", "0")
+    assert _lib.default_flags(a, b) == 0
+    monkeypatch.setenv("GOF_SAVE_CONTRIB", "1")
+    monkeypatch.setenv("GOF_EXACT_BLEND", "1")
+    assert _lib.default_flags(a) == (_lib.FLAG_SAVE_CONTRIB | _lib.FLAG_EXACT_BLEND)
