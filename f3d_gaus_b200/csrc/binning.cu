@@ -93,7 +93,7 @@ tile_scan_kernel(int VT, int T, int V, const uint32_t* __restrict__ counts, uint
 {
 	__shared__ uint32_t s_part[SCAN_THREADS];
 	__shared__ uint32_t s_max[SCAN_THREADS / 32];
-	__shared__ uint32_t s_bucket[64], s_bmax;
+	__shared__ uint32_t s_bucket[SCAN_THREADS], s_bmax;
 	pdl_trigger();
 	pdl_wait();                    // the tile counts come from the preprocess
 	const int tid = threadIdx.x;
@@ -141,25 +141,45 @@ tile_scan_kernel(int VT, int T, int V, const uint32_t* __restrict__ counts, uint
 	}
 	__syncthreads();
 	if (order != nullptr) {
-		// Launch order of the blend CTAs: longest tile lists first (64 length classes, counting sort), so that the
-		// last wave of a launch is made of short tiles instead of whatever the row-major order leaves.
+		// Launch order of the blend CTAs: longest tile lists first (counting sort over 1024 length classes, one per
+		// thread), so that the last wave of a launch is made of short tiles instead of whatever the row-major order leaves.
 		if (tid == 0) {
 			uint32_t m = 0;
 			for (int k = 0; k < SCAN_THREADS / 32; k++) m = max(m, s_max[k]);
 			s_bmax = m;
 		}
-		if (tid < 64) s_bucket[tid] = 0;
+		s_bucket[tid] = 0;
 		__syncthreads();
-		const uint32_t bm = s_bmax + 1;
-		for (int i = lo; i < hi; i++) atomicAdd(&s_bucket[63 - min(63u, (uint32_t)(((unsigned long long)counts[i] * 64) / bm))], 1u);
+		const float scale = (float)SCAN_THREADS / (float)(s_bmax + 1u);      // class = floor(count * scale), monotone in count
+		auto bucket_of = [&](uint32_t c) { return (uint32_t)(SCAN_THREADS - 1) - min((uint32_t)(SCAN_THREADS - 1), (uint32_t)((float)c * scale)); };
+		for (int i = lo; i < hi; i++) atomicAdd(&s_bucket[bucket_of(counts[i])], 1u);
 		__syncthreads();
-		if (tid == 0) {
-			uint32_t run2 = 0;
-			for (int k = 0; k < 64; k++) { const uint32_t c = s_bucket[k]; s_bucket[k] = run2; run2 += c; }
+		{	// exclusive scan of the class sizes (same two-level shuffle scan as above)
+			const int lane = tid & 31, wid = tid >> 5;
+			const uint32_t mine = s_bucket[tid];
+			uint32_t v = mine;
+#pragma unroll
+			for (int off = 1; off < 32; off <<= 1) {
+				const uint32_t u = __shfl_up_sync(0xffffffffu, v, off);
+				if (lane >= off) v += u;
+			}
+			__shared__ uint32_t s_bsum[SCAN_THREADS / 32];
+			if (lane == 31) s_bsum[wid] = v;
+			__syncthreads();
+			if (wid == 0) {
+				uint32_t t = s_bsum[lane];
+#pragma unroll
+				for (int off = 1; off < 32; off <<= 1) {
+					const uint32_t u = __shfl_up_sync(0xffffffffu, t, off);
+					if (lane >= off) t += u;
+				}
+				s_bsum[lane] = t;
+			}
+			__syncthreads();
+			s_bucket[tid] = v - mine + (wid ? s_bsum[wid - 1] : 0u);
 		}
 		__syncthreads();
-		for (int i = lo; i < hi; i++)
-			order[atomicAdd(&s_bucket[63 - min(63u, (uint32_t)(((unsigned long long)counts[i] * 64) / bm))], 1u)] = (uint32_t)i;
+		for (int i = lo; i < hi; i++) order[atomicAdd(&s_bucket[bucket_of(counts[i])], 1u)] = (uint32_t)i;
 		__syncthreads();
 	}
 	if (tid == 0) {
