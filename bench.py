@@ -801,7 +801,8 @@ def measure(wl: Workload, timer: Timer, K: int, local: int, sample_clocks: bool)
                       "readback": getattr(wl, "readback", None),
                       "what": "K scenes streamed from pinned host buffers to pinned host frames, 2 in flight: H2D of scene "
                               "k+1 (copy stream) | render k | frames of k-1 to host; host clock over the whole K-step region, "
-                              "every step's copies inside it; the host is the consumer, so no GPU-to-GPU gather"}
+                              "every step's copies inside it (no artificial L2 flush: each scene's inputs arrive fresh from the host); "
+                              "the host is the consumer, so no GPU-to-GPU gather"}
 
     # roofline of the dominant kernel
     launches = wl.roofline_launches()
