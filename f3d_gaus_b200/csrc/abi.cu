@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <atomic>
 #include <vector>
 
 namespace gof {
@@ -36,7 +37,9 @@ void set_error(const char* fmt, ...)
 
 struct GofContext {
 	int device = 0;
-	int32_t* pinned = nullptr;      // host mailbox for num_rendered (callback mode)
+	int32_t* pinned = nullptr;      // host mailbox for num_rendered (callback mode): MAILBOX_HEAD + GOF_MAX_VIEWS ints + a sequence word
+	int32_t* pinned_dev = nullptr;  // the same memory in the device's address space (the tile scan writes it directly)
+	int32_t handoff_seq = 0;        // sequence number of the last direct hand-off
 	float* gacc = nullptr;          // backward gradient accumulator, grown on demand
 	size_t gacc_floats = 0;
 	size_t gacc_used = 0;           // floats written by the last backward (P * V * GACC_FLOATS)
@@ -82,8 +85,10 @@ int gof_context_create(int device, GofContext** out)
 	GOF_CUDA_CHECK(cudaSetDevice(device));
 	GofContext* c = new GofContext();
 	c->device = device;
-	cudaError_t e = cudaMallocHost(&c->pinned, (MAILBOX_HEAD + GOF_MAX_VIEWS) * sizeof(int32_t));
-	if (e != cudaSuccess) { delete c; set_error("cudaMallocHost failed: %s", cudaGetErrorString(e)); return GOF_ECUDA; }
+	cudaError_t e = cudaHostAlloc(&c->pinned, (MAILBOX_HEAD + GOF_MAX_VIEWS + 1) * sizeof(int32_t), cudaHostAllocMapped);
+	if (e != cudaSuccess) { delete c; set_error("cudaHostAlloc failed: %s", cudaGetErrorString(e)); return GOF_ECUDA; }
+	memset(c->pinned, 0, (MAILBOX_HEAD + GOF_MAX_VIEWS + 1) * sizeof(int32_t));
+	if (cudaHostGetDevicePointer(&c->pinned_dev, c->pinned, 0) != cudaSuccess) { c->pinned_dev = nullptr; cudaGetLastError(); }   // fall back to a copy
 	*out = c;
 	return GOF_OK;
 }
@@ -302,16 +307,40 @@ int gof_forward_batch(GofContext* ctx, const GofParams* prm, const GofInputs* in
 			if (!blob) { set_error("gof_forward: binning allocation callback returned NULL for %zu bytes", need); return GOF_ENOMEM; }
 			capacity = blob_capacity(blob, need, VT);      // the layout every later call derives from (blob, need)
 			b = BinState::carve(align_base(blob), (size_t)capacity, VT);
-			if ((rc = launch_tile_scan(f, g, im, capacity, s, save_contrib)) != GOF_OK) return rc;
+			// num_rendered reaches the host without a copy in the stream (a copy between the scan and the scatter costs
+			// ~10 us of GPU time per frame and breaks their programmatic dependency): the scan stores the mailbox into
+			// mapped pinned memory and releases a sequence number behind it, the host polls that word.
+			const bool direct = ctx->pinned_dev != nullptr && !ctx->profiling;
+			const int32_t seq = ++ctx->handoff_seq;
+			if ((rc = launch_tile_scan(f, g, im, capacity, s, save_contrib, direct ? ctx->pinned_dev : nullptr, seq)) != GOF_OK) return rc;
 			GOF_PROF_MARK(ctx, marks, s);
-			GOF_CUDA_CHECK(cudaMemcpyAsync(ctx->pinned, g.mailbox, (MAILBOX_HEAD + V) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-			GOF_CUDA_CHECK(cudaEventRecord(ctx->handoff, s));
+			if (!direct) {
+				GOF_CUDA_CHECK(cudaMemcpyAsync(ctx->pinned, g.mailbox, (MAILBOX_HEAD + V) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+				GOF_CUDA_CHECK(cudaEventRecord(ctx->handoff, s));
+			}
 			GOF_PROF_MARK(ctx, marks, s);
 			if ((rc = launch_binning(f, g, im, b, capacity, s, 0.0f, save_contrib)) != GOF_OK) return rc;
 			GOF_PROF_MARK(ctx, marks, s);
 			if ((rc = launch_render_fwd(*prm, f, g, im, b, in->background, bg_stride, out_color, sink, sink_hwc, s)) != GOF_OK) return rc;
 			GOF_PROF_MARK(ctx, marks, s);
-			GOF_CUDA_CHECK(cudaEventSynchronize(ctx->handoff));
+			if (direct) {
+				// the event (behind every kernel of the call) only ends the wait if the scan never ran (a failed launch)
+				GOF_CUDA_CHECK(cudaEventRecord(ctx->handoff, s));
+				volatile int32_t* seq_word = ctx->pinned + MAILBOX_HEAD + GOF_MAX_VIEWS;
+				for (uint32_t spins = 1; *seq_word != seq; spins++) {
+					if ((spins & 0x3ffu) == 0) {
+						const cudaError_t q = cudaEventQuery(ctx->handoff);
+						if (q == cudaErrorNotReady) continue;
+						if (q != cudaSuccess || *seq_word != seq) {
+							set_error("gof_forward: the tile scan did not deliver num_rendered (%s)", cudaGetErrorString(q == cudaSuccess ? cudaGetLastError() : q));
+							return GOF_ECUDA;
+						}
+					}
+				}
+				std::atomic_thread_fence(std::memory_order_acquire);
+			} else {
+				GOF_CUDA_CHECK(cudaEventSynchronize(ctx->handoff));
+			}
 			const int64_t R = ctx->pinned[0];
 			ctx->spec_capacity = R + R / 4 + 4096;
 			if (!ctx->pinned[1]) {

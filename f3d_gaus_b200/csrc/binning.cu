@@ -89,7 +89,7 @@ constexpr int SCAN_THREADS = 1024;
 __global__ void __launch_bounds__(SCAN_THREADS)
 tile_scan_kernel(int VT, int T, int V, const uint32_t* __restrict__ counts, uint2* __restrict__ ranges,
                  uint32_t* __restrict__ cursor, int32_t* __restrict__ mailbox, long long capacity,
-                 uint32_t* __restrict__ order, int save_contrib)
+                 uint32_t* __restrict__ order, int save_contrib, volatile int32_t* host_mail, int32_t host_seq)
 {
 	__shared__ uint32_t s_part[SCAN_THREADS];
 	__shared__ uint32_t s_max[SCAN_THREADS / 32];
@@ -140,6 +140,33 @@ tile_scan_kernel(int VT, int T, int V, const uint32_t* __restrict__ counts, uint
 		if ((i + 1) % T == 0) mailbox[MAILBOX_HEAD + i / T] = (int32_t)run;   // inclusive prefix; differenced below
 	}
 	__syncthreads();
+	if (tid == 0) {
+		const uint32_t total = s_part[SCAN_THREADS - 1];
+		uint32_t m = 0;
+		for (int k = 0; k < SCAN_THREADS / 32; k++) m = max(m, s_max[k]);
+		const int32_t over = ((long long)total > capacity) ? 1 : 0;
+		mailbox[0] = (int32_t)total;
+		mailbox[1] = over;
+		mailbox[2] = (int32_t)m;
+		mailbox[3] = save_contrib;
+		int32_t prev = 0;
+		for (int v = 0; v < V; v++) {   // per-view R from the inclusive prefixes written above
+			const int32_t inc = mailbox[MAILBOX_HEAD + v];
+			mailbox[MAILBOX_HEAD + v] = inc - prev;
+			if (host_mail) host_mail[MAILBOX_HEAD + v] = inc - prev;
+			prev = inc;
+		}
+		if (host_mail) {
+			// num_rendered hand-off without a copy in the stream: the mailbox goes straight to mapped pinned host memory
+			// (posted PCIe writes) and the sequence number is released behind it; the host polls the sequence word.
+			host_mail[0] = (int32_t)total;
+			host_mail[1] = over;
+			host_mail[2] = (int32_t)m;
+			host_mail[3] = save_contrib;
+			__threadfence_system();
+			host_mail[MAILBOX_HEAD + GOF_MAX_VIEWS] = host_seq;
+		}
+	}
 	if (order != nullptr) {
 		// Launch order of the blend CTAs: longest tile lists first (counting sort over 1024 length classes, one per
 		// thread), so that the last wave of a launch is made of short tiles instead of whatever the row-major order leaves.
@@ -181,21 +208,6 @@ tile_scan_kernel(int VT, int T, int V, const uint32_t* __restrict__ counts, uint
 		__syncthreads();
 		for (int i = lo; i < hi; i++) order[atomicAdd(&s_bucket[bucket_of(counts[i])], 1u)] = (uint32_t)i;
 		__syncthreads();
-	}
-	if (tid == 0) {
-		const uint32_t total = s_part[SCAN_THREADS - 1];
-		uint32_t m = 0;
-		for (int k = 0; k < SCAN_THREADS / 32; k++) m = max(m, s_max[k]);
-		mailbox[0] = (int32_t)total;
-		mailbox[1] = ((long long)total > capacity) ? 1 : 0;
-		mailbox[2] = (int32_t)m;
-		mailbox[3] = save_contrib;
-		int32_t prev = 0;
-		for (int v = 0; v < V; v++) {   // per-view R from the inclusive prefixes written above
-			const int32_t inc = mailbox[MAILBOX_HEAD + v];
-			mailbox[MAILBOX_HEAD + v] = inc - prev;
-			prev = inc;
-		}
 	}
 }
 
@@ -475,17 +487,19 @@ extract_offsets_kernel(int P, const uint32_t* __restrict__ tiles_touched, uint32
 
 }  // namespace
 
-int launch_tile_scan(const Frame& f, const GeomState& g, const ImgState& im, int64_t capacity, cudaStream_t s, int save_contrib)
+int launch_tile_scan(const Frame& f, const GeomState& g, const ImgState& im, int64_t capacity, cudaStream_t s, int save_contrib,
+                     int32_t* host_mail, int32_t host_seq)
 {
 	GOF_CUDA_CHECK(launch_chained(PDL_SCAN, tile_scan_kernel, dim3(1), dim3(SCAN_THREADS), 0, s, f.V * f.T, f.T, f.V, im.tile_counts, im.ranges,
-	                              im.tile_cursor, g.mailbox, (long long)capacity, im.tile_order, save_contrib));
+	                              im.tile_cursor, g.mailbox, (long long)capacity, im.tile_order, save_contrib,
+	                              (volatile int32_t*)host_mail, host_seq));
 	return GOF_OK;
 }
 
 int launch_tile_scan_raw(int T, const uint32_t* counts, uint2* ranges, uint32_t* cursor, int32_t* mailbox, cudaStream_t s)
 {
 	GOF_CUDA_CHECK(launch_chained(PDL_SCAN, tile_scan_kernel, dim3(1), dim3(SCAN_THREADS), 0, s, T, T, 1, counts, ranges, cursor, mailbox,
-	                              (long long)1 << 40, (uint32_t*)nullptr, 0));
+	                              (long long)1 << 40, (uint32_t*)nullptr, 0, (volatile int32_t*)nullptr, 0));
 	return GOF_OK;
 }
 

@@ -140,7 +140,8 @@ struct Frame {
 int launch_preprocess(const GofParams& prm, const GofInputs& in, const Frame& f, const GeomState& g,
                       const ImgState& im, int32_t* radii, cudaStream_t s);
 // save_contrib: recorded in mailbox[3] -- tells the backward that the forward left per-pixel contributor masks
-int launch_tile_scan(const Frame& f, const GeomState& g, const ImgState& im, int64_t capacity, cudaStream_t s, int save_contrib = 0);
+int launch_tile_scan(const Frame& f, const GeomState& g, const ImgState& im, int64_t capacity, cudaStream_t s, int save_contrib = 0,
+                     int32_t* host_mail = nullptr, int32_t host_seq = 0);   // host_mail: mapped pinned mailbox + sequence word
 // ray_pad: 0 for the blend (rays through pixel centres), 0.5 for point integration (conic.cuh)
 // for_backward: also write BinState::bwd_rec (a training forward, GOF_FLAG_SAVE_CONTRIB)
 int launch_binning(const Frame& f, const GeomState& g, const ImgState& im, const BinState& b, int64_t capacity,
