@@ -25,6 +25,7 @@
 //     modes.  With GOF_FLAG_EXACT_BLEND the depth mapping and the normal normalisation also use
 //     its IEEE double divide / double sqrt / float divides (all nine channels bit-identical);
 //     without it they use float32 reciprocal arithmetic (normals, distortion within ~1e-6).
+#include <cstdlib>
 #include "blend_math.cuh"
 #include "conic.cuh"
 
@@ -43,6 +44,10 @@ namespace {
 #endif
 #ifndef GOF_FWD_SWEEP_ILP
 #define GOF_FWD_SWEEP_ILP 4       // records per trip of the conic sweep (A/B on B200: 2: 392 us, 3: 385, 4: 387, 6: 391 per 8-view launch; one frame: 4 saves 4 us)
+#endif
+#ifndef GOF_FWD_SPLIT_MAX_TILES
+#define GOF_FWD_SPLIT_MAX_TILES 256 // launches of at most this many tiles take render_fwd_split_kernel (one 256^2 frame: 120 -> 106 us;
+                                   // one 512^2 frame, 1024 tiles: 243 us against 198 us, so not there)
 #endif
 #ifndef GOF_FWD_FOLD_W
 #define GOF_FWD_FOLD_W 1          // fast blend: normals / distortion accumulate with w = alpha*T formed once
@@ -133,10 +138,11 @@ constexpr int FWD_THREADS = TILE_PIX;                  // every warp blends; the
 // the window overwrites the rows of the chunk that left it); registers hold only the word being consumed (`cur`, the
 // bits not popped yet) and its index in the list (`p`).  Invariant ("normalised"): cur != 0 unless nothing is queued.
 constexpr int QUEUE_ROWS = 2 * NW;
-struct LaneQueue {
+template <int ROWS, int COLS>
+struct LaneQueueT {
 	uint32_t cur, p;
 	uint32_t col;                                   // shared-window address of this thread's column (row 0)
-	__device__ __forceinline__ uint32_t row(uint32_t w) const { return col + (w % QUEUE_ROWS) * (FWD_THREADS * 4); }
+	__device__ __forceinline__ uint32_t row(uint32_t w) const { return col + (w % ROWS) * (COLS * 4); }
 	__device__ __forceinline__ void store_chunk(int c, const uint32_t (&m)[NW]) const
 	{
 #pragma unroll
@@ -163,6 +169,7 @@ struct LaneQueue {
 		return true;
 	}
 };
+using LaneQueue = LaneQueueT<QUEUE_ROWS, FWD_THREADS>;
 
 // MASK: also record, per pixel, which records of the tile list were blended (GOF_FLAG_SAVE_CONTRIB): one bit per list
 // position, kept for the window's two chunks in shared memory ([chunk parity][word][thread], lane-private columns) and
@@ -479,6 +486,275 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 	}
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Small launches (the one-frame-per-call API): render_fwd_split_kernel.
+//
+// A launch of one 256^2 frame is 256 tiles on 148 SMs, and its time is the time of the longest tile's warps: every warp
+// walks the whole list alone -- conic sweep of chunk c+2, then the lane-private blend of chunks c, c+1 -- at ~0.2
+// instructions per cycle, while three quarters of the SM's issue slots idle (ncu, one frame: issue active 49 % on the
+// SMs that are busy, SMs busy 56 % of the launch).  The throughput kernel above has nothing to offer here; this variant
+// spends the idle issue slots on thread-level parallelism INSIDE a tile without touching the arithmetic:
+//   * a CTA owns HALF a tile (16x8 pixels = four 8x4 blocks), so a frame is 512 CTAs and the longest tile is spread over
+//     two SMs; each half streams the tile's slab through its own TMA ring (the second read comes from L2);
+//   * per 8x4 block TWO warps: a SWEEPER that runs the conic pre-test up to four chunks ahead and leaves the
+//     per-pixel survivor words in the shared-memory queue, and a BLENDER that only walks survivors (pass 2 of the
+//     kernel above, same code, same order, same roundings).  The sweep (~1/3 of the longest warp's path) leaves the
+//     critical path; the two meet through two monotonic counters in shared memory (chunks swept / chunks consumed).
+// Results are bit-identical to render_fwd_kernel (tests/test_gpu_batch.py compares one-frame calls with batched ones).
+constexpr int SPLIT_BLENDERS = 4;                       // 8x4 blocks per half tile
+constexpr int SPLIT_THREADS = 2 * SPLIT_BLENDERS * 32;  // 4 blender warps + 4 sweeper warps
+constexpr int SPLIT_PIX = SPLIT_BLENDERS * 32;          // 128 pixels per CTA
+constexpr int SPLIT_AHEAD = 4;                          // chunks of survivor words held per block (window of 2 + 2 swept ahead)
+constexpr int SPLIT_QROWS = SPLIT_AHEAD * NW;
+static_assert(SPLIT_AHEAD <= STAGES, "a swept chunk's records must still be in the ring when the blender reaches it");
+using SplitQueue = LaneQueueT<SPLIT_QROWS, SPLIT_PIX>;
+
+__device__ __forceinline__ uint32_t lds_volatile_u32(const uint32_t* p)
+{
+	uint32_t v;
+	asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+	return v;
+}
+__device__ __forceinline__ void sts_volatile_u32(uint32_t* p, uint32_t v)
+{
+	asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(SPLIT_THREADS, 3)
+render_fwd_split_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int T, int tiles_x,
+                        const float* __restrict__ slab, int W, int H,
+                        float focal_x, float focal_y, const float* __restrict__ bg_colors, int bg_stride,
+                        float* __restrict__ final_T_all, uint32_t* __restrict__ n_contrib_all, float* __restrict__ out_color_all,
+                        const int32_t* __restrict__ mailbox, const uint8_t* __restrict__ block_mask)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	uint64_t* s_full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * CHUNK * SLAB_BYTES);
+	uint32_t* s_released = reinterpret_cast<uint32_t*>(s_full + STAGES);      // per stage: blenders that have let go of it (monotonic)
+	uint32_t* s_swept = s_released + STAGES;                                   // per block: chunks whose survivor words are queued
+	uint32_t* s_consumed = s_swept + SPLIT_BLENDERS;                           // per block: chunks the blender has left behind
+	uint32_t* s_wdone = s_consumed + SPLIT_BLENDERS;                           // per block: every pixel saturated, nothing left to sweep
+	uint32_t* s_queue = s_wdone + SPLIT_BLENDERS;                              // [SPLIT_QROWS][128] survivor words
+
+	const int tid = threadIdx.x;
+	const int warp = tid >> 5, lane = tid & 31;
+	const bool sweeper = warp >= SPLIT_BLENDERS;
+	const int bw = warp & (SPLIT_BLENDERS - 1);
+	pdl_trigger();
+	pdl_wait();
+	const uint32_t gt = tile_order[blockIdx.x >> 1];       // the two halves of a tile are neighbours in launch order
+	const int half = (int)(blockIdx.x & 1u);
+	const int view = (int)(gt / (uint32_t)T);
+	const int tile = (int)(gt - (uint32_t)view * (uint32_t)T);
+	const int tile_y = tile / tiles_x, tile_x = tile - tile_y * tiles_x;
+	const size_t N = (size_t)W * H;
+
+	const uint2 range = ranges[gt];
+	const bool overflow = mailbox[1] != 0;                 // see render_fwd_kernel
+	const int n = overflow ? 0 : (int)(range.y - range.x);
+	const int nchunks = (n + CHUNK - 1) / CHUNK;
+	const float* tile_slab = slab + (size_t)range.x * SLAB_FLOATS;
+
+	auto request_chunk = [&](int c) {
+		const int s = c % STAGES;
+		const uint32_t bytes = (uint32_t)min(CHUNK, n - c * CHUNK) * SLAB_BYTES;
+		mbar_arrive_expect_tx(&s_full[s], bytes);
+		tma_bulk_g2s(smem_raw + (size_t)s * (CHUNK * SLAB_BYTES), tile_slab + (size_t)c * CHUNK * SLAB_FLOATS, bytes, &s_full[s]);
+	};
+	if (tid == 0) {
+#pragma unroll
+		for (int s = 0; s < STAGES; s++) { mbar_init(&s_full[s], 1); s_released[s] = 0; }
+#pragma unroll
+		for (int k = 0; k < SPLIT_BLENDERS; k++) { s_swept[k] = 0; s_consumed[k] = 0; s_wdone[k] = 0; }
+		mbar_fence_init();
+		for (int c = 0; c < min(STAGES, nchunks); c++) request_chunk(c);
+	}
+	__syncthreads();
+
+	const int blk = half * SPLIT_BLENDERS + bw;            // 8x4 block of the tile = bit of the records' block masks
+	const int lx = (blk & 1) * 8 + (lane & 7), ly = (blk >> 1) * 4 + (lane >> 3);
+	const uint32_t rec_base = smem_u32(smem_raw);
+	SplitQueue q;
+	q.cur = 0;
+	q.p = 0;
+	q.col = smem_u32(s_queue) + (uint32_t)(bw * 32 + lane) * 4u;
+
+	if (sweeper) {
+		// ---- conic sweep of chunk c (pass 1 of render_fwd_kernel) for this block's 32 pixels, up to SPLIT_AHEAD chunks
+		// in front of the blender's oldest chunk
+		const uint8_t* tile_bm = block_mask + range.x;
+		const float fx = (float)lx, fy = (float)ly;
+		for (int c = 0; c < nchunks; c++) {
+			while ((int)lds_volatile_u32(&s_consumed[bw]) + SPLIT_AHEAD <= c) __nanosleep(20);   // the rows of chunk c - AHEAD are free
+			if (lds_volatile_u32(&s_wdone[bw])) break;
+			const int s = c % STAGES;
+			const int cnt = min(CHUNK, n - c * CHUNK);
+			uint32_t bm[NW];
+			{
+				const uint8_t* p = tile_bm + c * CHUNK + lane;
+#pragma unroll
+				for (int k = 0; k < NW; k++) bm[k] = (32 * k + lane < cnt) ? (uint32_t)__ldg(p + 32 * k) : 0u;
+			}
+			mbar_wait(&s_full[s], (uint32_t)((c / STAGES) & 1));
+			uint32_t m[NW];
+#pragma unroll
+			for (int k = 0; k < NW; k++) m[k] = 0;
+			const uint32_t rec = rec_base + (uint32_t)s * (CHUNK * SLAB_BYTES);
+#pragma unroll
+			for (int w = 0; w < NW; w++) {
+				uint32_t rel = __ballot_sync(0xffffffffu, (bm[w] >> blk) & 1u);
+				uint32_t bits = 0;
+				const uint32_t rw = rec + (uint32_t)w * (32 * SLAB_BYTES);
+				while (rel != 0) {
+					int j[SWEEP_ILP];
+					j[0] = __ffs((int)rel) - 1;
+					rel &= rel - 1;
+#pragma unroll
+					for (int k = 1; k < SWEEP_ILP; k++) {
+						j[k] = rel ? __ffs((int)rel) - 1 : j[0];
+						rel &= rel - 1;
+					}
+					float4 a[SWEEP_ILP];
+					float2 b[SWEEP_ILP];
+#pragma unroll
+					for (int k = 0; k < SWEEP_ILP; k++) {
+						a[k] = lds128(rw + j[k] * SLAB_BYTES);
+						b[k] = lds64(rw + j[k] * SLAB_BYTES + 16);
+					}
+#pragma unroll
+					for (int k = 0; k < SWEEP_ILP; k++)
+						if (!conic_reject(a[k].x, a[k].y, a[k].z, a[k].w, b[k].x, b[k].y, fx, fy)) bits |= 1u << j[k];
+				}
+				m[w] = bits;
+			}
+			q.store_chunk(c, m);
+			__syncwarp();
+			if (lane == 0) {
+				__threadfence_block();
+				sts_volatile_u32(&s_swept[bw], (uint32_t)(c + 1));
+			}
+		}
+		__syncwarp();
+		if (lane == 0) {
+			__threadfence_block();
+			sts_volatile_u32(&s_swept[bw], (uint32_t)nchunks);          // (early exit: the blender only lets go of the stages)
+		}
+		return;
+	}
+
+	// -------------------- blender: pass 2 of render_fwd_kernel over the queued survivor words --------------------
+	const uint32_t px = tile_x * TILE_X + lx;
+	const uint32_t py = tile_y * TILE_Y + ly;
+	const bool inside = px < (uint32_t)W && py < (uint32_t)H;
+	const uint32_t pix_id = W * py + px;
+	const float rx = pixel_ray(px, W, focal_x);
+	const float ry = pixel_ray(py, H, focal_y);
+
+	PixState st;
+	st.T = 1.0f;
+#pragma unroll
+	for (int k = 0; k < 8; k++) st.C[k] = 0.0f;
+	st.dist1 = st.dist2 = st.distortion = 0.0f;
+	st.last_contributor = 0;
+	st.max_contributor = 0xFFFFFFFFu;
+	bool done = !inside;
+	if (__all_sync(0xffffffffu, done) && lane == 0) sts_volatile_u32(&s_wdone[bw], 1u);
+
+	auto release_stage = [&](int c) {
+		__syncwarp();
+		if (lane == 0) {
+			__threadfence_block();
+			const uint32_t before = atomicAdd(&s_released[c % STAGES], 1u);
+			if ((before % SPLIT_BLENDERS) == SPLIT_BLENDERS - 1 && c + STAGES < nchunks) {
+				__threadfence_block();
+				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+				request_chunk(c + STAGES);
+			}
+			sts_volatile_u32(&s_consumed[bw], (uint32_t)(c + 1));
+		}
+	};
+	// chunks [0, k) are swept and their records have landed (the blender observes the stage's barrier itself, so the
+	// TMA writes are ordered before its reads without relying on the sweeper's observation)
+	auto wait_chunk = [&](int c) {
+		while ((int)lds_volatile_u32(&s_swept[bw]) <= c) __nanosleep(20);
+		__threadfence_block();
+		mbar_wait(&s_full[c % STAGES], (uint32_t)((c / STAGES) & 1));
+	};
+	if (nchunks > 0) {
+		wait_chunk(0);
+		if (nchunks > 1) wait_chunk(1);
+		if (done) {                                    // pixel outside the image: never reads the queue
+			q.p = 0xffffff00u;
+		} else {
+			asm volatile("ld.shared.u32 %0, [%1];" : "=r"(q.cur) : "r"(q.row(0)) : "memory");
+			q.normalise((uint32_t)min(nchunks, 2) * NW);
+		}
+	}
+	constexpr uint32_t RING_MASK = STAGES * CHUNK - 1;
+	for (int ca = 0; ca < nchunks; ca++) {
+		const uint32_t p_end = (uint32_t)min(nchunks, ca + 2) * NW;
+		const uint32_t p_b = (uint32_t)(ca + 1) * NW;
+		while (__any_sync(0xffffffffu, q.pending_below(p_b))) {
+			uint32_t ja, jb;
+			if (!q.pop(ja, p_end)) continue;
+			const bool hb = q.pop(jb, p_end);
+			if (!hb) jb = ja;
+			const uint32_t ra = rec_base + (ja & RING_MASK) * SLAB_BYTES;
+			const uint32_t rb = rec_base + (jb & RING_MASK) * SLAB_BYTES;
+			const float4 a1 = lds128(ra + 16), a2 = lds128(ra + 32), a3 = lds128(ra + 48), a4 = lds128(ra + 64);
+			const float4 b1 = lds128(rb + 16), b2 = lds128(rb + 32), b3 = lds128(rb + 48), b4 = lds128(rb + 64);
+			const PairGeom ga = pair_geom(a1, a2, a3, rx, ry);
+			const PairGeom gb = pair_geom(b1, b2, b3, rx, ry);
+			float ta, alpha_a, tb, alpha_b;
+			const bool oka = pair_alpha_eval(ga, a4.x, a1.z, ta, alpha_a);
+			const bool okb = pair_alpha_eval(gb, b4.x, b1.z, tb, alpha_b) && hb;
+			bool saturated = false;
+			if (oka) saturated = blend_pair<EXACT>(st, ga, ta, alpha_a, make_float4(a4.y, a4.z, a4.w, 0.0f), ja + 1u);
+			if (okb && !saturated) saturated = blend_pair<EXACT>(st, gb, tb, alpha_b, make_float4(b4.y, b4.z, b4.w, 0.0f), jb + 1u);
+			if (saturated) {
+				done = true;
+				q.cur = 0;
+				q.p = 0xffffff00u;
+			}
+		}
+		release_stage(ca);
+		if (__all_sync(0xffffffffu, done)) {
+			if (lane == 0) sts_volatile_u32(&s_wdone[bw], 1u);
+		}
+		if (ca + 2 < nchunks) {
+			wait_chunk(ca + 2);
+			q.normalise((uint32_t)(ca + 3) * NW);
+		}
+	}
+
+	if (overflow) {
+		const float poison = __int_as_float(0x7fc00000);
+#pragma unroll
+		for (int k = 0; k < 8; k++) st.C[k] = poison;
+		st.distortion = poison;
+	}
+	if (inside) {
+		float* final_T = final_T_all + (size_t)view * 4 * N;
+		uint32_t* n_contrib = n_contrib_all + (size_t)view * 2 * N;
+		float* out_color = out_color_all + (size_t)view * OUT_CH * N;
+		const float* bg_color = bg_colors + (size_t)view * bg_stride;
+		const float T_ = st.T;
+		const float om = __fsub_rn(1.0f, T_);
+		const float dnorm = (float)((double)st.distortion / ((double)__fmul_rn(om, om) + 1e-7));
+		final_T[pix_id] = T_;
+		final_T[pix_id + N] = st.dist1;
+		final_T[pix_id + 2 * N] = st.dist2;
+		final_T[pix_id + 3 * N] = st.distortion;
+		n_contrib[pix_id] = st.last_contributor;
+		n_contrib[pix_id + N] = st.max_contributor;
+#pragma unroll
+		for (int ch = 0; ch < 3; ch++) out_color[ch * N + pix_id] = __fmaf_rn(T_, bg_color[ch], st.C[ch]);
+#pragma unroll
+		for (int ch = 3; ch < 8; ch++) out_color[ch * N + pix_id] = st.C[ch];
+		out_color[CH_DIST * N + pix_id] = dnorm;
+	}
+}
+
 }  // namespace
 
 int launch_render_fwd(const GofParams& prm, const Frame& f, const GeomState& g, const ImgState& im, const BinState& b,
@@ -496,6 +772,20 @@ int launch_render_fwd(const GofParams& prm, const Frame& f, const GeomState& g, 
 		               sink_hwc, b.contrib);
 	};
 	const bool exact = (prm.flags & GOF_FLAG_EXACT_BLEND) != 0;
+	// small launches (the one-frame-per-call API): the latency variant, two CTAs per tile (render_fwd_split_kernel)
+	static const int split_max = [] { const char* e = getenv("GOF_FWD_SPLIT_MAX_TILES"); return e ? atoi(e) : GOF_FWD_SPLIT_MAX_TILES; }();
+	if (!mask && !sink && (int)grid.x <= split_max) {
+		const size_t ssm = (size_t)STAGES * CHUNK * SLAB_BYTES + STAGES * sizeof(uint64_t) + (STAGES + 3 * SPLIT_BLENDERS) * sizeof(uint32_t) +
+		                   (size_t)SPLIT_QROWS * SPLIT_PIX * 4;
+		auto launch_split = [&](auto kernel) {
+			if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm) != cudaSuccess) return;
+			launch_chained(PDL_BLEND, kernel, dim3(grid.x * 2), dim3(SPLIT_THREADS), ssm, s, im.ranges, im.tile_order, f.T, (int)f.grid.x, b.slab,
+			               prm.W, prm.H, f.focal_x, f.focal_y, background, bg_stride, im.final_T, im.n_contrib, out_color, g.mailbox, b.block_mask);
+		};
+		if (exact) launch_split(render_fwd_split_kernel<true>); else launch_split(render_fwd_split_kernel<false>);
+		GOF_CUDA_CHECK(cudaGetLastError());
+		return GOF_OK;
+	}
 	if (mask) {
 		if (sink) { if (exact) launch(render_fwd_kernel<true, true, true>); else launch(render_fwd_kernel<false, true, true>); }
 		else      { if (exact) launch(render_fwd_kernel<true, false, true>); else launch(render_fwd_kernel<false, false, true>); }
