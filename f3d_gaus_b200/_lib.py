@@ -16,13 +16,20 @@ FLAG_EXACT_BLEND = 1
 FLAG_SAVE_CONTRIB = 2
 
 
+_environ_get = os.environ.get
+
+
 def default_flags(*differentiated) -> int:
     """Blend arithmetic mode: bit-exact contributing path iff GOF_EXACT_BLEND=1; FLAG_SAVE_CONTRIB when one of the
     tensors passed requires grad, i.e. a backward may follow this forward (see gof_b200.h; GOF_SAVE_CONTRIB=0/1 forces it)."""
-    flags = FLAG_EXACT_BLEND if os.environ.get("GOF_EXACT_BLEND", "0") not in ("0", "", "false") else 0
-    force = os.environ.get("GOF_SAVE_CONTRIB", "")
-    if force == "1" or (force != "0" and any(t is not None and getattr(t, "requires_grad", False) for t in differentiated)):
-        flags |= FLAG_SAVE_CONTRIB
+    flags = FLAG_EXACT_BLEND if _environ_get("GOF_EXACT_BLEND", "0") not in ("0", "", "false") else 0
+    force = _environ_get("GOF_SAVE_CONTRIB", "")
+    if force == "1":
+        return flags | FLAG_SAVE_CONTRIB
+    if force != "0":
+        for t in differentiated:
+            if t is not None and t.requires_grad:
+                return flags | FLAG_SAVE_CONTRIB
     return flags
 
 

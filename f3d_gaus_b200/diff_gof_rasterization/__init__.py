@@ -30,13 +30,35 @@ def _dev_ptr(t: torch.Tensor | None, device: torch.device, keep: list, dtype=tor
     (a tensor with numel()==0, RAST/diff_gof_rasterization/__init__.py:211-225)."""
     if t is None or t.numel() == 0:
         return None
-    if t.device != device:
-        raise RuntimeError(f"expected a tensor on {device}, got one on {t.device}")
-    if t.dtype != dtype:
+    if t.dtype is not dtype or not t.is_cuda or t.get_device() != device.index:
+        if t.device != device:
+            raise RuntimeError(f"expected a tensor on {device}, got one on {t.device}")
         raise RuntimeError(f"expected dtype {dtype}, got {t.dtype}")
-    t = t.contiguous()
-    keep.append(t)
+    if not t.is_contiguous():          # (the hot path hands over contiguous tensors: nothing to copy, nothing to keep alive)
+        t = t.contiguous()
+        keep.append(t)
     return t.data_ptr()
+
+
+class _on_device:
+    """`with torch.cuda.device(d)` for the hot path: nothing to do (and nothing to undo) when `d` is already current."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        self.idx = device.index
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if self.idx is None or cur == self.idx:
+            self.prev = -1
+        else:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev >= 0:
+            torch.cuda.set_device(self.prev)
+        return False
 
 
 _SIZES: dict = {}
@@ -100,7 +122,7 @@ class _CModule:
         P, H, W = int(means3D.size(0)), int(image_height), int(image_width)
         M = int(sh.size(1)) if (sh is not None and sh.numel() != 0 and sh.size(0) != 0) else 0
         keep: list = []
-        with torch.cuda.device(device):
+        with _on_device(device):
             stream = _lib.raw_stream(device)
             byte_opts = dict(dtype=torch.uint8, device=device)
             if P == 0:

@@ -24,7 +24,7 @@ import torch
 from .. import _lib
 from ..staging import PinnedScene  # noqa: F401  (public here; defined in a module that does not load the CUDA library)
 from ..diff_gof_rasterization import (BatchWorkspace, GaussianRasterizationSettings_GOF, GaussianRasterizer_GOF,
-                                     rasterize_views)
+                                     _absent, _on_device, rasterize_gaussians, rasterize_views)
 
 _EMPTY_OFFSET: dict = {}
 
@@ -37,7 +37,7 @@ def _epilogue_forward(raster, vm, V, W, H, FovX, FovY, want_normal=True, want_de
     dev = raster.device
     normal_world = torch.empty((V, 3, H, W), dtype=torch.float32, device=dev) if want_normal else None
     depth_normal = torch.empty((V, 3, H, W), dtype=torch.float32, device=dev) if want_depth_normal else None
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = _lib.lib.gof_render_epilogue_batch(raster.data_ptr(), vm.data_ptr(), V, W, H, ctypes.c_float(FovX),
                                                 ctypes.c_float(FovY),
                                                 normal_world.data_ptr() if want_normal else None,
@@ -78,13 +78,23 @@ class _FusedEpilogue(torch.autograd.Function):
 def fused_epilogue(rendered_image, world_view_transform, W, H, FovX, FovY):
     """normal_world[3,H,W], depth_normal[3,H,W] from out_color[9,H,W] in one kernel; differentiable w.r.t.
     `rendered_image` (the normal channels 3..5 and the median depth 6) when it carries a graph."""
-    vm = world_view_transform.reshape(1, 16).contiguous()
-    img = rendered_image.unsqueeze(0)
     if torch.is_grad_enabled() and rendered_image.requires_grad:
-        normal_world, depth_normal = _FusedEpilogue.apply(img, vm, W, H, FovX, FovY)
-    else:
-        normal_world, depth_normal = _epilogue_forward(img.contiguous(), vm, 1, W, H, FovX, FovY)
-    return normal_world[0], depth_normal[0]
+        vm = world_view_transform.reshape(1, 16).contiguous()
+        normal_world, depth_normal = _FusedEpilogue.apply(rendered_image.unsqueeze(0), vm, W, H, FovX, FovY)
+        return normal_world[0], depth_normal[0]
+    # inference: the single-frame entry point on the tensors as they are (no views, no reshapes on the per-frame path)
+    dev = rendered_image.device
+    img = rendered_image if rendered_image.is_contiguous() else rendered_image.contiguous()
+    vm = world_view_transform if world_view_transform.is_contiguous() else world_view_transform.contiguous()
+    if vm.numel() != 16 or vm.dtype is not torch.float32 or img.dtype is not torch.float32 or vm.device != dev:
+        raise RuntimeError("fused_epilogue: expected a float32 [9,H,W] frame and a 4x4 float32 view matrix on the same device")
+    normal_world = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+    depth_normal = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+    with _on_device(dev):
+        rc = _lib.lib.gof_render_epilogue(img.data_ptr(), vm.data_ptr(), W, H, FovX, FovY, normal_world.data_ptr(),
+                                          depth_normal.data_ptr(), _lib.raw_stream(dev))
+    _lib.check(rc, "gof_render_epilogue")
+    return normal_world, depth_normal
 
 
 def depth_to_normal(world_view_transform, image_width, image_height, FoVx, FoVy, depth):
@@ -172,20 +182,20 @@ def render_predicted_more_v2_gof(pc: dict, bs, world_view_transform, full_proj_t
         bg=bg_color, scale_modifier=scaling_modifier, viewmatrix=world_view_transform,
         projmatrix=full_proj_transform, sh_degree=cfg['model']['max_sh_degree'], campos=camera_center,
         prefiltered=False, debug=False)
-    rasterizer = GaussianRasterizer_GOF(raster_settings=raster_settings)
-
     opacity = pc["opacity"][bs]
     scales = pc["scaling"][bs]
     rotations = pc["rotation"][bs]
+    absent = _absent()
     if override_color is None:
         shs = _packed_sh(pc["features_dc"][bs], pc["features_rest"][bs])
-        colors_precomp = None
+        colors_precomp = absent
     else:
-        shs = None
+        shs = absent
         colors_precomp = pc["rgbs"][bs]
-    rendered_image, radii = rasterizer(means3D=xyz, means2D=screenspace_points, shs=shs,
-                                       colors_precomp=colors_precomp, opacities=opacity, scales=scales,
-                                       rotations=rotations, cov3D_precomp=None, view2gaussian_precomp=None)
+    # GaussianRasterizer_GOF(raster_settings)(...) of the reference (:1023-1041) without building an nn.Module per frame:
+    # its forward is this one call (the argument combination is fixed here, so there is nothing to validate)
+    rendered_image, radii = rasterize_gaussians(xyz, screenspace_points, shs, colors_precomp, opacity, scales, rotations,
+                                                absent, absent, raster_settings)
 
     normal_world, depth_normal = fused_epilogue(rendered_image, world_view_transform, image_width, image_height,
                                                 FovX, FovY)
