@@ -773,7 +773,8 @@ int launch_render_fwd(const GofParams& prm, const Frame& f, const GeomState& g, 
 	};
 	const bool exact = (prm.flags & GOF_FLAG_EXACT_BLEND) != 0;
 	// small launches (the one-frame-per-call API): the latency variant, two CTAs per tile (render_fwd_split_kernel)
-	static const int split_max = [] { const char* e = getenv("GOF_FWD_SPLIT_MAX_TILES"); return e ? atoi(e) : GOF_FWD_SPLIT_MAX_TILES; }();
+	const char* split_env = getenv("GOF_FWD_SPLIT_MAX_TILES");       // read per launch: the tests switch between the two kernels
+	const int split_max = split_env ? atoi(split_env) : GOF_FWD_SPLIT_MAX_TILES;
 	if (!mask && !sink && (int)grid.x <= split_max) {
 		const size_t ssm = (size_t)STAGES * CHUNK * SLAB_BYTES + STAGES * sizeof(uint64_t) + (STAGES + 3 * SPLIT_BLENDERS) * sizeof(uint32_t) +
 		                   (size_t)SPLIT_QROWS * SPLIT_PIX * 4;
