@@ -46,8 +46,10 @@ namespace {
 #define GOF_FWD_SWEEP_ILP 4       // records per trip of the conic sweep (A/B on B200: 2: 392 us, 3: 385, 4: 387, 6: 391 per 8-view launch; one frame: 4 saves 4 us)
 #endif
 #ifndef GOF_FWD_SPLIT_MAX_TILES
-#define GOF_FWD_SPLIT_MAX_TILES 256 // launches of at most this many tiles take render_fwd_split_kernel (one 256^2 frame: 120 -> 106 us;
-                                   // one 512^2 frame, 1024 tiles: 243 us against 198 us, so not there)
+#define GOF_FWD_SPLIT_MAX_TILES 444 // launches of at most this many tiles take render_fwd_split_kernel: as long as the tile kernel's
+                                   // CTAs fit in ONE wave (148 SMs x 3) the launch is latency-bound.  Measured per frame, one-frame
+                                   // calls, tile / split kernel: 256^2 (256 tiles) 167 / 154 us, 320^2 (400) 168 / 160, 384^2 (576)
+                                   // 164 / 182, 448^2 (784) 176 / 209, 512^2 (1024) 198 / 243
 #endif
 #ifndef GOF_FWD_FOLD_W
 #define GOF_FWD_FOLD_W 1          // fast blend: normals / distortion accumulate with w = alpha*T formed once
@@ -501,12 +503,22 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 //     kernel above, same code, same order, same roundings).  The sweep (~1/3 of the longest warp's path) leaves the
 //     critical path; the two meet through two monotonic counters in shared memory (chunks swept / chunks consumed).
 // Results are bit-identical to render_fwd_kernel (tests/test_gpu_batch.py compares one-frame calls with batched ones).
-constexpr int SPLIT_BLENDERS = 4;                       // 8x4 blocks per half tile
-constexpr int SPLIT_THREADS = 2 * SPLIT_BLENDERS * 32;  // 4 blender warps + 4 sweeper warps
+constexpr int SPLIT_BLENDERS = 4;                       // 8x4 blocks per half tile, one blender warp each
+#ifndef GOF_SPLIT_SWEEPERS
+#define GOF_SPLIT_SWEEPERS 2
+#endif
+#ifndef GOF_SPLIT_MIN_CTAS
+#define GOF_SPLIT_MIN_CTAS 4
+#endif
+constexpr int SPLIT_SWEEPERS = GOF_SPLIT_SWEEPERS;      // sweeper warps, each serving two of the blocks (or one, with four sweepers)
+constexpr int SPLIT_THREADS = (SPLIT_BLENDERS + SPLIT_SWEEPERS) * 32;   // 192: four CTAs per SM, so that the 512 CTAs of one
+                                                        // 256^2 frame are resident at once (592 slots)
 constexpr int SPLIT_PIX = SPLIT_BLENDERS * 32;          // 128 pixels per CTA
 constexpr int SPLIT_AHEAD = 4;                          // chunks of survivor words held per block (window of 2 + 2 swept ahead)
 constexpr int SPLIT_QROWS = SPLIT_AHEAD * NW;
 static_assert(SPLIT_AHEAD <= STAGES, "a swept chunk's records must still be in the ring when the blender reaches it");
+constexpr int SPLIT_BLOCKS_PER_SWEEPER = SPLIT_BLENDERS / SPLIT_SWEEPERS;
+static_assert(SPLIT_BLOCKS_PER_SWEEPER == 1 || SPLIT_BLOCKS_PER_SWEEPER == 2, "a sweeper serves one or two blocks");
 using SplitQueue = LaneQueueT<SPLIT_QROWS, SPLIT_PIX>;
 
 __device__ __forceinline__ uint32_t lds_volatile_u32(const uint32_t* p)
@@ -521,7 +533,7 @@ __device__ __forceinline__ void sts_volatile_u32(uint32_t* p, uint32_t v)
 }
 
 template <bool EXACT>
-__global__ void __launch_bounds__(SPLIT_THREADS, 3)
+__global__ void __launch_bounds__(SPLIT_THREADS, GOF_SPLIT_MIN_CTAS)
 render_fwd_split_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int T, int tiles_x,
                         const float* __restrict__ slab, int W, int H,
                         float focal_x, float focal_y, const float* __restrict__ bg_colors, int bg_stride,
@@ -539,7 +551,7 @@ render_fwd_split_kernel(const uint2* __restrict__ ranges, const uint32_t* __rest
 	const int tid = threadIdx.x;
 	const int warp = tid >> 5, lane = tid & 31;
 	const bool sweeper = warp >= SPLIT_BLENDERS;
-	const int bw = warp & (SPLIT_BLENDERS - 1);
+	int bw = warp & (SPLIT_BLENDERS - 1);                  // blender: its block; sweeper: set per sweep
 	pdl_trigger();
 	pdl_wait();
 	const uint32_t gt = tile_order[blockIdx.x >> 1];       // the two halves of a tile are neighbours in launch order
@@ -571,22 +583,37 @@ render_fwd_split_kernel(const uint2* __restrict__ ranges, const uint32_t* __rest
 	}
 	__syncthreads();
 
-	const int blk = half * SPLIT_BLENDERS + bw;            // 8x4 block of the tile = bit of the records' block masks
-	const int lx = (blk & 1) * 8 + (lane & 7), ly = (blk >> 1) * 4 + (lane >> 3);
 	const uint32_t rec_base = smem_u32(smem_raw);
 	SplitQueue q;
 	q.cur = 0;
 	q.p = 0;
-	q.col = smem_u32(s_queue) + (uint32_t)(bw * 32 + lane) * 4u;
 
 	if (sweeper) {
-		// ---- conic sweep of chunk c (pass 1 of render_fwd_kernel) for this block's 32 pixels, up to SPLIT_AHEAD chunks
-		// in front of the blender's oldest chunk
+		// ---- conic sweep (pass 1 of render_fwd_kernel) for the 32 pixels of a block, up to SPLIT_AHEAD chunks in front
+		// of the block's blender.  A sweeper warp serves two blocks and always sweeps the one that is further behind.
 		const uint8_t* tile_bm = block_mask + range.x;
-		const float fx = (float)lx, fy = (float)ly;
-		for (int c = 0; c < nchunks; c++) {
-			while ((int)lds_volatile_u32(&s_consumed[bw]) + SPLIT_AHEAD <= c) __nanosleep(20);   // the rows of chunk c - AHEAD are free
-			if (lds_volatile_u32(&s_wdone[bw])) break;
+		const int b0 = SPLIT_BLOCKS_PER_SWEEPER * (warp - SPLIT_BLENDERS);
+		int nx0 = 0, nx1 = SPLIT_BLOCKS_PER_SWEEPER == 2 ? 0 : nchunks;                              // next chunk to sweep for blocks b0, b0 + 1
+		// block k of this sweeper: done -> nchunks; else its next chunk if the queue rows are free, -1 if not yet
+		auto eligible = [&](int k, int& nx) -> int {
+			if (nx >= nchunks) return -1;
+			if (lds_volatile_u32(&s_wdone[b0 + k])) {      // every pixel of the block is saturated: nothing left to sweep
+				nx = nchunks;
+				if (lane == 0) sts_volatile_u32(&s_swept[b0 + k], (uint32_t)nchunks);   // (the blender only lets go of the stages)
+				return -1;
+			}
+			// the rows of chunk c reuse those of chunk c - AHEAD: the blender must have left that one behind
+			return ((int)lds_volatile_u32(&s_consumed[b0 + k]) + SPLIT_AHEAD > nx) ? nx : -1;
+		};
+		while (nx0 < nchunks || nx1 < nchunks) {
+			const int e0 = eligible(0, nx0), e1 = eligible(1, nx1);
+			if (e0 < 0 && e1 < 0) { __nanosleep(20); continue; }
+			const int pick = (e0 >= 0 && (e1 < 0 || e0 <= e1)) ? 0 : 1;
+			bw = b0 + pick;
+			const int c = pick ? e1 : e0;
+			const int blk = half * SPLIT_BLENDERS + bw;        // 8x4 block of the tile = bit of the records' block masks
+			const float fx = (float)((blk & 1) * 8 + (lane & 7)), fy = (float)((blk >> 1) * 4 + (lane >> 3));
+			q.col = smem_u32(s_queue) + (uint32_t)(bw * 32 + lane) * 4u;
 			const int s = c % STAGES;
 			const int cnt = min(CHUNK, n - c * CHUNK);
 			uint32_t bm[NW];
@@ -597,8 +624,6 @@ render_fwd_split_kernel(const uint2* __restrict__ ranges, const uint32_t* __rest
 			}
 			mbar_wait(&s_full[s], (uint32_t)((c / STAGES) & 1));
 			uint32_t m[NW];
-#pragma unroll
-			for (int k = 0; k < NW; k++) m[k] = 0;
 			const uint32_t rec = rec_base + (uint32_t)s * (CHUNK * SLAB_BYTES);
 #pragma unroll
 			for (int w = 0; w < NW; w++) {
@@ -633,14 +658,14 @@ render_fwd_split_kernel(const uint2* __restrict__ ranges, const uint32_t* __rest
 				__threadfence_block();
 				sts_volatile_u32(&s_swept[bw], (uint32_t)(c + 1));
 			}
-		}
-		__syncwarp();
-		if (lane == 0) {
-			__threadfence_block();
-			sts_volatile_u32(&s_swept[bw], (uint32_t)nchunks);          // (early exit: the blender only lets go of the stages)
+			if (pick) nx1 = c + 1; else nx0 = c + 1;
 		}
 		return;
 	}
+
+	const int blk = half * SPLIT_BLENDERS + bw;            // 8x4 block of the tile
+	const int lx = (blk & 1) * 8 + (lane & 7), ly = (blk >> 1) * 4 + (lane >> 3);
+	q.col = smem_u32(s_queue) + (uint32_t)(bw * 32 + lane) * 4u;
 
 	// -------------------- blender: pass 2 of render_fwd_kernel over the queued survivor words --------------------
 	const uint32_t px = tile_x * TILE_X + lx;
