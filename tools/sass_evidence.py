@@ -8,7 +8,7 @@ from `cuobjdump -sass` of the built objects.  Writes profiles/<tag>_sass_<kernel
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJ = os.path.join(ROOT, "f3d_gaus_b200", "csrc", "build")
-KERNELS = [("render_fwd.o", "render_fwd_kernelILb0ELb0ELb0E", "render_fwd"), ("render_fwd.o", "render_fwd_kernelILb0ELb1ELb1E", "render_fwd_sink_mask"),
+KERNELS = [("render_fwd.o", "render_fwd_kernelILb0ELb0ELb0E", "render_fwd"), ("render_fwd.o", "render_fwd_split_kernelILb0E", "render_fwd_split"), ("render_fwd.o", "render_fwd_kernelILb0ELb1ELb1E", "render_fwd_sink_mask"),
            ("render_bwd.o", "render_bwd_kernel", "render_bwd"), ("integrate.o", "integrate_pixels_kernel", "integrate"),
            ("binning.o", "tile_sort_gather_kernel", "tile_sort_gather")]
 MARK = re.compile(r"UBLKCP|SYNCS|FENCE|REDG|ATOMG|ATOMS|MEMBAR|VOTE|MUFU|UTMA|LDGSTS|griddep|ACQBULK|CCTL")

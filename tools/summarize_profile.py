@@ -115,10 +115,15 @@ def main():
              f"{tag}: ncu --set full, backward blend of one train256 step (8 views of 65,536 Gaussians, 256x256)",
              os.path.join(prof, "kernel_traffic.json"), "render_bwd", "train256",
              "bench.py train256 step: one launch walks back the 8 views of 65536 f3d-like Gaussians, 256x256")
+    rep = os.path.join(src, "prof_split.ncu-rep")
+    if os.path.exists(rep):
+        full(rep, os.path.join(prof, f"{tag}_split_ncu.md"),
+             f"{tag}: ncu --set full, one-frame launches (65,536 Gaussians, one 256x256 orbit view): render_fwd_split_kernel and the stages in front of it")
     rep = os.path.join(src, "prof_head.ncu-rep")
     if os.path.exists(rep):
         full(rep, os.path.join(prof, f"{tag}_head_ncu.md"), f"{tag}: ncu --set full, predictor output head (64 images of 256x256, 23 channels)")
-    for name in ("bench_ours.json", "bench_reference.json", "quick_bench.log", "head_bench.json", "train_bench.json"):
+    for name in ("bench_ours.json", "bench_reference.json", "quick_bench.log", "head_bench.json", "train_bench.json",
+                 "single_frame.log", "per_view_timeline.log"):
         p = os.path.join(src, name)
         if os.path.exists(p):
             with open(p) as f, open(os.path.join(prof, f"{tag}_{name}"), "w") as g:
