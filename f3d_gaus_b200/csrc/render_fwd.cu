@@ -37,8 +37,9 @@ namespace {
 #define GOF_FWD_STAGES 4          // power of two (ring addressing by list position); a warp reads two chunks and sweeps a third
 #endif
 #ifndef GOF_FWD_MIN_CTAS
-#define GOF_FWD_MIN_CTAS 3
-#endif
+#define GOF_FWD_MIN_CTAS 4        // inference kernels: 64 registers (12 bytes of spills) for four CTAs = 32 warps per SM: 386 -> 366 us per
+#endif                            // 8-view launch, 512^2 batches 7.80 -> 7.21 ms (round 1, with a ninth producer warp: 56 registers, slower).
+                                  // The training instantiations (MASK) keep three: their second queue does not fit four times.
 #ifndef GOF_FWD_CHUNK
 #define GOF_FWD_CHUNK 128
 #endif
@@ -177,7 +178,7 @@ using LaneQueue = LaneQueueT<QUEUE_ROWS, FWD_THREADS>;
 // position, kept for the window's two chunks in shared memory ([chunk parity][word][thread], lane-private columns) and
 // written out as whole 128-record blocks when the warp lets go of a chunk -- contrib[slot][word][thread], coalesced.
 template <bool EXACT, bool SINK, bool MASK>
-__global__ void __launch_bounds__(FWD_THREADS, GOF_FWD_MIN_CTAS)
+__global__ void __launch_bounds__(FWD_THREADS, MASK ? 3 : GOF_FWD_MIN_CTAS)
 render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ tile_order, int T, int tiles_x,
                   const float* __restrict__ slab, int W, int H,
                   float focal_x, float focal_y, const float* __restrict__ bg_colors, int bg_stride,
