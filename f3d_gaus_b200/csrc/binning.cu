@@ -367,7 +367,7 @@ __device__ __forceinline__ void bitonic_sort_regs(uint64_t* s, int n)
 }
 
 #ifndef GOF_SORT_MIN_CTAS
-#define GOF_SORT_MIN_CTAS 3
+#define GOF_SORT_MIN_CTAS 4      // 64 registers (36 bytes of spills): 92.7 -> 90.5 us per 8-view batch
 #endif
 
 // One CTA per tile of the batch: sort the bucket, write point_list and the slab.

@@ -242,8 +242,11 @@ __device__ V3 sh_backward(int deg, int M, const V3 pos, const V3 campos, const f
 // per-frame backward).  Per view: gacc[v], radii[v], clamped[v], viewmatrix[v], campos[v].
 // 128 threads per CTA: the double-precision quadric chain needs ~220 registers per thread, so a 256-thread CTA would
 // be alone on its SM; 128-thread CTAs sit two per SM and spread 65,536 Gaussians over 512 CTAs instead of 256.
+#ifndef GOF_PRE_BWD_MIN_CTAS
+#define GOF_PRE_BWD_MIN_CTAS 2
+#endif
 constexpr int PRE_BWD_THREADS = 128;
-__global__ void __launch_bounds__(PRE_BWD_THREADS)
+__global__ void __launch_bounds__(PRE_BWD_THREADS, GOF_PRE_BWD_MIN_CTAS)
 preprocess_bwd_kernel(int P, int V, int D, int M, const float* __restrict__ means3D, const int* __restrict__ radii_all,
                       const float* __restrict__ shs, const uint8_t* __restrict__ clamped_all,
                       const float* __restrict__ scales, const float* __restrict__ rotations,
