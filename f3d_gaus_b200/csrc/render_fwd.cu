@@ -4,21 +4,21 @@
 // out_color[9,H,W] (rgb, view-space normal, median depth, alpha, normalised distortion),
 // final_T[4,H,W] = (T, dist1, dist2, distortion_raw), n_contrib[2,H,W] = (last, max contributor).
 //
-// B200 design:
-//   * One CTA per 16x16 tile (the tile size is part of the binning contract): 8 consumer warps,
-//     each owning an 8x4 pixel block, plus one producer warp.
-//   * The tile's sorted Gaussians arrive as a contiguous slab of 80-byte records (binning.cu).
-//     The producer streams it into a 4-stage shared-memory ring with TMA bulk copies
-//     (cp.async.bulk, completion on a "full" mbarrier per stage); each consumer warp releases a
-//     stage by arriving on its "empty" mbarrier.  There is no CTA-wide barrier in the loop: warps
-//     drift up to three chunks apart, so a warp that has many contributors in one chunk does not
-//     stall the other seven (the reference, and our first version, synchronise every batch).
-//   * Per 128-record chunk, two passes.  Pass 1 is a branch-free sweep: every pixel evaluates the
-//     tile-local CONIC pre-test (conic.cuh: a quadratic in the pixel's tile coordinates, five FMAs,
-//     coefficients broadcast from shared memory) for the 128 records and keeps the survivors as a
-//     128-bit mask.  Pass 2 is lane-private: each pixel walks ITS OWN survivors in list order
-//     (float32 quadric, the tight float32 pre-test, exact FP64 ray minimum, expf, blend).  A warp
-//     spends pass-2 iterations equal to its busiest pixel's survivor count over the whole chunk
+// B200 design (render_fwd_kernel, the throughput kernel of batched launches; one-frame launches take
+// render_fwd_split_kernel further down):
+//   * One CTA per 16x16 tile (the tile size is part of the binning contract): 8 warps, each owning an 8x4 pixel
+//     block.  64 registers per thread, four CTAs = 32 warps per SM.
+//   * The tile's sorted Gaussians arrive as a contiguous slab of 80-byte records (binning.cu), streamed into a 4-stage
+//     shared-memory ring with TMA bulk copies (cp.async.bulk, completion on a "full" mbarrier per stage).  There is
+//     no producer warp: the warp that is the last to let go of a stage requests the chunk that reuses it.  No
+//     CTA-wide barrier in the loop: warps drift up to three chunks apart, so a warp that has many contributors in one
+//     chunk does not stall the other seven (the reference, and our first version, synchronise every batch).
+//   * Per 128-record chunk, two passes.  Pass 1 is the sweep: every pixel evaluates the tile-local CONIC pre-test
+//     (conic.cuh: a quadratic in the pixel's tile coordinates, five FMAs, coefficients broadcast from shared memory)
+//     for the chunk's records whose block mask reaches this warp's 8x4 block, and keeps the survivors as a 128-bit
+//     mask.  Pass 2 is lane-private: each pixel walks ITS OWN survivors in list order (float32 quadric, exact FP64 ray
+//     minimum, expf, blend), two per trip, from a queue that spans two chunks so that the lanes of a warp are not
+//     synchronised at chunk boundaries.  A warp spends pass-2 iterations equal to its busiest pixel's survivor count
 //     (~11% of the list) instead of running the expensive path for every record any pixel touches.
 //   * Rounding: alpha, T, rgb, median depth, alpha channel and the contributor counters follow
 //     the reference's sm_100a build operation by operation and are bit-identical to it in both
