@@ -502,7 +502,9 @@ render_fwd_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__
 //   * per 8x4 block TWO warps: a SWEEPER that runs the conic pre-test up to four chunks ahead and leaves the
 //     per-pixel survivor words in the shared-memory queue, and a BLENDER that only walks survivors (pass 2 of the
 //     kernel above, same code, same order, same roundings).  The sweep (~1/3 of the longest warp's path) leaves the
-//     critical path; the two meet through two monotonic counters in shared memory (chunks swept / chunks consumed).
+//     critical path; the two meet through two monotonic counters in shared memory (chunks swept / chunks consumed):
+//     writer = data stores, __syncwarp, fence, volatile counter store; reader = volatile counter load, fence, data
+//     loads (compute-sanitizer's racecheck only models barriers and reports these hand-offs as hazards; memcheck is clean).
 // Results are bit-identical to render_fwd_kernel (tests/test_gpu_batch.py compares one-frame calls with batched ones).
 constexpr int SPLIT_BLENDERS = 4;                       // 8x4 blocks per half tile, one blender warp each
 #ifndef GOF_SPLIT_SWEEPERS
@@ -610,6 +612,7 @@ render_fwd_split_kernel(const uint2* __restrict__ ranges, const uint32_t* __rest
 			const int e0 = eligible(0, nx0), e1 = eligible(1, nx1);
 			if (e0 < 0 && e1 < 0) { __nanosleep(20); continue; }
 			const int pick = (e0 >= 0 && (e1 < 0 || e0 <= e1)) ? 0 : 1;
+			__threadfence_block();                         // acquire side of the blender's `consumed` release: its reads of the rows come first
 			bw = b0 + pick;
 			const int c = pick ? e1 : e0;
 			const int blk = half * SPLIT_BLENDERS + bw;        // 8x4 block of the tile = bit of the records' block masks
