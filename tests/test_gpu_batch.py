@@ -365,3 +365,33 @@ def test_scene_streamer_pipeline(zero_copy):
     for k, ((f, R), (wf, wR)) in enumerate(zip(got, want)):
         assert R == wR, k
         assert torch.equal(f, wf), k
+
+
+def test_cycle_loop_deferred_overflow_check():
+    """cycle_aggregate(check_overflow=False) never synchronises; an undersized workspace then shows in the caller's
+    workspace.finish() (None), the merged set derived from the NaN-poisoned frames is discarded, and the re-run on the
+    grown workspace equals the checked loop bit for bit."""
+    from f3d_gaus_b200 import cameras, cycle, synthetic
+    from f3d_gaus_b200.diff_gof_rasterization import BatchWorkspace
+    dev = "cuda"
+    res = 128
+    cfg = synthetic.cfg_for(res)
+    pc = {k: v.to(dev) for k, v in synthetic.f3d_like(1, 64).items()}
+    orbit = cameras.orbit_cameras(8)
+    cams = cameras.Cameras(*[t[[1, 6]].to(dev) for t in orbit])
+    bg = torch.zeros(3, device=dev)
+    predict = cycle.unproject_predictor(cfg)
+    want, want_frames = cycle.cycle_aggregate(pc, predict, cams, cfg, bg, workspace=BatchWorkspace("cuda:0"))
+
+    ws = BatchWorkspace("cuda:0")
+    ws.capacity_hint = 256                              # far too small for two 128^2 frames of 4096 Gaussians
+    got, frames = cycle.cycle_aggregate(pc, predict, cams, cfg, bg, workspace=ws, check_overflow=False)
+    torch.cuda.synchronize()
+    assert ws.finish() is None                          # the caller's check: this step has to be computed again
+    assert torch.isnan(frames["rgb"]).any()
+    got, frames = cycle.cycle_aggregate(pc, predict, cams, cfg, bg, workspace=ws, check_overflow=False)
+    torch.cuda.synchronize()
+    assert ws.finish() is not None
+    for k in want:
+        assert torch.equal(got[k], want[k]), k
+    assert torch.equal(frames["depth"], want_frames["depth"])

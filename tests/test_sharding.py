@@ -107,3 +107,20 @@ def test_cycle_aggregate_bookkeeping():
     back = torch.cat([blk, torch.ones(B, res * res, 1)], dim=-1) @ cams.world_view[k]
     assert torch.allclose(back[..., 2], frames["depth"][:, k].reshape(B, -1), atol=1e-4)
     assert torch.allclose(merged["rotation"].norm(dim=-1), torch.ones(B, merged["rotation"].shape[1]), atol=1e-5)
+
+
+def test_view_quaternions_cached_per_camera_tensor():
+    """cycle.view_quaternions reads the matrices back once per camera set; an in-place change of the tensor (its
+    version counter) or another tensor gives a fresh result."""
+    from f3d_gaus_b200 import cameras, cycle
+    cams = cameras.orbit_cameras(4)
+    v2w = cams.view_to_world.clone()
+    q1 = cycle.view_quaternions(v2w)
+    assert cycle.view_quaternions(v2w) is q1            # cached: same object back
+    want = torch.stack([cameras.matrix_to_quaternion(m[:3, :3].T.contiguous()) for m in v2w])
+    assert torch.allclose(q1, want, atol=1e-6)
+    v2w[0].copy_(v2w[2])                                # in-place edit bumps the version counter
+    q2 = cycle.view_quaternions(v2w)
+    assert q2 is not q1 and torch.allclose(q2[0], want[2], atol=1e-6)
+    other = cams.view_to_world.clone()
+    assert torch.allclose(cycle.view_quaternions(other), want, atol=1e-6)
