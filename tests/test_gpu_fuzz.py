@@ -5,6 +5,7 @@ opacities below the 1/255 cut and at 1, SH degrees 0-3 and precomputed colours, 
 This is the test of the conic pre-test's soundness proof (csrc/conic.cuh): any wrongly skipped pair shows up as
 a contributor-count or image mismatch."""
 import math
+import os
 
 import pytest
 import torch
@@ -67,7 +68,7 @@ def random_case(seed: int, device="cuda") -> dict:
 
 @needs_ref
 @pytest.mark.parametrize("exact", [False, True], ids=["fast_blend", "exact_blend"])
-@pytest.mark.parametrize("seed", list(range(24)))
+@pytest.mark.parametrize("seed", list(range(int(os.environ.get("GOF_FUZZ_SEEDS", "24")))))      # GOF_FUZZ_SEEDS=300 for a long soak
 def test_random_case_matches_reference(seed, exact, monkeypatch):
     monkeypatch.setenv("GOF_EXACT_BLEND", "1" if exact else "0")
     c = random_case(seed)
