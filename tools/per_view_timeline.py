@@ -60,5 +60,3 @@ def t_host(fn, n=2000):
 print("torch.empty(9,H,W): %.1f us" % t_host(lambda: torch.empty((9, res, res), dtype=torch.float32, device=dev)))
 print("torch.empty(bytes): %.1f us" % t_host(lambda: torch.empty(20_000_000, dtype=torch.uint8, device=dev)))
 print("zeros_like(xyz)   : %.1f us" % t_host(lambda: torch.zeros_like(pc["xyz"][0])))
-e = torch.Tensor([])
-c = dict(bg=bg, means3D=pc["xyz"][0].contiguous())
